@@ -1,0 +1,138 @@
+/*
+ * apus_layout.h -- HBM layout of one replica and the structures shared between
+ * the host engine (apus_engine.cu) and the kernels (apus_kernels.cu).
+ *
+ * One cudaMalloc'd REGION per replica (one IPC handle maps all of it in a peer):
+ *
+ *   +0        apus_ctrl_t   4 KiB   words written by REMOTE peers and kernel state
+ *   +4096     apus_loghdr_t         mirror of dare_log_t up to entries[]
+ *                                   (dare_log.h:77-103: head 0, apply 8, commit 16,
+ *                                   end 24, tail 32, old_end 40, old_commit 48, len 56,
+ *                                   nc_buf 64 .. 319656), padded to 320 KiB
+ *   +APUS_ENTRIES_OFF  entries[log_len]   the reference's circular byte log
+ *
+ * entries[] starts 4 KiB-aligned so that a log offset and its address agree
+ * modulo 16 (vectorised 16 B peer stores need that).
+ *
+ * Who writes what (all cross-GPU traffic is stores; nothing on the hot path reads
+ * over NVLink):
+ *   leader  -> follower.entries[range]       entry bytes           (replaces RDMA WRITE dare_ibv_rc.c:1606)
+ *   leader  -> follower.hdr.end              tail publish, 8 B     (dare_ibv_rc.c:1549-1573)
+ *   leader  -> follower.hdr.commit           commit publish, 8 B   (dare_ibv_rc.c:1810)
+ *   follower-> leader.entries[e+28+idx]      reply byte, 1 B       (dare_ibv_rc.c:1833-1854)
+ *   follower-> leader.ctrl.ack[idx]          ack word, 8 B         (the word the quorum ballot polls)
+ *   follower-> leader.ctrl.apply_off[idx]    apply offset, 8 B     (push form of rc_get_remote_apply_offsets :1970)
+ */
+#ifndef APUS_LAYOUT_H
+#define APUS_LAYOUT_H
+
+#include <stdint.h>
+
+#define APUS_MAX_SERVERS      13
+#define APUS_HDR_BYTES        64u
+#define APUS_CTRL_BYTES       4096u
+#define APUS_LOGHDR_REF_BYTES 319656u                 /* offsetof(dare_log_t, entries) */
+#define APUS_LOGHDR_BYTES     (320u * 1024u)
+#define APUS_ENTRIES_OFF      (APUS_CTRL_BYTES + APUS_LOGHDR_BYTES)
+
+/* entry field offsets (dare_log.h:33-48) */
+#define E_IDX     0
+#define E_TERM    8
+#define E_REQID  16
+#define E_CLTID  24
+#define E_TYPE   26
+#define E_SENDER 27
+#define E_REPLY  28
+#define E_DATA   48
+#define E_CMD    50
+
+#define T_NOOP   0
+#define T_CONFIG 2
+#define T_HEAD   3
+
+/* dare_log_t header mirror (first 64 bytes; nc_buf follows, unused on the hot path) */
+typedef struct apus_loghdr {
+    uint64_t head, apply, commit, end, tail, old_end, old_commit, len;
+} apus_loghdr_t;
+
+#define APUS_PUB_RING 1024u     /* leader: publishes in flight (power of two) */
+#define APUS_LAT_RING 65536u    /* device-side latency samples (power of two) */
+
+/* ctrl block: remote-written words first, each group on its own 128 B line */
+typedef struct apus_ctrl {
+    /* --- written by remote followers into the LEADER's region --- */
+    uint64_t ack[16];            /* [i] = entries follower i has acked (monotone count) */
+    uint64_t apply_off[16];      /* [i] = follower i's apply offset */
+    /* --- kernel-owned state that survives between launches --- */
+    uint64_t next_idx;           /* leader: idx of the next entry (last.idx + 1) */
+    uint64_t consumed;           /* leader: tickets taken from the submission ring */
+    uint64_t published;          /* leader: entries whose tail has been published */
+    uint64_t committed;          /* leader: entries committed */
+    uint64_t committed_tickets;  /* leader: tickets committed */
+    uint64_t hwm;                /* leader: high-water mark of bytes ever written (fresh beyond) */
+    uint64_t bytes_replicated;
+    uint64_t batches;
+    uint64_t acked;              /* follower: entries acked */
+    uint64_t lat_count;          /* leader: latency samples written */
+    uint64_t pad0[6];
+} apus_ctrl_t;
+
+/* submission descriptor, 16 B: the fields of tailq_entry_t (message.h:11-17) */
+typedef struct apus_desc {
+    uint64_t req_id;
+    uint32_t type_off;           /* type << 24 | payload offset in 16 B units */
+    uint16_t len;                /* cmd length (CSM-like) */
+    uint16_t clt_id;             /* connection_id */
+} apus_desc_t;
+
+/* words in pinned, mapped host memory shared with the kernels */
+typedef struct apus_hostwords {
+    volatile uint64_t sub_tail;          /* host -> kernel doorbell (RING_HOST_MAPPED) */
+    uint64_t pad0[15];
+    volatile uint64_t committed_tickets; /* kernel -> host */
+    volatile uint64_t consumed;          /* kernel -> host (ring space) */
+    volatile uint64_t commit_off;
+    uint64_t pad1[13];
+    volatile uint32_t stop;              /* host -> kernel */
+    uint32_t pad2[31];
+    volatile uint64_t heartbeat;         /* kernel liveness (debug) */
+    volatile uint64_t error;             /* kernel-detected protocol error code */
+} apus_hostwords_t;
+
+#define APUS_ROLE_NONE     0
+#define APUS_ROLE_LEADER   1
+#define APUS_ROLE_FOLLOWER 2
+
+/* everything a kernel role needs; lives in device memory, written by the host
+ * before each launch */
+typedef struct apus_devctx {
+    uint8_t  idx, group_size, leader_idx, quorum;
+    uint32_t flags;
+    uint64_t term;
+    uint64_t log_len;
+    uint64_t target;                      /* cumulative ticket / entry target of this launch */
+    uint8_t *region;                      /* own region */
+    uint8_t *peer[APUS_MAX_SERVERS];      /* peers' regions as mapped here (NULL = absent) */
+    /* leader submission ring */
+    const apus_desc_t *sub_desc;
+    const uint8_t     *sub_pay;
+    uint32_t           sub_mask;          /* slots - 1 */
+    uint32_t           pad;
+    const volatile uint64_t *sub_tail;    /* doorbell word (host-mapped or device) */
+    apus_hostwords_t  *hw;                /* host-mapped words */
+    uint32_t          *lat_ns;            /* device latency ring (APUS_LAT_RING) or NULL */
+} apus_devctx_t;
+
+typedef struct apus_role {
+    uint32_t       kind;
+    uint32_t       pad;
+    apus_devctx_t *ctx;
+} apus_role_t;
+
+#define APUS_LEADER_THREADS   512
+#define APUS_FOLLOWER_THREADS 512
+#define APUS_MAX_TILE_ENTRIES 512u
+#define APUS_IMG_BYTES        (96u * 1024u)
+#define APUS_KERNEL_THREADS   512
+
+#endif /* APUS_LAYOUT_H */

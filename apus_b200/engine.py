@@ -1,0 +1,320 @@
+"""ctypes binding of include/apus_gpu.h (the C ABI is the product boundary).
+
+`Group` mirrors how the reference deploys a Paxos group: `group_size` replicas,
+`server_idx` 0..n-1 (env vars of benchmarks/run.sh:26), one of them the leader.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libapus_gpu.so")
+
+APUS_OK, APUS_ERROR, APUS_RETRY = 0, 1, -1
+NOOP, CSM, CONFIG, HEAD, CONNECT, SEND, CLOSE = 0, 1, 2, 3, 4, 5, 6
+RING_HOST_MAPPED, RING_DEVICE = 0, 1
+LOG_SIZE = 16384 * 4096
+MAX_SERVERS = 13
+F_FENCED_ACK, F_DEVICE_STATS, F_EXPLICIT = 0x1, 0x2, 0x80000000
+UINT64_MAX = (1 << 64) - 1
+
+u64, u32, u16, u8, i64, i32 = C.c_uint64, C.c_uint32, C.c_uint16, C.c_uint8, C.c_int64, C.c_int32
+
+
+class ApusError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("struct_size", u32), ("device", i32), ("server_idx", u8), ("group_size", u8),
+                ("leader_idx", u8), ("ring_mode", u8), ("flags", u32), ("term", u64),
+                ("log_size", u64), ("ring_slots", u32), ("ring_bytes", u32)]
+
+
+class PeerHandle(C.Structure):
+    _fields_ = [("bytes", u8 * 128)]
+
+
+class LogOffsets(C.Structure):
+    _fields_ = [(k, u64) for k in ("head", "apply", "commit", "end", "tail", "old_end", "old_commit", "len")]
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, u64) for k in ("tickets_submitted", "tickets_consumed", "tickets_committed",
+                                   "entries_acked", "bytes_replicated", "batches", "kernel_launches",
+                                   "lat_samples")]
+
+
+_lib = None
+
+EXPORTS = [
+    "apus_abi_version", "apus_last_error", "apus_device_count", "apus_replica_create",
+    "apus_replica_destroy", "apus_replica_export", "apus_replica_connect", "apus_replicas_launch",
+    "apus_replica_wait", "apus_replica_last_launch_ms", "apus_replicas_stop", "apus_submit",
+    "apus_submit_batch", "apus_submit_defer", "apus_submit_flush", "apus_committed_tickets",
+    "apus_wait_committed", "apus_log_offsets", "apus_log_read", "apus_get_stats",
+    "apus_latency_samples", "apus_set_head", "apus_remote_apply_offsets",
+]
+
+
+def load_library(path=LIB_PATH):
+    """Load libapus_gpu.so; raises (no fallback) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise ApusError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(make -C apus_b200/csrc). There is no CPU fallback.")
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.apus_abi_version.restype = C.c_int
+    L.apus_last_error.restype = C.c_char_p
+    L.apus_device_count.restype = C.c_int
+    L.apus_replica_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.apus_replica_destroy.argtypes = [vp]
+    L.apus_replica_destroy.restype = None
+    L.apus_replica_export.argtypes = [vp, C.POINTER(PeerHandle)]
+    L.apus_replica_connect.argtypes = [vp, u8, C.POINTER(PeerHandle)]
+    L.apus_replicas_launch.argtypes = [C.POINTER(vp), C.c_int, u64]
+    L.apus_replica_wait.argtypes = [vp, i64]
+    L.apus_replica_last_launch_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.apus_replicas_stop.argtypes = [C.POINTER(vp), C.c_int]
+    L.apus_submit.argtypes = [vp, u8, u16, u64, vp, u16, C.POINTER(u64)]
+    L.apus_submit_batch.argtypes = [vp, u32, vp, vp, vp, vp, vp, C.c_size_t, C.POINTER(u64)]
+    L.apus_submit_defer.argtypes = [vp, C.c_int]
+    L.apus_submit_flush.argtypes = [vp]
+    L.apus_committed_tickets.argtypes = [vp]
+    L.apus_committed_tickets.restype = u64
+    L.apus_wait_committed.argtypes = [vp, u64, i64]
+    L.apus_log_offsets.argtypes = [vp, C.POINTER(LogOffsets)]
+    L.apus_log_read.argtypes = [vp, u64, u64, vp]
+    L.apus_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.apus_latency_samples.argtypes = [vp, vp, u32, C.POINTER(u32)]
+    L.apus_set_head.argtypes = [vp, u64]
+    L.apus_remote_apply_offsets.argtypes = [vp, C.POINTER(u64)]
+    _lib = L
+    return L
+
+
+def lib():
+    return load_library()
+
+
+def _ck(rc, what):
+    if rc == APUS_OK:
+        return
+    msg = lib().apus_last_error().decode(errors="replace")
+    if rc == APUS_RETRY:
+        raise BlockingIOError(f"{what}: {msg}")
+    raise ApusError(f"{what}: {msg}")
+
+
+class Replica:
+    def __init__(self, device, server_idx, group_size, leader_idx=0, term=1, log_size=0,
+                 ring_mode=RING_HOST_MAPPED, ring_slots=0, ring_bytes=0, flags=None):
+        cfg = Config()
+        cfg.struct_size = C.sizeof(Config)
+        cfg.device, cfg.server_idx, cfg.group_size, cfg.leader_idx = device, server_idx, group_size, leader_idx
+        cfg.ring_mode, cfg.term, cfg.log_size = ring_mode, term, log_size
+        cfg.ring_slots, cfg.ring_bytes = ring_slots, ring_bytes
+        cfg.flags = 0 if flags is None else (flags | F_EXPLICIT)
+        self.h = C.c_void_p()
+        _ck(lib().apus_replica_create(C.byref(cfg), C.byref(self.h)), "apus_replica_create")
+        self.cfg = cfg
+        self.device, self.idx, self.n, self.leader = device, server_idx, group_size, leader_idx
+        self.log_len = log_size or LOG_SIZE
+
+    @property
+    def is_leader(self):
+        return self.idx == self.leader
+
+    def close(self):
+        if self.h:
+            lib().apus_replica_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def export(self) -> bytes:
+        ph = PeerHandle()
+        _ck(lib().apus_replica_export(self.h, C.byref(ph)), "apus_replica_export")
+        return bytes(ph.bytes)
+
+    def connect(self, peer_idx, blob: bytes):
+        ph = PeerHandle()
+        C.memmove(ph.bytes, blob, 128)
+        _ck(lib().apus_replica_connect(self.h, peer_idx, C.byref(ph)), "apus_replica_connect")
+
+    def wait(self, timeout_ms=-1):
+        _ck(lib().apus_replica_wait(self.h, timeout_ms), "apus_replica_wait")
+
+    def last_launch_ms(self):
+        ms = C.c_float()
+        _ck(lib().apus_replica_last_launch_ms(self.h, C.byref(ms)), "apus_replica_last_launch_ms")
+        return float(ms.value)
+
+    def submit(self, typ, conn, req_id, payload=b""):
+        t = u64()
+        buf = (u8 * max(len(payload), 1)).from_buffer_copy(bytes(payload) or b"\0")
+        _ck(lib().apus_submit(self.h, typ, conn, req_id, C.cast(buf, C.c_void_p), len(payload), C.byref(t)),
+            "apus_submit")
+        return int(t.value)
+
+    def submit_batch(self, types, conns, req_ids, lens, payloads, stride):
+        """numpy arrays: types u8[n], conns u16[n], req_ids u64[n], lens u16[n], payloads u8[n*stride]."""
+        n = len(types)
+        types = np.ascontiguousarray(types, dtype=np.uint8)
+        conns = np.ascontiguousarray(conns, dtype=np.uint16)
+        req_ids = np.ascontiguousarray(req_ids, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint16)
+        pp = None
+        if payloads is not None:
+            payloads = np.ascontiguousarray(payloads, dtype=np.uint8)
+            pp = payloads.ctypes.data
+        t = u64()
+        _ck(lib().apus_submit_batch(self.h, n, types.ctypes.data, conns.ctypes.data, req_ids.ctypes.data,
+                                    lens.ctypes.data, pp, stride, C.byref(t)), "apus_submit_batch")
+        return int(t.value)
+
+    def defer(self, on=True):
+        _ck(lib().apus_submit_defer(self.h, 1 if on else 0), "apus_submit_defer")
+
+    def flush(self):
+        _ck(lib().apus_submit_flush(self.h), "apus_submit_flush")
+
+    def committed(self):
+        return int(lib().apus_committed_tickets(self.h))
+
+    def wait_committed(self, ticket, timeout_us=10_000_000):
+        _ck(lib().apus_wait_committed(self.h, ticket, timeout_us), "apus_wait_committed")
+
+    def offsets(self):
+        o = LogOffsets()
+        _ck(lib().apus_log_offsets(self.h, C.byref(o)), "apus_log_offsets")
+        return {k: int(getattr(o, k)) for k, _ in LogOffsets._fields_}
+
+    def image(self, start=0, stop=None):
+        stop = self.log_len if stop is None else stop
+        out = np.empty(stop - start, dtype=np.uint8)
+        if stop > start:
+            _ck(lib().apus_log_read(self.h, start, stop - start, out.ctypes.data), "apus_log_read")
+        return out
+
+    def stats(self):
+        s = Stats()
+        _ck(lib().apus_get_stats(self.h, C.byref(s)), "apus_get_stats")
+        return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+    def latency_ns(self, max_samples=65536):
+        out = np.empty(max_samples, dtype=np.uint32)
+        n = u32()
+        _ck(lib().apus_latency_samples(self.h, out.ctypes.data, max_samples, C.byref(n)), "apus_latency_samples")
+        return out[: n.value].copy()
+
+    def set_head(self, head):
+        _ck(lib().apus_set_head(self.h, head), "apus_set_head")
+
+    def remote_apply_offsets(self):
+        arr = (u64 * MAX_SERVERS)()
+        _ck(lib().apus_remote_apply_offsets(self.h, arr), "apus_remote_apply_offsets")
+        return [int(x) for x in arr]
+
+
+def cid_image(n: int) -> bytes:
+    """dare_cid_t of a fresh stable group (dare_server.c:285-291)."""
+    return (0).to_bytes(8, "little") + bytes([n, 0, 0, 0]) + ((1 << n) - 1).to_bytes(4, "little")
+
+
+class Group:
+    """All replicas of one Paxos group inside this process (tests, 1..8 GPUs)."""
+
+    def __init__(self, n, devices=None, leader=0, term=1, log_size=0, ring_mode=RING_HOST_MAPPED,
+                 ring_slots=0, ring_bytes=0, flags=None):
+        ndev = lib().apus_device_count()
+        if ndev <= 0:
+            raise ApusError("no CUDA device visible: the engine has no CPU fallback")
+        if devices is None:
+            devices = [i % ndev for i in range(n)]
+        self.n, self.leader_idx, self.devices = n, leader, list(devices)
+        self.replicas = [Replica(devices[i], i, n, leader, term, log_size, ring_mode, ring_slots, ring_bytes, flags)
+                         for i in range(n)]
+        blobs = [r.export() for r in self.replicas]
+        for r in self.replicas:
+            for j, b in enumerate(blobs):
+                if j != r.idx:
+                    r.connect(j, b)
+        self.tickets = 0
+
+    @property
+    def leader(self) -> Replica:
+        return self.replicas[self.leader_idx]
+
+    def close(self):
+        for r in self.replicas:
+            r.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        try:
+            self.stop()
+        except Exception:
+            pass
+        self.close()
+
+    def launch(self, target=None):
+        """One fused launch per device; `target` = cumulative tickets (None -> all submitted)."""
+        target = self.tickets if target is None else target
+        by_dev = {}
+        for r in self.replicas:
+            by_dev.setdefault(r.device, []).append(r)
+        # followers first, so a leader never waits for a CTA that is not scheduled yet
+        for dev, rs in sorted(by_dev.items(), key=lambda kv: any(r.is_leader for r in kv[1])):
+            arr = (C.c_void_p * len(rs))(*[r.h for r in rs])
+            _ck(lib().apus_replicas_launch(arr, len(rs), target), "apus_replicas_launch")
+
+    def wait(self, timeout_ms=60_000):
+        for r in self.replicas:
+            r.wait(timeout_ms)
+
+    def stop(self):
+        arr = (C.c_void_p * self.n)(*[r.h for r in self.replicas])
+        _ck(lib().apus_replicas_stop(arr, self.n), "apus_replicas_stop")
+
+    def prologue(self):
+        """Blank CONFIG entry the election winner appends (dare_server.c:1412-1421);
+        none when the group has a single member (dare_server.c:416-424)."""
+        if self.n == 1:
+            return 0
+        self.tickets = self.leader.submit(CONFIG, 0, 0, cid_image(self.n))
+        return self.tickets
+
+    def submit(self, typ, conn, req_id, payload=b""):
+        self.tickets = self.leader.submit(typ, conn, req_id, payload)
+        return self.tickets
+
+    def submit_stream(self, stream):
+        """stream: iterable of (type, connection_id, req_id, payload) -- tailq_entry_t fields."""
+        self.leader.defer(True)
+        try:
+            for typ, conn, rid, payload in stream:
+                self.tickets = self.leader.submit(typ, conn, rid, payload)
+        finally:
+            self.leader.flush()
+            self.leader.defer(False)
+        return self.tickets
+
+    def submit_uniform(self, n_req, length, conn, first_req_id, payloads=None, typ=SEND):
+        """n_req requests of `length` bytes on one connection (batch ABI call)."""
+        types = np.full(n_req, typ, dtype=np.uint8)
+        conns = np.full(n_req, conn, dtype=np.uint16)
+        req_ids = np.arange(first_req_id, first_req_id + n_req, dtype=np.uint64)
+        lens = np.full(n_req, length, dtype=np.uint16)
+        t0 = self.leader.submit_batch(types, conns, req_ids, lens, payloads, length)
+        self.tickets = t0 + n_req - 1
+        return self.tickets
+
+    def run(self, timeout_ms=60_000):
+        """Launch for everything submitted so far and wait until it is committed everywhere."""
+        self.launch()
+        self.wait(timeout_ms)

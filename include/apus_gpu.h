@@ -1,0 +1,174 @@
+/*
+ * apus_gpu.h -- C ABI of the B200-native Paxos log-replication engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of hku-systems/apus that this
+ * repository accelerates: leader append -> replicate to every
+ * follower -> majority ack -> commit.  It replaces the "lower" callee set the
+ * reference's consensus thread calls into,
+ *     src/include/dare/dare_ibv.h:141-201  (dare_ib_poll_tailq,
+ *     dare_ib_write_remote_logs, dare_ib_send_entries_reply, ...) implemented by
+ *     src/dare/dare_ibv_rc.c (RC queue pairs, RDMA WRITE/READ) and
+ *     src/dare/dare_ibv_ud.c:780-790 (get_tailq_message),
+ * together with the log placement of src/include/dare/dare_log.h.
+ * Plain C types only: pointers, sizes, integers.  No CUDA or torch types.
+ *
+ * Each replica of a Paxos group is one `apus_replica_t`, bound to one GPU; its
+ * consensus log (reference layout, byte for byte) and its ack / tail / commit
+ * words live in that GPU's HBM.  The leader's hot loop and the followers' ack
+ * loops are persistent sm_100a kernels (apus_b200/csrc/apus_kernels.cu); peers
+ * are reached with P2P stores over NVLink (same process: peer access; one
+ * process per replica: CUDA IPC handles exchanged with apus_replica_export /
+ * apus_replica_connect -- the analogue of the raddr/rkey exchange in RC_SYN,
+ * src/dare/dare_ibv_ud.c:1116-1119).
+ *
+ * The reference-facing "engine entry" symbols that src/proxy/proxy.c links
+ * against (dare_server_init, is_leader, get_node_id, the tailhead queue) are
+ * declared in apus_dare_entry.h and implemented on top of this ABI.
+ *
+ * Error convention follows the reference transport (dare_ibv_rc.c:27-29):
+ * 0 = success, 1 = error, -1 = "retry later"; apus_last_error() gives the text.
+ * There is NO CPU fallback: every entry point fails with 1 when no CUDA device
+ * is usable.
+ */
+#ifndef APUS_GPU_H
+#define APUS_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APUS_ABI_VERSION 1
+
+#define APUS_OK       0
+#define APUS_ERROR    1
+#define APUS_RETRY  (-1)
+
+#define APUS_MAX_SERVER_COUNT 13            /* dare.h:26 */
+#define APUS_LOG_SIZE (16384ull * 4096ull)  /* dare_log.h:76 LOG_SIZE */
+#define APUS_ENTRY_HDR 64u                  /* sizeof(dare_log_entry_t) */
+
+/* entry types: dare_log.h:21-24 and proxy.h:9-11 */
+#define APUS_NOOP    0
+#define APUS_CSM     1
+#define APUS_CONFIG  2
+#define APUS_HEAD    3
+#define APUS_CONNECT 4
+#define APUS_SEND    5
+#define APUS_CLOSE   6
+
+/* where the leader's submission ring lives */
+#define APUS_RING_HOST_MAPPED 0   /* pinned host memory, read by the kernel over PCIe */
+#define APUS_RING_DEVICE      1   /* HBM; the host fills it with cudaMemcpyAsync batches */
+
+/* apus_config_t.flags */
+#define APUS_F_FENCED_ACK   0x1u  /* follower: reply bytes visible before the ack word (default on) */
+#define APUS_F_DEVICE_STATS 0x2u  /* leader: record per-batch device-side commit latency */
+
+typedef struct apus_replica apus_replica_t;
+
+typedef struct apus_config {
+    uint32_t struct_size;      /* sizeof(apus_config_t), for ABI growth */
+    int32_t  device;           /* CUDA device ordinal hosting this replica */
+    uint8_t  server_idx;       /* env server_idx (proxy.c:33-36) */
+    uint8_t  group_size;       /* env group_size (proxy.c:37-40); 1..13 */
+    uint8_t  leader_idx;       /* who leads in `term` (static until the control plane lands) */
+    uint8_t  ring_mode;        /* APUS_RING_* (leader only) */
+    uint32_t flags;            /* APUS_F_* */
+    uint64_t term;             /* SID term stamped into entries (dare_server.h:53-61) */
+    uint64_t log_size;         /* bytes of entries[]; 0 -> APUS_LOG_SIZE (reference) */
+    uint32_t ring_slots;       /* submission descriptors, power of two; 0 -> default */
+    uint32_t ring_bytes;       /* payload ring bytes, multiple of 4096; 0 -> default */
+} apus_config_t;
+
+/* Opaque blob a replica publishes so that peers can map its HBM region.
+ * Same process: carries the pointer; other process: a cudaIpcMemHandle_t. */
+typedef struct apus_peer_handle {
+    uint8_t bytes[128];
+} apus_peer_handle_t;
+
+/* the offsets of dare_log_t (dare_log.h:77-103) as this replica holds them */
+typedef struct apus_log_offsets {
+    uint64_t head, apply, commit, end, tail, old_end, old_commit, len;
+} apus_log_offsets_t;
+
+typedef struct apus_stats {
+    uint64_t tickets_submitted;   /* requests accepted by apus_submit* */
+    uint64_t tickets_consumed;    /* appended to the leader log by the kernel */
+    uint64_t tickets_committed;   /* committed (majority acked), in log order */
+    uint64_t entries_acked;       /* follower: entries acked to the leader */
+    uint64_t bytes_replicated;    /* leader: sum over followers of entry bytes stored */
+    uint64_t batches;             /* leader: replicate steps (tail publishes) */
+    uint64_t kernel_launches;     /* launches of apus kernels that included this replica */
+    uint64_t lat_samples;         /* device-side latency samples available */
+} apus_stats_t;
+
+/* ---- library ------------------------------------------------------------------- */
+int         apus_abi_version(void);
+const char *apus_last_error(void);
+int         apus_device_count(void);
+
+/* ---- replica life cycle --------------------------------------------------------- */
+/* Allocates the HBM region (log header + entries + ctrl words), zeroed like
+ * log_new() (dare_log.h:120-137: end = tail = old_end = len). */
+int  apus_replica_create(const apus_config_t *cfg, apus_replica_t **out);
+void apus_replica_destroy(apus_replica_t *r);
+
+/* replaces the RC_SYN/SYNACK exchange of raddr+rkey (dare_ibv_ud.c:1116-1119) */
+int  apus_replica_export(apus_replica_t *r, apus_peer_handle_t *out);
+int  apus_replica_connect(apus_replica_t *r, uint8_t peer_idx, const apus_peer_handle_t *peer);
+
+/* Launch the persistent kernel(s) for `n` replicas that live on the SAME device
+ * in ONE fused launch (one CTA group per replica role).  The kernels return when
+ * the cumulative ticket target is reached -- leader: that many requests committed;
+ * follower: that many entries acked and applied -- or when apus_replicas_stop()
+ * is called.  target_tickets == UINT64_MAX runs until stopped (service mode).
+ * Asynchronous: returns after the launch. */
+int  apus_replicas_launch(apus_replica_t **rs, int n, uint64_t target_tickets);
+/* Wait for the launch that included `r` to finish; timeout_ms < 0 waits forever.
+ * APUS_RETRY on timeout. */
+int  apus_replica_wait(apus_replica_t *r, int64_t timeout_ms);
+/* device time of the last finished launch that included r, in milliseconds (CUDA events) */
+int  apus_replica_last_launch_ms(apus_replica_t *r, float *ms);
+int  apus_replicas_stop(apus_replica_t **rs, int n);
+
+/* ---- leader admission: the fields of tailq_entry_t (message.h:11-17) ------------- */
+/* One request; `cmd` has `len` bytes (sm_cmd_t.cmd).  For APUS_CONFIG pass the
+ * 16-byte dare_cid_t, for APUS_HEAD the 8-byte head offset, for APUS_NOOP nothing.
+ * *ticket (optional) receives the 1-based position in the leader's append order.
+ * APUS_RETRY when the submission ring is full. */
+int  apus_submit(apus_replica_t *leader, uint8_t type, uint16_t connection_id, uint64_t req_id,
+                 const void *cmd, uint16_t len, uint64_t *ticket);
+/* n requests; payload k is payloads + k*stride (len[k] bytes).  conn/req arrays of n. */
+int  apus_submit_batch(apus_replica_t *leader, uint32_t n, const uint8_t *types,
+                       const uint16_t *connection_ids, const uint64_t *req_ids,
+                       const uint16_t *lens, const void *payloads, size_t stride,
+                       uint64_t *first_ticket);
+/* make everything submitted so far visible to the kernel (doorbell); apus_submit*
+ * ring it themselves unless the replica was put in deferred mode */
+int  apus_submit_defer(apus_replica_t *leader, int defer);
+int  apus_submit_flush(apus_replica_t *leader);
+
+/* ---- commit observation (what update_state / do_action hang off) ---------------- */
+uint64_t apus_committed_tickets(apus_replica_t *leader);
+/* spin until ticket is committed; APUS_RETRY on timeout */
+int  apus_wait_committed(apus_replica_t *leader, uint64_t ticket, int64_t timeout_us);
+
+/* ---- inspection (parity tests, snapshots) --------------------------------------- */
+int  apus_log_offsets(apus_replica_t *r, apus_log_offsets_t *out);
+/* copy entries[off, off+len) of this replica's log image to host memory */
+int  apus_log_read(apus_replica_t *r, uint64_t off, uint64_t len, void *dst);
+int  apus_get_stats(apus_replica_t *r, apus_stats_t *out);
+/* device-side commit latencies (ns), newest `max` samples; returns count in *n */
+int  apus_latency_samples(apus_replica_t *r, uint32_t *dst_ns, uint32_t max, uint32_t *n);
+
+/* control plane hooks used by pruning (log_pruning, dare_server.c:1996-2067) */
+int  apus_set_head(apus_replica_t *r, uint64_t head);
+int  apus_remote_apply_offsets(apus_replica_t *leader, uint64_t out[APUS_MAX_SERVER_COUNT]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APUS_GPU_H */

@@ -1,0 +1,63 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads and exports
+every symbol include/apus_gpu.h declares; without a GPU every entry point fails
+loudly (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    from apus_b200 import engine
+    return engine
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "apus_gpu.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(apus_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(built):
+    lib = built.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/apus_gpu.h but not exported"
+    assert sorted(built.EXPORTS) == syms
+    assert lib.apus_abi_version() == 1
+
+
+def test_nm_shows_kernel_and_c_abi(built):
+    out = subprocess.run(["nm", "-D", "--defined-only", built.LIB_PATH], capture_output=True, text=True).stdout
+    for s in declared_symbols():
+        assert re.search(rf"\bT {s}\b", out), s
+
+
+def test_sass_is_sm100a(built):
+    out = subprocess.run(["cuobjdump", "-lelf", built.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback(built):
+    """Without a visible GPU, creating a replica is an error, not a silent CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(built.ApusError):
+        built.Replica(0, 0, 1)
+
+
+def test_config_struct_matches_header(built):
+    # struct_size is checked by the library itself; this pins the Python mirror
+    assert C.sizeof(built.Config) == 40
+    assert C.sizeof(built.PeerHandle) == 128
+    assert C.sizeof(built.LogOffsets) == 64
+    assert C.sizeof(built.Stats) == 64

@@ -1,0 +1,238 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the CPU oracle and the
+golden vectors.  Bit-exact: integer/byte work, no tolerance.  Marked gpu."""
+import json
+import os
+import hashlib
+
+import numpy as np
+import pytest
+
+import engine_util as EU
+import orc as O
+import streams as S
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import __graft_entry__ as g
+    g.build()
+    import apus_b200
+    if apus_b200.lib().apus_device_count() < 1:
+        pytest.fail("no CUDA device visible on a gpu-marked test")
+    return apus_b200
+
+
+def devices_for(eng, n):
+    nd = eng.lib().apus_device_count()
+    return [i % nd for i in range(n)]
+
+
+def run_and_compare(eng, orc, n, L, stream, ring_mode=0, prologue=True, exact=True, devices=None, chunks=1):
+    devices = devices or devices_for(eng, n)
+    with eng.Group(n, devices=devices, log_size=L, ring_mode=ring_mode) as g:
+        if prologue:
+            g.prologue()
+        per = (len(stream) + chunks - 1) // chunks
+        for k in range(chunks):                       # several launches: state carries over
+            g.submit_stream(stream[k * per:(k + 1) * per])
+            g.run()
+        c = EU.oracle_cluster(orc, n, L, stream, prologue=prologue)
+        try:
+            eo, oo = EU.compare_group_to_oracle(g, c, exact=exact)
+            st = g.leader.stats()
+            total = len(stream) + (1 if (prologue and n > 1) else 0)
+            assert st["tickets_committed"] == total == st["tickets_consumed"]
+            assert g.leader.committed() == total
+            # bytes accounted for the roofline = (N-1) * log bytes of the stream
+            assert st["bytes_replicated"] == c.bytes_replicated()
+            for i, r in enumerate(g.replicas):
+                if i != g.leader_idx:
+                    assert r.stats()["entries_acked"] == total
+        finally:
+            c.close()
+
+
+def test_one_replica_degenerate(eng, orc):
+    """group_size 1: no CONFIG prologue, the leader's own vote is the majority
+    (dare_server.c:416-424)."""
+    run_and_compare(eng, orc, 1, 1 << 20, S.uniform_stream(2000, 64), prologue=False)
+
+
+@pytest.mark.parametrize("n", [3, 5, 7])
+def test_uniform_64B(eng, orc, n):
+    run_and_compare(eng, orc, n, 1 << 21, S.uniform_stream(6000, 64, conns=4))
+
+
+@pytest.mark.parametrize("n,seed", [(3, 11), (5, 12), (7, 13), (13, 14)])
+def test_ragged_lengths(eng, orc, n, seed):
+    """0-length, odd and unaligned payloads: entries start at arbitrary byte offsets (H1)."""
+    run_and_compare(eng, orc, n, 1 << 21, S.ragged_stream(3000, 300, conns=5, seed=seed, close_every=70))
+
+
+def test_device_ring_mode(eng, orc):
+    run_and_compare(eng, orc, 5, 1 << 21, S.ragged_stream(2500, 500, seed=21), ring_mode=1)
+
+
+def test_multiple_launches_carry_state(eng, orc):
+    run_and_compare(eng, orc, 3, 1 << 21, S.ragged_stream(2000, 128, seed=22), chunks=5)
+
+
+def test_large_payloads(eng, orc):
+    stream = [(S.CONNECT, 1, 1, b"")] + [(S.SEND, 1, 2 + i, bytes([(i * 7 + k) & 0xFF for k in range(256)]) * 16)
+                                          for i in range(40)]
+    stream += [(S.SEND, 1, 100 + i, np.random.default_rng(i).integers(0, 256, 65535, dtype=np.uint8).tobytes())
+               for i in range(6)]
+    stream += [(S.SEND, 1, 200, b""), (S.CLOSE, 1, 201, b"")]
+    run_and_compare(eng, orc, 3, 1 << 21, stream)
+
+
+def test_default_log_size_64MiB(eng, orc):
+    """The reference's LOG_SIZE (dare_log.h:76), 4 KiB requests."""
+    run_and_compare(eng, orc, 3, 0 or O.LOG_SIZE, S.uniform_stream(3000, 4096, conns=2))
+
+
+def test_exact_fit_wrap_rule_E1(eng, orc):
+    """An entry that ends exactly at len: the engine stores end = 0 (divergence E1; the
+    reference's end == len would read as "log empty", SURVEY.md H11 iv)."""
+    n, L = 3, 8192
+    orc.set_rules(O.RULES_ENGINE)
+    c = O.Cluster(orc, n, leader=0, term=1, length=L)
+    c.prologue()
+    with eng.Group(n, devices=devices_for(eng, n), log_size=L) as g:
+        g.prologue()
+        part = S.uniform_stream(62, 64)                 # CONFIG 64 + CONNECT 64 + 62*128 = 8064
+        for typ, clt, rid, payload in part:
+            assert c.submit(typ, clt, rid, O.cmd_image(payload))
+        c.round(); c.round()
+        g.submit_stream(part); g.run()
+        assert prune_both(g, c)                          # HEAD entry: 8064 -> 8128
+        c.round(); c.round(); g.run()
+        tail_part = [(S.SEND, 0, 64, b""),               # 64 B stride: ends exactly at 8192
+                     (S.SEND, 0, 65, b"after the wrap" * 3), (S.SEND, 0, 66, b"x" * 100)]
+        for typ, clt, rid, payload in tail_part[:1]:
+            assert c.submit(typ, clt, rid, O.cmd_image(payload))
+        c.round(); c.round()
+        assert c.offsets(0)["end"] == 0
+        g.submit_stream(tail_part[:1]); g.run()
+        assert g.leader.offsets()["end"] == 0
+        for typ, clt, rid, payload in tail_part[1:]:
+            assert c.submit(typ, clt, rid, O.cmd_image(payload))
+        c.round(); c.round()
+        g.submit_stream(tail_part[1:]); g.run()
+        EU.compare_group_to_oracle(g, c, exact=True)
+    c.close()
+
+
+def prune_both(g, c):
+    """log_pruning (dare_server.c:1996-2067) on both sides: head := min apply, HEAD entry."""
+    idx = c.prune()
+    if not idx:
+        return False
+    head = c.offsets(0)["head"]
+    g.leader.set_head(head)
+    g.submit(eng_HEAD, 0, 0, head.to_bytes(8, "little"))
+    return True
+
+
+eng_HEAD = 3
+
+
+@pytest.mark.parametrize("n,L,seed", [(3, 16384, 77), (5, 32768, 78), (3, 8192, 79)])
+def test_wrap_laps_with_pruning(eng, orc, n, L, seed):
+    """Several laps around a small ring: ghost headers, header-does-not-fit jumps,
+    stale bytes in entry holes, HEAD entries.  Pruning happens at quiescent points
+    so that the stream of appends is identical on both sides."""
+    stream = S.ragged_stream(1500, 180, conns=3, seed=seed)
+    orc.set_rules(O.RULES_ENGINE)
+    c = O.Cluster(orc, n, leader=0, term=1, length=L)
+    c.prologue()
+    with eng.Group(n, devices=devices_for(eng, n), log_size=L) as g:
+        g.prologue()
+        step = 12
+        total = 1
+        for k in range(0, len(stream), step):
+            part = stream[k:k + step]
+            for typ, clt, rid, payload in part:
+                assert c.submit(typ, clt, rid, O.cmd_image(payload)) != 0
+            c.round(); c.round()
+            g.submit_stream(part)
+            total += len(part)
+            g.run()
+            if prune_both(g, c):
+                total += 1
+                c.round(); c.round()
+                g.run()
+        EU.compare_group_to_oracle(g, c, exact=True)
+        assert g.leader.committed() == total
+        assert c.offsets(0)["head"] != 0
+    c.close()
+
+
+def test_persistent_service_mode_closed_loop(eng, orc):
+    """Kernels stay resident (target = forever); a single client submits one request
+    at a time and waits for its commit, like proxy.c:160."""
+    n, L = 3, 1 << 20
+    stream = S.ragged_stream(400, 100, conns=2, seed=31)
+    with eng.Group(n, devices=devices_for(eng, n), log_size=L) as g:
+        g.launch(target=(1 << 64) - 1)
+        t = g.prologue()
+        g.leader.wait_committed(t)
+        for typ, clt, rid, payload in stream:
+            t = g.submit(typ, clt, rid, payload)
+            g.leader.wait_committed(t, 5_000_000)
+            assert g.leader.committed() >= t
+        g.stop()
+        c = EU.oracle_cluster(orc, n, L, stream)
+        # followers were stopped right after the last commit: their commit offset may lag
+        lo = g.leader.offsets()
+        assert lo["commit"] == lo["end"] == c.offsets(0)["end"]
+        ents = O.walk_entries(c.image(0), 0, lo["end"], L)
+        assert np.array_equal(O.mask_replies(g.leader.image(), ents), O.mask_replies(c.image(0), ents))
+        for i in range(1, n):
+            fo = g.replicas[i].offsets()
+            assert fo["end"] == lo["end"]
+            assert np.array_equal(O.mask_replies(g.replicas[i].image(), ents), O.mask_replies(c.image(i), ents))
+        c.close()
+
+
+def test_commit_is_monotone_prefix(eng, orc):
+    """Observe the committed-ticket word while a long run is in flight: it only grows
+    and never passes what was submitted (invariant I3)."""
+    n, L = 5, 1 << 22
+    stream = S.uniform_stream(20000, 64, conns=8)
+    with eng.Group(n, devices=devices_for(eng, n), log_size=L) as g:
+        g.prologue()
+        g.submit_stream(stream)
+        g.launch()
+        seen = []
+        while g.leader.committed() < g.tickets:
+            seen.append(g.leader.committed())
+            if len(seen) > 5_000_000:
+                break
+        g.wait()
+        assert all(b >= a for a, b in zip(seen, seen[1:]))
+        assert g.leader.committed() == g.tickets
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden.json")
+
+
+@pytest.mark.parametrize("name,n,seed", [("cluster3_ragged", 3, 13), ("cluster5_ragged", 5, 15),
+                                         ("cluster7_ragged", 7, 17), ("cluster1_ragged", 1, 11)])
+def test_against_reference_golden(eng, name, n, seed):
+    """No oracle at run time: SHA-256 of every replica's log image against the vectors
+    generated from the COMPILED REFERENCE HEADER (tests/golden/gen_golden.py)."""
+    gold = {g["name"]: g for g in json.load(open(GOLD))["scenarios"]}[name]
+    stream = S.ragged_stream(500, 256, seed=seed, close_every=60)
+    L = 1 << 20
+    with eng.Group(n, devices=devices_for(eng, n), log_size=L) as g:
+        g.prologue()
+        g.submit_stream(stream)
+        g.run()
+        for i, r in enumerate(g.replicas):
+            assert hashlib.sha256(r.image().tobytes()).hexdigest() == gold["sha"][i], f"replica {i}"
+            o = r.offsets()
+            assert o["end"] == gold["offsets"][i]["end"] and o["commit"] == gold["offsets"][i]["commit"]
+        assert g.leader.stats()["bytes_replicated"] == gold["bytes_replicated"]
