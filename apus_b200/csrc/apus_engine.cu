@@ -144,6 +144,7 @@ extern "C" int apus_replica_create(const apus_config_t *cfg, apus_replica_t **ou
     apus_ctrl_t c;
     memset(&c, 0, sizeof c);
     c.next_idx = 1;
+    c.pend_head_end = log_len;   /* no HEAD entry pending */
     CK(cudaMemcpy(r->region, &c, sizeof c, cudaMemcpyHostToDevice));
 
     CK(cudaHostAlloc(&r->hw, sizeof(apus_hostwords_t), cudaHostAllocMapped | cudaHostAllocPortable));
@@ -552,6 +553,8 @@ extern "C" int apus_get_stats(apus_replica_t *r, apus_stats_t *out)
     out->batches = c.batches;
     out->kernel_launches = r->launches;
     out->lat_samples = c.lat_count;
+    out->auto_heads = c.auto_heads;
+    out->entries_published = c.published;
     return APUS_OK;
 }
 

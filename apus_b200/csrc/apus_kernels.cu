@@ -140,6 +140,8 @@ struct LeaderShared {
     uint32_t ghost;          // 1: ghost header is composed at a
     uint32_t fresh;          // 1: the range was never written (holes are zero)
     uint32_t finish;         // producers are done
+    uint32_t auto_head;      // 1: the tile starts with a HEAD entry appended by the pruning rule
+    uint64_t auto_head_val;  // ... carrying this head offset
     uint64_t a, b;           // byte range of the tile in the log
     uint64_t idx0;           // idx of the tile's first entry
     uint64_t t_dequeue;
@@ -161,6 +163,7 @@ struct FollowerShared {
     uint32_t n;
     uint32_t done;
     uint64_t win_lo, win_hi, next;           // window bounds in the log, next walk offset
+    uint64_t head_val, head_end;             // last HEAD entry of the window (head_end == len: none)
     uint64_t end_seen, commit_seen;
 };
 
@@ -284,16 +287,27 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx, LeaderS
         if (lane == 0) {
             if (S->producers_done && committed == S->published) ex = 1;
             else if ((++spins & 0x3ffu) == 0) {
-                if (ld_relaxed_sys_u32(&hw->stop) || S->abort_flag) ex = 1;
+                if (ld_relaxed_sys_u32(&hw->stop) || S->abort_flag) ex = 2;
                 else if (cx->target != ~0ull && globaltimer_ns() - last_progress > WATCHDOG_NS &&
                          committed != S->published) {
                     st_relaxed_sys(&hw->error, APUS_KERR_WATCHDOG_COMMIT);
                     S->abort_flag = 1;
-                    ex = 1;
+                    ex = 2;
                 }
             }
         }
-        if (__shfl_sync(0xffffffffu, ex, 0)) break;
+        ex = __shfl_sync(0xffffffffu, ex, 0);
+        if (ex) {
+            // clean end of a bounded launch: tell every follower how many entries exist, so
+            // that it can leave once it has acked and applied all of them
+            if (ex == 1 && cx->target != ~0ull && lane < N && lane != me && cx->peer[lane]) {
+                apus_ctrl_t *pc = reinterpret_cast<apus_ctrl_t *>(cx->peer[lane]);
+                st_relaxed_sys(&pc->fin_entries, committed);
+                __threadfence_system();
+                st_relaxed_sys(&pc->fin_target, cx->target);
+            }
+            break;
+        }
     }
 }
 
@@ -334,8 +348,10 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
     uint64_t end = hdr->end, tailpos = hdr->tail, next_idx = ctrl->next_idx;
     uint64_t consumed = ctrl->consumed, published = ctrl->published, hwm = ctrl->hwm;
     uint64_t bytes_rep = ctrl->bytes_replicated, batches = ctrl->batches;
+    uint64_t auto_heads = ctrl->auto_heads;
     uint64_t last_progress = globaltimer_ns();
     bool pending_gap = false;   // a gap tile was stored and awaits the next publish
+    bool prev_head = false;     // the last entry appended is a HEAD entry of the pruning rule
 
     for (;;) {
         // ---- T0: wait for requests (thread 0) ---------------------------------------
@@ -387,26 +403,53 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
 
         // ---- T2: placement (warp 0): log_append_entry's offset rules over the tile ----
         if (warp == 0) {
-            const uint64_t head = ld_relaxed_sys(&hdr->head);
+            uint64_t head = ld_relaxed_sys(&hdr->head);
             const uint64_t pos0 = (end == L) ? 0 : end;               // empty log starts at 0 (dare_log.h:216-219)
-            const uint64_t used = (end == L) ? 0 : (end >= head ? end - head : L - (head - end));
+            uint64_t used = (end == L) ? 0 : (end >= head ? end - head : L - (head - end));
+            // ---- device-side log pruning (log_pruning / force_log_pruning,
+            //      dare_server.c:1996-2122): head := the smallest apply offset in the group,
+            //      published through a HEAD entry placed in front of this tile
+            uint32_t autoh = 0;
+            uint64_t new_head = 0;
+            if ((cx->flags & APUS_FLAG_AUTOPRUNE) && end != L && used >= (L >> 2) && !prev_head &&
+                L - pos0 >= APUS_HDR_BYTES) {
+                uint64_t d = 0;                                   // distance apply -> end, per replica
+                if (lane < N) {
+                    const uint64_t ap = (lane == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[lane]);
+                    d = (end >= ap) ? end - ap : L - (ap - end);
+                    if (d > used) d = used;                       // never behind the current head
+                }
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    const uint64_t o = __shfl_xor_sync(0xffffffffu, d, sft);
+                    d = o > d ? o : d;
+                }
+                if (d == 0) d = (end >= tailpos) ? end - tailpos : L - (tailpos - end);   // leave one entry (:2031-2034)
+                if (d <= used && used - d >= (L >> 3)) {
+                    autoh = 1;
+                    new_head = (end >= d) ? end - d : L - (d - end);
+                    used = d;                                     // the head moves before the append (:2041)
+                    head = new_head;
+                }
+            }
+            const uint64_t hbytes = autoh ? APUS_HDR_BYTES : 0;
             // limits for a contiguous tile starting at pos0
             uint64_t lim = L - pos0;                                   // no entry may cross len
             const uint64_t imgcap = APUS_IMG_BYTES - 16u - (pos0 & 15u);
             if (lim > imgcap) lim = imgcap;
-            const uint64_t space = (L - used > 0) ? (L - used - 1) : 0;   // rule E2: stay strictly before head
-            const uint64_t lim_space = space;
+            // rule E2: stay strictly before head (keep room for one HEAD entry when pruning on the device)
+            const uint64_t reserve = (cx->flags & APUS_FLAG_AUTOPRUNE) ? APUS_HDR_BYTES : 0;
+            const uint64_t lim_space = (L - used > 1 + reserve) ? (L - used - 1 - reserve) : 0;
             // per-lane strip of entries, two-level exclusive scan of strides
             const uint32_t per = (nf + 31u) / 32u;
             const uint32_t k0 = lane * per, k1 = (k0 + per < nf) ? k0 + per : nf;
             uint32_t sum = 0;
             for (uint32_t k = k0; k < k1; k++) sum += entry_stride(S->type[k], S->len[k]);
             uint32_t incl = sum;
-            for (int s = 1; s < 32; s <<= 1) {
-                uint32_t o = __shfl_up_sync(0xffffffffu, incl, s);
-                if (lane >= s) incl += o;
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                uint32_t o = __shfl_up_sync(0xffffffffu, incl, sft);
+                if (lane >= sft) incl += o;
             }
-            uint64_t run = incl - sum;   // bytes before my strip
+            uint64_t run = hbytes + (incl - sum);   // bytes before my strip (behind the optional HEAD entry)
             uint32_t first_bad = nf;
             for (uint32_t k = k0; k < k1; k++) {
                 uint32_t es = entry_stride(S->type[k], S->len[k]);
@@ -414,29 +457,31 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
                 if (first_bad == nf && (run + es > lim || run + es > lim_space)) first_bad = k;
                 run += es;
             }
-            for (int s = 16; s > 0; s >>= 1) {
-                uint32_t o = __shfl_xor_sync(0xffffffffu, first_bad, s);
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                uint32_t o = __shfl_xor_sync(0xffffffffu, first_bad, sft);
                 first_bad = o < first_bad ? o : first_bad;
             }
             if (lane == 0) {
                 uint32_t m = first_bad;
                 S->gap = 0; S->ghost = 0;
-                if (m == 0) {
+                if (m == 0 && !autoh) {
                     // entry 0 does not fit at pos0: wrap (dare_log.h:502-504, 526-538) or no space
                     const uint32_t es0 = entry_stride(S->type[0], S->len[0]);
                     const uint64_t left = L - pos0;
-                    if (es0 > left && used + left + es0 < L) {
+                    if (es0 > left && used + left + es0 + reserve < L) {
                         S->gap = 1;
-                        S->ghost = (left >= APUS_HDR_BYTES) ? 1u : 0u;   // header fits: ghost stays behind
+                        S->ghost = (left >= APUS_HDR_BYTES && has_cmd(S->type[0])) ? 1u : 0u;   // header fits: ghost stays behind
                         S->a = pos0; S->b = L;
                     } else {
                         S->a = S->b = pos0;   // back-pressure: wait for head to advance
                     }
                 } else {
                     S->a = pos0;
-                    S->b = pos0 + S->rel[m - 1] + entry_stride(S->type[m - 1], S->len[m - 1]);
+                    S->b = pos0 + (m ? S->rel[m - 1] + entry_stride(S->type[m - 1], S->len[m - 1]) : hbytes);
                 }
                 S->m = m;
+                S->auto_head = autoh; S->auto_head_val = new_head;
+                if (autoh) st_relaxed_sys(&hdr->head, new_head);
                 S->idx0 = next_idx;
                 S->fresh = (S->a >= hwm) ? 1u : 0u;
             }
@@ -482,13 +527,21 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
                 if (lane == 0) { e[E_DATA] = (uint8_t)(S->len[0] & 0xff); e[E_DATA + 1] = (uint8_t)(S->len[0] >> 8); }
             }
         } else {
+            const uint32_t autoh = S->auto_head;
+            if (autoh && warp == N_PRODUCER_WARPS - 1) {
+                // <HEAD, head_offset> entry (dare_log.h:29-32, dare_server.c:2043-2046)
+                uint8_t *e = img + (a - a16);
+                for (uint32_t j = lane; j < 41; j += 32)
+                    e[j] = (uint8_t)hdr_byte(j, S->idx0, cx->term, 0, 0, T_HEAD, me);
+                if (lane < 8) e[E_DATA + lane] = (uint8_t)(S->auto_head_val >> (8 * lane));
+            }
             for (uint32_t k = warp; k < m; k += N_PRODUCER_WARPS) {
                 uint8_t *e = img + (a - a16) + S->rel[k];
                 const uint32_t ty = S->type[k], ln = S->len[k];
                 const uint64_t rq = S->req_id[k];
                 const uint32_t cl = S->clt[k];
                 for (uint32_t j = lane; j < 41; j += 32)
-                    e[j] = (uint8_t)hdr_byte(j, S->idx0 + k, cx->term, rq, cl, ty, me);
+                    e[j] = (uint8_t)hdr_byte(j, S->idx0 + autoh + k, cx->term, rq, cl, ty, me);
                 const uint32_t nb = data_bytes(ty, ln);
                 if (nb) warp_copy_to_smem(e + E_DATA, cx->sub_pay + 16ull * S->pay_off[k], nb, lane);
             }
@@ -530,9 +583,12 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
         }
         uint64_t new_end = b;
         if (new_end == L) new_end = 0;                     // rule E1
-        tailpos = a + S->rel[m - 1];
+        const uint32_t autoh = S->auto_head;
+        tailpos = m ? a + S->rel[m - 1] : a;
         end = new_end;
-        next_idx += m; consumed += m; published += m;
+        next_idx += m + autoh; consumed += m; published += m + autoh;
+        auto_heads += autoh;
+        prev_head = (autoh && m == 0);                     // never two HEAD entries in a row (dare_log.h:477-480)
         if (b > hwm) hwm = b;
         bytes_rep += (b - a) * (uint64_t)(N - 1);
         batches++;
@@ -546,6 +602,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
                 hdr->end = new_end; hdr->tail = tailpos; hdr->old_end = new_end;
                 ctrl->next_idx = next_idx; ctrl->consumed = consumed; ctrl->published = published;
                 ctrl->hwm = hwm; ctrl->bytes_replicated = bytes_rep; ctrl->batches = batches;
+                ctrl->auto_heads = auto_heads;
                 const uint64_t h = S->pub_head;
                 S->pub_cum[h & (PUB_RING - 1)] = published;
                 S->pub_end[h & (PUB_RING - 1)] = new_end;
@@ -566,6 +623,11 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
 // ---------------------------------------------------------------------------------
 // FOLLOWER
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t ring_dist(uint64_t from, uint64_t to, uint64_t L)
+{
+    return to >= from ? to - from : L - (from - to);
+}
+
 __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
 {
     FollowerShared *S = reinterpret_cast<FollowerShared *>(smem_raw);
@@ -580,11 +642,12 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
     apus_ctrl_t *lctrl = reinterpret_cast<apus_ctrl_t *>(lregion);
     uint8_t *lentries = lregion + APUS_ENTRIES_OFF;
     const uint64_t L = cx->log_len;
-    const bool fenced = (cx->flags & 0x1u) != 0;
+    const bool fenced = (cx->flags & APUS_FLAG_FENCED_ACK) != 0;
 
     uint64_t old_end = hdr->old_end;     // walk position (dare_server.c:1795)
     uint64_t acked = ctrl->acked;
-    uint64_t applied_commit = hdr->apply;
+    uint64_t applied = hdr->apply;       // apply offset (== commit as far as I hold the entries)
+    uint64_t pend_val = ctrl->pend_head_val, pend_end = ctrl->pend_head_end;
     uint64_t last_progress = globaltimer_ns();
     uint32_t spins = 0;
 
@@ -596,9 +659,14 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
                 e = ld_acquire_sys(&hdr->end);
                 c = ld_relaxed_sys(&hdr->commit);
                 const bool new_entries = (e != L) && (e != old_end);
-                const bool new_commit = (c != applied_commit);
+                // commit moved, and I hold entries beyond what I applied
+                const bool new_commit = (c != applied) && (old_end != L) && (applied != old_end);
                 if (new_entries || new_commit) break;
-                if (acked >= cx->target && c == old_end) { done = 1; break; }
+                // bounded launch: the leader says how many entries exist in total
+                if (cx->target != ~0ull && ld_acquire_sys(&ctrl->fin_target) == cx->target) {
+                    const uint64_t fe = ld_relaxed_sys(&ctrl->fin_entries);
+                    if (acked >= fe && (e == L || (applied == old_end && c == old_end))) { done = 1; break; }
+                }
                 if ((++spins & 0xffu) == 0) {
                     if (ld_relaxed_sys_u32(&hw->stop)) { done = 1; break; }
                     if (cx->target != ~0ull && globaltimer_ns() - last_progress > WATCHDOG_NS) {
@@ -638,6 +706,7 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
                 uint32_t n = 0;
                 uint64_t next = off;
                 bool wrapped = false;
+                uint64_t hv = 0, he = L;
                 while (off < hi) {
                     if (L - off < APUS_HDR_BYTES) { next = 0; wrapped = true; break; }   // jump to 0
                     if (hi - off < APUS_HDR_BYTES) { next = off; break; }                // header not in window yet
@@ -647,12 +716,18 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
                     const uint32_t es = entry_stride(ty, ln);
                     if (L - off < es) { next = 0; wrapped = true; break; }              // ghost: entry continues at 0
                     if (off + es > hi) { next = off; break; }                            // entry crosses the window
+                    if (ty == T_HEAD) {                                                  // poll_config_entries (dare_server.c:2163-2170)
+                        hv = 0;
+                        for (int q = 7; q >= 0; q--) hv = (hv << 8) | e[E_DATA + q];
+                        he = (off + es == L) ? 0 : off + es;
+                    }
                     S->off[n++] = (uint32_t)(off - lo);
                     off += es;
                     next = off;
                 }
                 if (!wrapped && next == L) next = 0;      // rule E1 on walker offsets
                 S->n = n; S->next = next;
+                S->head_val = hv; S->head_end = he;
             }
             __syncthreads();
             const uint32_t n = S->n;
@@ -670,6 +745,7 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
                 old_end = end_seen;
                 break;
             }
+            if (S->head_end != L) { pend_val = S->head_val; pend_end = S->head_end; }
             acked += n;
             old_end = next;
             if (tid == 0) {
@@ -677,18 +753,31 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
                 st_relaxed_sys(&lctrl->ack[me], acked); // the word the leader's quorum ballot polls
                 hdr->old_end = old_end;
                 ctrl->acked = acked;
+                ctrl->pend_head_val = pend_val; ctrl->pend_head_end = pend_end;
             }
             last_progress = globaltimer_ns();
         }
 
         // ---- follow the commit offset (invariant I4: never beyond what I hold) ----------
-        if (commit_seen != applied_commit) {
-            applied_commit = commit_seen;
-            if (tid == 0) {
-                hdr->apply = applied_commit;            // host-side apply (do_action) drains behind this
-                st_relaxed_sys(&lctrl->apply_off[me], applied_commit);
+        if (old_end != L && applied != old_end && commit_seen != applied) {
+            const uint64_t from = (applied == L) ? 0 : applied;
+            const uint64_t held = ring_dist(from, old_end, L);          // entries I hold beyond `applied`
+            uint64_t want = ring_dist(from, commit_seen, L);
+            uint64_t to = commit_seen;
+            if (want > held) { want = held; to = old_end; }             // the leader clamps the same way (dare_ibv_rc.c:1783-1787)
+            if (want) {
+                if (pend_end != L && ring_dist(from, pend_end, L) <= want && ring_dist(from, pend_end, L) > 0) {
+                    // the HEAD entry is committed: adopt the head it carries (dare_server.c:2166-2169, 2182-2186)
+                    if (tid == 0) { hdr->head = pend_val; ctrl->pend_head_end = L; }
+                    pend_end = L;
+                }
+                applied = to;
+                if (tid == 0) {
+                    hdr->apply = applied;               // host-side apply (do_action) drains behind this
+                    st_relaxed_sys(&lctrl->apply_off[me], applied);
+                }
+                last_progress = globaltimer_ns();
             }
-            last_progress = globaltimer_ns();
         }
         __syncthreads();
     }

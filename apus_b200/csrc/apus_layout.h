@@ -74,7 +74,14 @@ typedef struct apus_ctrl {
     uint64_t batches;
     uint64_t acked;              /* follower: entries acked */
     uint64_t lat_count;          /* leader: latency samples written */
-    uint64_t pad0[6];
+    uint64_t auto_heads;         /* leader: HEAD entries appended by the device-side pruning rule */
+    uint64_t pend_head_val;      /* follower: head carried by the last HEAD entry seen ... */
+    uint64_t pend_head_end;      /* ... and the offset right after that entry (len = none) */
+    uint64_t pad0[3];
+    /* --- written by the LEADER into each follower's region at the end of a launch --- */
+    uint64_t fin_entries;        /* entries the leader has published in total */
+    uint64_t fin_target;         /* the launch (its ticket target) this refers to */
+    uint64_t pad1[14];
 } apus_ctrl_t;
 
 /* submission descriptor, 16 B: the fields of tailq_entry_t (message.h:11-17) */
@@ -98,6 +105,10 @@ typedef struct apus_hostwords {
     volatile uint64_t heartbeat;         /* kernel liveness (debug) */
     volatile uint64_t error;             /* kernel-detected protocol error code */
 } apus_hostwords_t;
+
+#define APUS_FLAG_FENCED_ACK 0x1u
+#define APUS_FLAG_STATS      0x2u
+#define APUS_FLAG_AUTOPRUNE  0x4u
 
 #define APUS_ROLE_NONE     0
 #define APUS_ROLE_LEADER   1

@@ -1,0 +1,478 @@
+#!/usr/bin/env python
+"""bench.py -- committed ops/s of the replication hot path (BASELINE.json metric:
+"committed ops/s and p50/p99 commit latency, 64B reqs, 5 replicas").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch of synthetic requests:
+`--batch` SEND requests of `--payload` bytes are appended to the leader's log,
+replicated to every follower, acked, and committed by majority.
+
+  value      requests already resident in HBM (device submission ring) when the timed
+             region starts; one fused kernel launch per GPU per step
+  e2e        the same metric through the C ABI with HOST buffers: apus_submit_batch()
+             from host memory + apus_wait_committed(); the kernels stay resident
+  roofline   algorithmic bytes (N-1)*(64+L) per committed op / CUDA-event time of the
+             replica kernel, against MEASURED_PEAKS.json (HBM copy bandwidth: with all
+             replicas on one GPU the "peer" stores land in local HBM; NVLink peer-copy
+             figure when replicas sit on different GPUs)
+  cpu_baseline  the reference's own log code (oracle/_ref, else the oracle port) run
+             on the host cores: leader thread + follower threads, memcpy transport
+
+N = 1: all `--replicas` replicas of ONE group live on GPU 0 (the 5-replica configuration
+of the metric fits one GPU).  N > 1 (torchrun, one process per GPU): N groups, group g
+led by GPU g, replica r of group g on GPU (g + r) % N, peers mapped with CUDA IPC; no
+data-path collective (weak scaling: every GPU leads one group of the same size).
+
+The log ring is the reference's LOG_SIZE (64 MiB); sustained runs wrap it many times,
+kept alive by the device-side pruning rule (HEAD entries, APUS_F_AUTOPRUNE).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SEND, CONNECT = 5, 4
+UINT64_MAX = (1 << 64) - 1
+NVLINK_PEER_GBS = 770.0     # measured peer copy per direction (B200_PROFILING.md)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--replicas", type=int, default=5)
+    ap.add_argument("--payload", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=65536, help="requests per step")
+    ap.add_argument("--log-size", type=int, default=0, help="bytes of entries[]; 0 = reference LOG_SIZE (64 MiB)")
+    ap.add_argument("--lat-requests", type=int, default=3000, help="closed-loop requests for p50/p99")
+    ap.add_argument("--e2e-ring", default="mapped", choices=["mapped", "device"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--spread", action="store_true",
+                    help="single process: place replica r on GPU r %% visible GPUs (NVLink path)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured HBM copy (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback HBM copy 6.65 TB/s (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------
+# CPU baseline / reference arm
+# ------------------------------------------------------------------------------------
+def cpu_library():
+    import orc as O
+    O.build_oracle()
+    if O.have_ref():
+        return O.Oracle("ref"), "reference"
+    return O.Oracle("orc"), "port"
+
+
+def cpu_run(oracle, n, payload, nreq, clients=64):
+    secs = C.c_double()
+    ops = oracle.bench_run(n, payload, nreq, clients, C.byref(secs))
+    return float(ops), float(secs.value)
+
+
+def cpu_nreq(payload, batch):
+    # stay inside one 64 MiB ring: the CPU run has no pruning
+    return max(1, min(batch, (60 << 20) // (64 + payload)))
+
+
+def cpu_baseline(n, payload, batch, budget_s=10.0):
+    oracle, kind = cpu_library()
+    nreq = cpu_nreq(payload, batch)
+    best, total, runs = 0.0, 0.0, 0
+    while total < budget_s and runs < 200:
+        ops, s = cpu_run(oracle, n, payload, nreq)
+        best = max(best, ops); total += s; runs += 1
+    return {"value": round(best, 1), "unit": "ops/s", "cores": n, "kind": kind,
+            "sample": f"best of {runs} runs x {nreq} requests of {payload} B; {n} replicas as threads of one process "
+                      f"(leader + {n - 1} followers), closed loop with 64 outstanding requests, memcpy transport "
+                      f"(zero latency), no BerkeleyDB put, fresh 64 MiB ring per run"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    oracle, kind = cpu_library()
+    n, payload = args.replicas, args.payload
+    nreq = cpu_nreq(payload, args.batch)
+    for _ in range(args.warmup):
+        cpu_run(oracle, n, payload, nreq)
+    t = 0.0
+    for _ in range(args.steps):
+        _, s = cpu_run(oracle, n, payload, nreq)
+        t += s
+    value = args.steps * nreq / t
+    out = {
+        "impl": "reference", "metric": "committed ops/s", "value": round(value, 1), "unit": "ops/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1e3 * t / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{n} replicas, {payload} B SEND requests, {nreq} requests per step; the reference's "
+                               f"log code on host threads (memcpy transport), one fresh 64 MiB ring per step",
+                   "replicas": n, "payload_bytes": payload, "batch": nreq},
+        "cpu_baseline": {"value": round(value, 1), "unit": "ops/s", "cores": n, "kind": kind,
+                         "sample": f"{args.steps} steps x {nreq} requests, closed loop, 64 outstanding"},
+        "e2e": {"value": round(value, 1), "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------
+class Cell:
+    """The replicas this process hosts: in a single process all replicas of one group;
+    under torchrun the leader of group `rank` plus the followers of the neighbouring
+    groups that the placement (g + r) % N puts on this GPU."""
+
+    def __init__(self, A, E, args, ring_mode, slots, ring_bytes, flags, dist=None, rank=0, world=1, local=0):
+        self.A, self.E = A, E
+        n, L = args.replicas, (args.log_size or A.LOG_SIZE)
+        self.n, self.L = n, L
+        self.local = []
+        if world == 1:
+            nd = A.lib().apus_device_count()
+            devs = [r % nd for r in range(n)] if args.spread else [0] * n
+            self.group = A.Group(n, devices=devs, log_size=L, ring_mode=ring_mode, ring_slots=slots,
+                                 ring_bytes=ring_bytes, flags=flags)
+            self.leader = self.group.leader
+            self.local = list(self.group.replicas)
+            self.devices = sorted(set(devs))
+            self.placement = "all replicas on GPU 0" if not args.spread else f"replica r on GPU r % {nd}"
+        else:
+            self.group = None
+            mine = {}
+            for g in range(world):
+                for r in range(n):
+                    if (g + r) % world == rank:
+                        mine[(g, r)] = E.Replica(local, r, n, 0, 1, L, ring_mode, slots if r == 0 else 0,
+                                                 ring_bytes if r == 0 else 0, flags)
+            blobs = {k: v.export() for k, v in mine.items()}
+            allb = [None] * world
+            dist.all_gather_object(allb, blobs)
+            merged = {}
+            for d in allb:
+                merged.update(d)
+            for (g, r), rep in mine.items():
+                for r2 in range(n):
+                    if r2 != r:
+                        rep.connect(r2, merged[(g, r2)])
+            self.leader = mine[(rank, 0)]
+            self.local = list(mine.values())
+            self.devices = [local]
+            self.placement = f"group g led by GPU g, replica r on GPU (g + r) % {world}, CUDA IPC"
+        self.tickets = 0
+
+    def launch(self, target):
+        E, A = self.E, self.A
+        by_dev = {}
+        for r in self.local:
+            by_dev.setdefault(r.device, []).append(r)
+        for dev, rs in sorted(by_dev.items(), key=lambda kv: any(r.is_leader for r in kv[1])):
+            arr = (C.c_void_p * len(rs))(*[r.h for r in rs])
+            E._ck(A.lib().apus_replicas_launch(arr, len(rs), target), "apus_replicas_launch")
+
+    def wait(self, timeout_ms=120_000):
+        for r in self.local:
+            r.wait(timeout_ms)
+
+    def stop(self):
+        arr = (C.c_void_p * len(self.local))(*[r.h for r in self.local])
+        self.E._ck(self.A.lib().apus_replicas_stop(arr, len(self.local)), "apus_replicas_stop")
+
+    def submit(self, typ, conn, req, payload=b""):
+        self.tickets = self.leader.submit(typ, conn, req, payload)
+        return self.tickets
+
+    def submit_uniform(self, nreq, length, conn, first_req, payloads):
+        types = np.full(nreq, SEND, dtype=np.uint8)
+        conns = np.full(nreq, conn, dtype=np.uint16)
+        reqs = np.arange(first_req, first_req + nreq, dtype=np.uint64)
+        lens = np.full(nreq, length, dtype=np.uint16)
+        t0 = self.leader.submit_batch(types, conns, reqs, lens, payloads, length)
+        self.tickets = t0 + nreq - 1
+        return self.tickets
+
+    def close(self):
+        for r in self.local:
+            r.close()
+
+
+def run_ours(args):
+    import __graft_entry__ as ge
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import apus_b200 as A
+    from apus_b200 import engine as E
+
+    if not torch.cuda.is_available() or A.lib().apus_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+
+    n, payload, batch = args.replicas, args.payload, args.batch
+    K, W = args.steps, args.warmup
+    L = args.log_size or A.LOG_SIZE
+    stride = 64 + payload
+    if batch * stride * 4 > L * 3:
+        raise SystemExit("batch too large for the log ring")
+    img = (2 + payload + 15) // 16 * 16
+    total_req = (K + W) * batch + 64
+    slots = 1 << max(16, (total_req - 1).bit_length())
+    ring_bytes = ((total_req * img + (1 << 20)) + 4095) // 4096 * 4096
+    if ring_bytes // 16 > 0xFFFFFF:
+        raise SystemExit("steps*batch*payload too large for the device submission ring (256 MiB)")
+    flags = E.F_FENCED_ACK | E.F_DEVICE_STATS | E.F_AUTOPRUNE
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    conn = 0
+    payloads = np.random.default_rng(0xA5A50000 + payload).integers(0, 256, size=batch * max(payload, 1), dtype=np.uint8)
+
+    # =========================== value: inputs resident in HBM ===========================
+    cell = Cell(A, E, args, A.RING_DEVICE, slots, ring_bytes, flags, dist, rank, world, local)
+    cell.submit(E.CONFIG, 0, 0, E.cid_image(n)) if n > 1 else None
+    cell.submit(CONNECT, conn, 1, b"")
+    barrier()
+    cell.launch(cell.tickets); cell.wait()
+    req = 2
+    targets = []
+    cell.leader.defer(True)
+    for s in range(W + K):
+        cell.submit_uniform(batch, payload, conn, req, payloads)
+        req += batch
+        targets.append(cell.tickets)
+    cell.leader.flush()            # every step's requests are now in the HBM ring
+    cell.leader.defer(False)
+    for s in range(W):
+        barrier()
+        cell.launch(targets[s]); cell.wait()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    kernel_ms = 0.0
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        cell.launch(targets[s]); cell.wait()
+        kernel_ms += cell.leader.last_launch_ms()
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed = max_over_ranks(t1 - t0)
+    kernel_ms = max_over_ranks(kernel_ms)
+    st = cell.leader.stats()
+    assert st["tickets_committed"] == targets[-1], (st, targets[-1])
+    value = world * K * batch / elapsed
+    launches = K * len(cell.devices) * world
+    lat_dev = cell.leader.latency_ns()
+    auto_heads = st["auto_heads"]
+    batches = st["batches"]
+    off = cell.leader.offsets()
+    cell.close()
+
+    # =========================== e2e: host buffers through the C ABI =====================
+    e2e = None
+    lat_host = None
+    if not args.no_e2e:
+        mode = A.RING_HOST_MAPPED if args.e2e_ring == "mapped" else A.RING_DEVICE
+        e_slots = 1 << max(16, (2 * batch - 1).bit_length())
+        e_bytes = ((2 * batch * img + (1 << 20)) + 4095) // 4096 * 4096
+        cell = Cell(A, E, args, mode, e_slots, e_bytes, flags, dist, rank, world, local)
+        barrier()
+        cell.launch(UINT64_MAX)
+        if n > 1:
+            cell.submit(E.CONFIG, 0, 0, E.cid_image(n))
+        t = cell.submit(CONNECT, conn, 1, b"")
+        cell.leader.wait_committed(t, 20_000_000)
+        req = 2
+        for s in range(W):
+            t = cell.submit_uniform(batch, payload, conn, req, payloads); req += batch
+            cell.leader.wait_committed(t, 60_000_000)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(K):
+            t = cell.submit_uniform(batch, payload, conn, req, payloads); req += batch
+            cell.leader.wait_committed(t, 60_000_000)
+        t1 = time.perf_counter()
+        e_elapsed = max_over_ranks(t1 - t0)
+        e2e = {"value": round(world * K * batch / e_elapsed, 1), "unit": "ops/s",
+               "h2d_bytes_per_step": batch * (16 + img), "d2h_bytes_per_step": 8,
+               "path": f"apus_submit_batch(host numpy buffers) -> {args.e2e_ring} submission ring -> resident kernels "
+                       f"-> apus_wait_committed (pinned commit word)"}
+        # closed loop, one request in flight: host-view commit latency (proxy.c:160 spin)
+        if rank == 0 and args.lat_requests > 0:
+            one = payloads[:max(payload, 1)].tobytes()[:payload]
+            lats = []
+            for i in range(args.lat_requests):
+                a = time.perf_counter_ns()
+                t = cell.submit(SEND, conn, req, one); req += 1
+                cell.leader.wait_committed(t, 5_000_000)
+                lats.append(time.perf_counter_ns() - a)
+            lats = np.sort(np.array(lats[args.lat_requests // 10:], dtype=np.float64)) / 1e3
+            lat_host = {"p50_us": round(float(lats[len(lats) // 2]), 2), "p99_us": round(float(lats[int(len(lats) * 0.99)]), 2),
+                        "n": int(len(lats)), "what": "apus_submit -> apus_wait_committed, one request in flight "
+                                                      "(includes ~1-2 us of ctypes call overhead)"}
+            d = cell.leader.latency_ns(args.lat_requests - args.lat_requests // 10)
+            if len(d):
+                d = np.sort(d.astype(np.float64)) / 1e3
+                lat_host["device_p50_us"] = round(float(d[len(d) // 2]), 2)
+                lat_host["device_p99_us"] = round(float(d[int(len(d) * 0.99)]), 2)
+        barrier()
+        cell.stop()
+        cell.close()
+
+    # =========================== CPU baseline, JSON line ==================================
+    if rank != 0:
+        return
+    cpu = None if (args.no_cpu or world > 1) else cpu_baseline(n, payload, batch)
+    alg_bytes_per_op = (n - 1) * (64 + payload)
+    ach = alg_bytes_per_op * batch / (kernel_ms / K * 1e-3) / 1e9
+    if world == 1 and not args.spread:
+        peak, peak_src = hbm_peak()
+        bound = "hbm"
+    else:
+        peak, peak_src = NVLINK_PEER_GBS, "measured NVLink peer copy per direction (B200_PROFILING.md)"
+        bound = "nvlink"
+    dl = np.sort(lat_dev.astype(np.float64)) / 1e3 if len(lat_dev) else None
+    out = {
+        "metric": "committed ops/s", "value": round(value, 1), "unit": "ops/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": round(1e3 * elapsed / K, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {
+            "workload": f"{n}-replica Paxos group, {payload} B SEND requests, {batch} requests per step, "
+                        f"device-resident submission ring",
+            "replicas": n, "payload_bytes": payload, "batch": batch, "groups": world,
+            "placement": ("all replicas of the group on GPU 0" if world == 1 and not args.spread else
+                          ("replica r on GPU r % visible GPUs, one process" if world == 1 else
+                           f"group g led by GPU g, replica r on GPU (g + r) % {world}, one process per GPU, CUDA IPC")),
+            "log_ring_bytes": L, "log_pruning": "device-side HEAD entries (APUS_F_AUTOPRUNE)",
+            "cache": f"inputs larger than L2: {(K + W) * batch * (16 + img) >> 20} MiB of requests stream through once; "
+                     f"log writes cover the 64 MiB ring x {n} replicas",
+        },
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": launches,
+        "roofline": {"bound": bound, "achieved": round(ach, 3), "peak": peak, "unit": "GB/s",
+                     "frac": round(ach / peak, 6), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_op": alg_bytes_per_op,
+                     "kernel": "apus_replica_kernel (one fused launch per step: leader CTA + follower CTAs)",
+                     "kernel_ms_per_launch": round(kernel_ms / K, 4)},
+        "cpu_baseline": cpu,
+        "latency": {"device_commit_us": (None if dl is None else
+                                         {"p50": round(float(dl[len(dl) // 2]), 2), "p99": round(float(dl[int(len(dl) * 0.99)]), 2),
+                                          "n": int(len(dl)), "what": "per replicate step: dequeue -> majority observed (%globaltimer), "
+                                                                     "open-loop run (queueing included)"}),
+                    "closed_loop": lat_host},
+        "engine": {"replicate_steps": batches, "auto_head_entries": auto_heads, "final_offsets": off},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

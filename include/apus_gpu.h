@@ -66,6 +66,10 @@ extern "C" {
 /* apus_config_t.flags */
 #define APUS_F_FENCED_ACK   0x1u  /* follower: reply bytes visible before the ack word (default on) */
 #define APUS_F_DEVICE_STATS 0x2u  /* leader: record per-batch device-side commit latency */
+#define APUS_F_AUTOPRUNE    0x4u  /* leader: device-side log pruning (force_log_pruning rule,
+                                     dare_server.c:2069-2122): when the ring is a quarter full the
+                                     kernel appends a HEAD entry carrying min(apply offsets) */
+#define APUS_F_EXPLICIT     0x80000000u /* flags are exactly as given (no defaults OR-ed in) */
 
 typedef struct apus_replica apus_replica_t;
 
@@ -103,6 +107,8 @@ typedef struct apus_stats {
     uint64_t batches;             /* leader: replicate steps (tail publishes) */
     uint64_t kernel_launches;     /* launches of apus kernels that included this replica */
     uint64_t lat_samples;         /* device-side latency samples available */
+    uint64_t auto_heads;          /* leader: HEAD entries appended by the device-side pruning rule */
+    uint64_t entries_published;   /* leader: entries appended (tickets + auto HEAD entries) */
 } apus_stats_t;
 
 /* ---- library ------------------------------------------------------------------- */

@@ -236,3 +236,64 @@ def test_against_reference_golden(eng, name, n, seed):
             o = r.offsets()
             assert o["end"] == gold["offsets"][i]["end"] and o["commit"] == gold["offsets"][i]["commit"]
         assert g.leader.stats()["bytes_replicated"] == gold["bytes_replicated"]
+
+
+def check_replica_images_consistent(g, L):
+    """Size-independent properties for runs too long for the oracle: every follower
+    holds exactly the leader's live log bytes (modulo reply[]), entries parse from
+    head to end with consecutive idx, HEAD entries carry offsets inside the ring."""
+    lo = g.leader.offsets()
+    limg = g.leader.image()
+    assert lo["commit"] == lo["end"]
+    start = lo["head"]
+    ents = O.walk_entries(limg, start, lo["end"], L)
+    assert len(ents) > 0
+    idx = [int.from_bytes(limg[o:o + 8].tobytes(), "little") for o, _ in ents]
+    assert idx == list(range(idx[0], idx[0] + len(idx)))
+    for o, _ in ents:
+        if limg[o + 26] == 3:
+            h = int.from_bytes(limg[o + 48:o + 56].tobytes(), "little")
+            assert 0 <= h < L
+        assert limg[o + 27] == g.leader_idx
+    lm = O.mask_replies(limg, ents)
+    for i, r in enumerate(g.replicas):
+        if i == g.leader_idx:
+            continue
+        fo = r.offsets()
+        assert fo["end"] == lo["end"] and fo["commit"] == lo["commit"] and fo["apply"] == lo["commit"]
+        fimg = O.mask_replies(r.image(), ents)
+        for o, stride in ents:
+            assert np.array_equal(fimg[o:o + stride], lm[o:o + stride]), f"replica {i} entry at {o}"
+        for o, _ in ents[-50:]:
+            assert r.image(o + 28 + i, o + 29 + i)[0] == 1
+    return len(ents), idx[-1]
+
+
+@pytest.mark.parametrize("n,L,payload", [(3, 1 << 20, 64), (5, 1 << 20, 200), (3, 1 << 18, 1000)])
+def test_sustained_autoprune_many_laps(eng, n, L, payload):
+    """Device-side pruning (APUS_F_AUTOPRUNE): 40+ laps around a small ring in a few
+    launches, no host-side HEAD submission."""
+    from apus_b200 import engine as E
+    flags = E.F_FENCED_ACK | E.F_DEVICE_STATS | E.F_AUTOPRUNE
+    per, rounds = 20000, 4
+    with eng.Group(n, devices=devices_for(eng, n), log_size=L, ring_mode=eng.RING_DEVICE,
+                   ring_slots=1 << 17, ring_bytes=64 << 20, flags=flags) as g:
+        g.prologue()
+        g.submit(S.CONNECT, 0, 1, b"")
+        req = 2
+        rng = np.random.default_rng(5)
+        for _ in range(rounds):
+            pl = rng.integers(0, 256, size=per * payload, dtype=np.uint8)
+            g.submit_uniform(per, payload, 0, req, pl)
+            req += per
+            g.run(timeout_ms=120_000)
+        st = g.leader.stats()
+        assert st["tickets_committed"] == g.tickets
+        assert st["auto_heads"] > 0
+        laps = (per * rounds * (64 + payload)) / L
+        assert laps > 4
+        n_live, last_idx = check_replica_images_consistent(g, L)
+        assert last_idx == g.tickets + st["auto_heads"]
+        # followers adopted a head carried by a committed HEAD entry
+        for i in range(1, n):
+            assert g.replicas[i].offsets()["head"] != 0
