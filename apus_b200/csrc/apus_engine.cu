@@ -80,9 +80,9 @@ struct apus_replica {
     apus_hostwords_t *hw;         /* pinned + mapped */
     apus_hostwords_t *hw_dev;
     /* submission ring (leader) */
-    apus_desc_t *ring_desc_host;  /* pinned: the ring itself (mapped mode) or its staging mirror */
+    apus_slot_t *ring_desc_host;  /* pinned: the slot ring itself (mapped mode) or its staging mirror */
     uint8_t     *ring_pay_host;
-    apus_desc_t *ring_desc_dev;   /* device-visible address the kernel reads */
+    apus_slot_t *ring_desc_dev;   /* device-visible address the kernel reads */
     uint8_t     *ring_pay_dev;
     uint64_t    *sub_tail_dev;    /* device doorbell (device mode) */
     uint64_t    *sub_tail_stage;  /* pinned staging word for the device doorbell */
@@ -168,13 +168,13 @@ extern "C" int apus_replica_create(const apus_config_t *cfg, apus_replica_t **ou
         r->ring_slots = slots; r->ring_bytes = bytes;
         r->pay_end = (uint64_t *)calloc(slots, sizeof(uint64_t));
         if (!r->pay_end) return fail("out of memory");
-        CK(cudaHostAlloc(&r->ring_desc_host, sizeof(apus_desc_t) * slots, cudaHostAllocMapped | cudaHostAllocPortable));
+        CK(cudaHostAlloc(&r->ring_desc_host, sizeof(apus_slot_t) * slots, cudaHostAllocMapped | cudaHostAllocPortable));
         CK(cudaHostAlloc(&r->ring_pay_host, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
         if (cfg->ring_mode == APUS_RING_HOST_MAPPED) {
             CK(cudaHostGetDevicePointer(&r->ring_desc_dev, r->ring_desc_host, 0));
             CK(cudaHostGetDevicePointer(&r->ring_pay_dev, r->ring_pay_host, 0));
         } else {
-            CK(cudaMalloc(&r->ring_desc_dev, sizeof(apus_desc_t) * slots));
+            CK(cudaMalloc(&r->ring_desc_dev, sizeof(apus_slot_t) * slots));
             CK(cudaMalloc(&r->ring_pay_dev, bytes));
             CK(cudaMalloc(&r->sub_tail_dev, 128));
             CK(cudaMemset(r->sub_tail_dev, 0, 128));
@@ -267,7 +267,7 @@ static void fill_ctx(apus_replica *r, uint64_t target)
     c->region = r->region;
     for (int i = 0; i < APUS_MAX_SERVER_COUNT; i++)
         c->peer[i] = (i == r->cfg.server_idx) ? NULL : (uint8_t *)r->peer_ptr[i];
-    c->sub_desc = r->ring_desc_dev; c->sub_pay = r->ring_pay_dev;
+    c->sub_slots = r->ring_desc_dev; c->sub_pay = r->ring_pay_dev;
     c->sub_mask = r->ring_slots ? r->ring_slots - 1 : 0;
     c->sub_tail = (r->cfg.ring_mode == APUS_RING_HOST_MAPPED) ? (const volatile uint64_t *)&r->hw_dev->sub_tail
                                                               : (const volatile uint64_t *)r->sub_tail_dev;
@@ -366,36 +366,44 @@ static inline uint32_t image_bytes(uint8_t type, uint16_t len)
     return 2u + len;
 }
 
-/* Payload space is tracked with monotone byte counters: pay_head (bytes handed
- * out, skip gaps included) and, per ticket, the counter value after its image. */
+/* Requests whose data image fits APUS_SLOT_INLINE travel inside their 128 B slot;
+ * larger images go to the payload byte ring.  Payload space is tracked with monotone
+ * byte counters: pay_head (bytes handed out, skip gaps included) and, per ticket, the
+ * counter value after its image. */
 static int ring_put(apus_replica *r, uint8_t type, uint16_t conn, uint64_t req_id, const void *cmd, uint16_t len)
 {
     const uint64_t consumed = r->hw->consumed;
     const uint32_t mask = r->ring_slots - 1;
     if (r->submitted - consumed >= r->ring_slots) return APUS_RETRY;
     const uint32_t nb = image_bytes(type, len);
-    const uint32_t need = (nb + 15u) & ~15u;
-    const uint64_t R = r->ring_bytes;
+    apus_slot_t *d = &r->ring_desc_host[r->submitted & mask];
+    uint32_t type_off = ((uint32_t)type & APUS_SLOT_TYPE_MASK) << APUS_SLOT_TYPE_SHIFT;
     uint64_t head = r->pay_head;
-    uint64_t pos = head % R;
-    if (need) {
-        uint64_t skip = (pos + need > R) ? (R - pos) : 0;          /* an image never wraps */
+    uint8_t *dst = d->inl;
+    if (nb > APUS_SLOT_INLINE) {
+        const uint32_t need = (nb + 15u) & ~15u;
+        const uint64_t R = r->ring_bytes;
+        uint64_t pos = head % R;
+        const uint64_t skip = (pos + need > R) ? (R - pos) : 0;          /* an image never wraps */
         const uint64_t tail = consumed ? r->pay_end[(consumed - 1) & mask] : 0;
         if ((head - tail) + skip + need > R) return APUS_RETRY;
         head += skip;
         pos = head % R;
-        uint8_t *dst = r->ring_pay_host + pos;
+        dst = r->ring_pay_host + pos;
+        type_off |= APUS_SLOT_EXT | (uint32_t)(pos / 16);
+        if (skip || (pos == 0 && head != 0)) type_off |= APUS_SLOT_WRAP;
+        head += need;
+    }
+    if (nb) {
         if (type == APUS_CONFIG || type == APUS_HEAD) {
             memcpy(dst, cmd, nb);
         } else {
             memcpy(dst, &len, 2);                    /* sm_cmd_t {u16 len; u8 cmd[]} (dare_sm.h:23-27) */
             if (len) memcpy(dst + 2, cmd, len);
         }
-        head += need;
     }
-    apus_desc_t *d = &r->ring_desc_host[r->submitted & mask];
     d->req_id = req_id;
-    d->type_off = ((uint32_t)type << 24) | (uint32_t)(pos / 16);
+    d->type_off = type_off;
     d->len = len;
     d->clt_id = conn;
     r->pay_end[r->submitted & mask] = head;
@@ -422,7 +430,7 @@ static int ring_flush(apus_replica *r)
         uint64_t i0 = f & mask;
         uint64_t run = r->submitted - f;
         if (i0 + run > r->ring_slots) run = r->ring_slots - i0;
-        CK(cudaMemcpyAsync(r->ring_desc_dev + i0, r->ring_desc_host + i0, run * sizeof(apus_desc_t),
+        CK(cudaMemcpyAsync(r->ring_desc_dev + i0, r->ring_desc_host + i0, run * sizeof(apus_slot_t),
                            cudaMemcpyHostToDevice, r->copy_stream));
         f += run;
     }
@@ -511,6 +519,38 @@ extern "C" int apus_wait_committed(apus_replica_t *r, uint64_t ticket, int64_t t
             }
         }
     }
+    return APUS_OK;
+}
+
+/* Closed loop with ONE request in flight, timed on the host around the two ABI steps a
+ * proxy thread performs (enqueue, then spin until committed -- proxy.c:108-161). */
+extern "C" int apus_closed_loop(apus_replica_t *r, uint32_t n, uint16_t payload_len, uint16_t connection_id,
+                                uint64_t first_req_id, uint32_t *lat_ns)
+{
+    if (!r || !lat_ns) return fail("null argument");
+    if (!is_leader(r)) return fail("submit on a follower");
+    uint8_t *buf = (uint8_t *)malloc(payload_len ? payload_len : 1);
+    if (!buf) return fail("out of memory");
+    for (uint32_t k = 0; k < payload_len; k++) buf[k] = (uint8_t)(k * 131u + 7u);
+    struct timespec t0, t1;
+    for (uint32_t i = 0; i < n; i++) {
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        int rc = ring_put(r, APUS_SEND, connection_id, first_req_id + i, buf, payload_len);
+        if (rc == APUS_OK) rc = ring_flush(r);
+        if (rc != APUS_OK) { free(buf); return rc == APUS_RETRY ? rc : fail("closed loop: submit failed"); }
+        const uint64_t ticket = r->submitted;
+        uint32_t spins = 0;
+        while (r->hw->committed_tickets < ticket) {
+            if ((++spins & 0xffffff) == 0) {
+                clock_gettime(CLOCK_MONOTONIC, &t1);
+                if (t1.tv_sec - t0.tv_sec > 10 || r->hw->error) { free(buf); return fail("closed loop: commit timeout"); }
+            }
+        }
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        int64_t ns = (t1.tv_sec - t0.tv_sec) * 1000000000ll + (t1.tv_nsec - t0.tv_nsec);
+        lat_ns[i] = ns > 0xffffffffll ? 0xffffffffu : (uint32_t)ns;
+    }
+    free(buf);
     return APUS_OK;
 }
 

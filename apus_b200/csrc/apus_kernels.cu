@@ -9,21 +9,23 @@
  *            (dare_log.h:466-558) + persist_new_entries' sender stamp
  *            (dare_server.c:1803-1804) + update_remote_logs step I/II
  *            (dare_ibv_rc.c:1526-1573: byte range then tail) + the commit rule
- *            (dare_ibv_rc.c:1725-1758) + the commit publish (:1760-1822).
+ *            (dare_ibv_rc.c:1725-1758) + the commit publish (:1760-1822) +
+ *            log pruning (dare_server.c:1996-2122).
  *            15 producer warps build a TILE of entries in shared memory and push
  *            it with 16 B vector stores into the local log and into every
  *            follower's log over NVLink; warp 15 is the commit warp: lane i
- *            polls follower i's ack word and a shuffle/ballot ranks the acks to
- *            find the offset a majority holds.
+ *            polls follower i's ack word and a shuffle ranking of the acks finds
+ *            the count a majority holds.
  *   FOLLOWER persist_new_entries' follower branch (dare_server.c:1792-1810) +
- *            rc_send_entries_reply (dare_ibv_rc.c:1828-1863): poll `end`, walk
- *            the new entries, set reply[me] locally and in the leader's copy,
- *            publish the ack word, follow `commit`.
+ *            rc_send_entries_reply (dare_ibv_rc.c:1828-1863): poll the tail
+ *            publish, walk the new entries, set reply[me] locally and in the
+ *            leader's copy, publish the ack word, follow `commit`, adopt `head`
+ *            from committed HEAD entries (dare_server.c:2163-2186).
  *
  * Ordering (invariant I1, "data before tail"): all data stores of a tile ->
- * bar.sync -> fence.acq_rel.sys -> st.relaxed.sys of `end`.  The follower reads
- * `end` with ld.acquire.sys and the entry bytes with ld.relaxed.sys (never
- * through a stale L1 line).  Acks mirror this in the other direction.
+ * bar.sync -> fence.acq_rel.sys -> 16 B st.relaxed.sys of {end, count}.  The
+ * follower reads the pair, fences, and reads the entry bytes with ld.relaxed.sys
+ * (never through a stale L1 line).  Acks mirror this in the other direction.
  *
  * Pure integer / byte work: no tensor cores, bound by NVLink store bandwidth and
  * by launch-free round-trip latency.
@@ -54,9 +56,17 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys_u32(const volatile void *p)
     asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void ld_relaxed_sys_2x64(const volatile void *p, uint64_t &a, uint64_t &b)
+{
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void st_relaxed_sys(volatile void *p, uint64_t v)
 {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_2x64(volatile void *p, uint64_t a, uint64_t b)
+{
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ void st_relaxed_sys_u8(volatile void *p, uint8_t v)
 {
@@ -109,6 +119,10 @@ __device__ __forceinline__ uint32_t entry_stride(uint32_t type, uint32_t len)
 {
     return has_cmd(type) ? APUS_HDR_BYTES + len : APUS_HDR_BYTES;   // dare_log.h:228-234
 }
+__device__ __forceinline__ uint64_t ring_dist(uint64_t from, uint64_t to, uint64_t L)
+{
+    return to >= from ? to - from : L - (from - to);
+}
 
 #define WATCHDOG_NS (20ull * 1000ull * 1000ull * 1000ull)
 
@@ -117,33 +131,33 @@ __device__ __forceinline__ uint32_t entry_stride(uint32_t type, uint32_t len)
 #define APUS_KERR_WATCHDOG_FOLLOWER 2
 #define APUS_KERR_WATCHDOG_COMMIT   3
 #define APUS_KERR_BAD_ENTRY         4
+#define APUS_KERR_COUNT_MISMATCH    5
 
 // ---------------------------------------------------------------------------------
 // shared memory
 // ---------------------------------------------------------------------------------
 #define PUB_RING 256u
 #define N_PRODUCER_WARPS 15
-#define N_PRODUCER_THREADS (N_PRODUCER_WARPS * 32)
+#define NT (N_PRODUCER_WARPS * 32)      // producer threads
+#define MAXB APUS_MAX_TILE_ENTRIES
 
 struct LeaderShared {
     // tile table (one row per entry of the tile)
-    uint64_t req_id[APUS_MAX_TILE_ENTRIES];
-    uint32_t pay_off[APUS_MAX_TILE_ENTRIES];   // 16 B units into the payload ring
-    uint32_t rel[APUS_MAX_TILE_ENTRIES];       // entry start - tile start (bytes)
-    uint16_t len[APUS_MAX_TILE_ENTRIES];
-    uint16_t clt[APUS_MAX_TILE_ENTRIES];
-    uint8_t  type[APUS_MAX_TILE_ENTRIES];
+    uint32_t rel[MAXB];        // entry start - tile start (bytes)
+    uint32_t xoff[MAXB];       // offset of the entry's image in the ext staging (EXT entries)
     // tile control (written by thread 0 / warp 0, read by all producers)
-    uint32_t n_fetch;        // descriptors fetched this round
-    uint32_t m;              // entries in the tile
-    uint32_t gap;            // 1: wrap-gap tile (range [a, len), optional ghost of entry 0)
-    uint32_t ghost;          // 1: ghost header is composed at a
-    uint32_t fresh;          // 1: the range was never written (holes are zero)
-    uint32_t finish;         // producers are done
-    uint32_t auto_head;      // 1: the tile starts with a HEAD entry appended by the pruning rule
-    uint64_t auto_head_val;  // ... carrying this head offset
-    uint64_t a, b;           // byte range of the tile in the log
-    uint64_t idx0;           // idx of the tile's first entry
+    uint32_t n_fetch;          // slots fetched this round
+    uint32_t m;                // entries in the tile
+    uint32_t gap;              // 1: wrap-gap tile (range [a, len), optional ghost of entry 0)
+    uint32_t ghost;            // 1: ghost header is composed at a
+    uint32_t fresh;            // 1: the range was never written (holes are zero)
+    uint32_t finish;           // producers are done
+    uint32_t auto_head;        // 1: the tile starts with a HEAD entry appended by the pruning rule
+    uint32_t ext_bytes;        // payload-ring bytes to stage for this tile
+    uint64_t ext_base;         // ... starting at this payload-ring offset
+    uint64_t auto_head_val;    // head offset carried by the auto HEAD entry
+    uint64_t a, b;             // byte range of the tile in the log
+    uint64_t idx0;             // idx of the tile's first entry
     uint64_t t_dequeue;
     uint8_t *peer_entries[APUS_MAX_SERVERS];
     // publishes in flight: producer -> commit warp
@@ -158,14 +172,22 @@ struct LeaderShared {
     volatile uint32_t abort_flag;
 };
 
+#define LS_BYTES ((sizeof(LeaderShared) + 127u) & ~127u)
+#define L_SLOTS_OFF LS_BYTES
+#define L_EXT_OFF   (L_SLOTS_OFF + MAXB * APUS_SLOT_BYTES)
+#define L_IMG_OFF   (L_EXT_OFF + APUS_LEADER_EXT_BYTES)
+#define L_TOTAL     (L_IMG_OFF + APUS_LEADER_IMG_BYTES + 16)
+
 struct FollowerShared {
-    uint32_t off[APUS_IMG_BYTES / 64 + 8];   // entry offsets found in the window (log offsets, low 32 bits)
+    uint32_t off[APUS_FOLLOWER_WIN_BYTES / 64 + 8];   // entry offsets found in the window (relative to win_lo)
     uint32_t n;
     uint32_t done;
     uint64_t win_lo, win_hi, next;           // window bounds in the log, next walk offset
     uint64_t head_val, head_end;             // last HEAD entry of the window (head_end == len: none)
-    uint64_t end_seen, commit_seen;
+    uint64_t end_seen, cum_seen, commit_seen;
 };
+#define FS_BYTES ((sizeof(FollowerShared) + 127u) & ~127u)
+#define F_TOTAL (FS_BYTES + APUS_FOLLOWER_WIN_BYTES + 16)
 
 extern __shared__ __align__(16) uint8_t smem_raw[];
 
@@ -186,28 +208,75 @@ __device__ __forceinline__ uint32_t hdr_byte(uint32_t j, uint64_t idx, uint64_t 
     return 0;   // reply[13]
 }
 
-// copy nbytes from a 16 B-aligned global source to an arbitrarily aligned smem destination
-__device__ __forceinline__ void warp_copy_to_smem(uint8_t *dst, const uint8_t *src, uint32_t nbytes, int lane)
+// bytes 0..40 of an entry header into shared memory at any alignment
+__device__ __forceinline__ void warp_write_header(uint8_t *e, int lane, uint64_t idx, uint64_t term, uint64_t req_id,
+                                                  uint32_t clt, uint32_t type, uint32_t sender, bool skip_sender)
 {
-    uint32_t nchunks = (nbytes + 15u) >> 4;
-    uint32_t dalign = (uint32_t)(uintptr_t)dst & 15u;
+    if ((((uint32_t)(uintptr_t)e) & 7u) == 0) {
+        // aligned entry: 8-byte stores for bytes 0..39, byte 40 separately; bytes 41..47 stay (hole)
+        if (lane == 0) *reinterpret_cast<uint64_t *>(e + 0) = idx;
+        else if (lane == 1) *reinterpret_cast<uint64_t *>(e + 8) = term;
+        else if (lane == 2) *reinterpret_cast<uint64_t *>(e + 16) = req_id;
+        else if (lane == 3) {
+            if (skip_sender) {
+                e[24] = (uint8_t)clt; e[25] = (uint8_t)(clt >> 8); e[26] = (uint8_t)type;
+                e[28] = 0; e[29] = 0; e[30] = 0; e[31] = 0;
+            } else {
+                *reinterpret_cast<uint64_t *>(e + 24) =
+                    (uint64_t)(clt & 0xffffu) | ((uint64_t)type << 16) | ((uint64_t)sender << 24);
+            }
+        } else if (lane == 4) *reinterpret_cast<uint64_t *>(e + 32) = 0;
+        else if (lane == 5) e[40] = 0;
+    } else {
+        for (uint32_t j = lane; j < 41; j += 32)
+            if (!(skip_sender && j == E_SENDER)) e[j] = (uint8_t)hdr_byte(j, idx, term, req_id, clt, type, sender);
+    }
+}
+
+// copy nbytes from a 16 B-aligned shared source to an arbitrarily aligned shared destination
+__device__ __forceinline__ void warp_copy_smem(uint8_t *dst, const uint8_t *src, uint32_t nbytes, int lane)
+{
+    const uint32_t nchunks = (nbytes + 15u) >> 4;
+    const uint32_t dalign = (uint32_t)(uintptr_t)dst & 15u;
     for (uint32_t c = lane; c < nchunks; c += 32) {
-        uint4 v = ld_relaxed_sys_v4(src + 16u * c);
+        const uint4 v = *reinterpret_cast<const uint4 *>(src + 16u * c);
         uint8_t *d = dst + 16u * c;
-        uint32_t left = nbytes - 16u * c;
+        const uint32_t left = nbytes - 16u * c;
         if (dalign == 0 && left >= 16) {
             *reinterpret_cast<uint4 *>(d) = v;
         } else if ((dalign & 3u) == 0 && left >= 16) {
             uint32_t *d4 = reinterpret_cast<uint32_t *>(d);
             d4[0] = v.x; d4[1] = v.y; d4[2] = v.z; d4[3] = v.w;
+        } else if ((dalign & 1u) == 0 && left >= 16) {
+            uint16_t *d2 = reinterpret_cast<uint16_t *>(d);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 8; k++) d2[k] = (uint16_t)(w[k >> 1] >> (16 * (k & 1)));
         } else {
-            uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t nb = left < 16 ? left : 16;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t nb = left < 16 ? left : 16;
 #pragma unroll
             for (uint32_t k = 0; k < 16; k++)
                 if (k < nb) d[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
         }
     }
+}
+
+// global (16 B aligned) -> shared, nchunks 16 B chunks, by all producer threads, 4 loads in flight each
+__device__ __forceinline__ void cta_fetch_chunks(uint8_t *dst, const uint8_t *src, uint32_t nchunks, int tid)
+{
+    uint32_t c = tid;
+    for (; c + 3u * NT < nchunks; c += 4u * NT) {
+        const uint4 v0 = ld_relaxed_sys_v4(src + 16ull * c);
+        const uint4 v1 = ld_relaxed_sys_v4(src + 16ull * (c + NT));
+        const uint4 v2 = ld_relaxed_sys_v4(src + 16ull * (c + 2u * NT));
+        const uint4 v3 = ld_relaxed_sys_v4(src + 16ull * (c + 3u * NT));
+        reinterpret_cast<uint4 *>(dst)[c] = v0;
+        reinterpret_cast<uint4 *>(dst)[c + NT] = v1;
+        reinterpret_cast<uint4 *>(dst)[c + 2u * NT] = v2;
+        reinterpret_cast<uint4 *>(dst)[c + 3u * NT] = v3;
+    }
+    for (; c < nchunks; c += NT) reinterpret_cast<uint4 *>(dst)[c] = ld_relaxed_sys_v4(src + 16ull * c);
 }
 
 __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx, LeaderShared *S)
@@ -254,7 +323,7 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx, LeaderS
                 off = S->pub_end[tail & (PUB_RING - 1)];
                 tickets = S->pub_tickets[tail & (PUB_RING - 1)];
                 t0 = S->pub_t0[tail & (PUB_RING - 1)];
-                if ((cx->flags & 0x2u) && cx->lat_ns && lane == 0) {
+                if ((cx->flags & APUS_FLAG_STATS) && cx->lat_ns && lane == 0) {
                     uint64_t d = globaltimer_ns() - t0;
                     cx->lat_ns[lat_count & (APUS_LAT_RING - 1)] = d > 0xffffffffull ? 0xffffffffu : (uint32_t)d;
                 }
@@ -268,11 +337,10 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx, LeaderS
                 if (peer_commit) st_relaxed_sys(peer_commit, off);          // dare_ibv_rc.c:1810
                 if (lane == 0) {
                     hdr->commit = off;
-                    hdr->apply = off;                                       // leader applies = update_state
+                    st_relaxed_sys(&hdr->apply, off);                       // leader applies = update_state
                     ctrl->committed = committed;
                     ctrl->committed_tickets = tickets;
                     ctrl->lat_count = lat_count;
-                    __threadfence_system();
                     st_relaxed_sys(&hw->commit_off, off);
                     st_relaxed_sys(&hw->committed_tickets, tickets);        // releases proxy.c:160 spinners
                     S->pub_tail = tail;
@@ -314,7 +382,9 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx, LeaderS
 __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
 {
     LeaderShared *S = reinterpret_cast<LeaderShared *>(smem_raw);
-    uint8_t *img = smem_raw + ((sizeof(LeaderShared) + 127u) & ~127u);
+    uint8_t *slots = smem_raw + L_SLOTS_OFF;
+    uint8_t *ext = smem_raw + L_EXT_OFF;
+    uint8_t *img = smem_raw + L_IMG_OFF;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = cx->group_size, me = cx->idx;
     apus_ctrl_t *ctrl = reinterpret_cast<apus_ctrl_t *>(cx->region);
@@ -322,6 +392,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
     uint8_t *entries = cx->region + APUS_ENTRIES_OFF;
     apus_hostwords_t *hw = cx->hw;
     const uint64_t L = cx->log_len;
+    const bool autoprune = (cx->flags & APUS_FLAG_AUTOPRUNE) != 0;
 
     if (tid == 0) {
         S->pub_head = 0; S->pub_tail = 0;
@@ -344,13 +415,12 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
     }
 
     // ---- producer warps 0..14 ------------------------------------------------------
-    // thread-0 state mirrored in registers of every producer thread after each barrier
+    // state mirrored in registers of every producer thread (updated uniformly)
     uint64_t end = hdr->end, tailpos = hdr->tail, next_idx = ctrl->next_idx;
     uint64_t consumed = ctrl->consumed, published = ctrl->published, hwm = ctrl->hwm;
     uint64_t bytes_rep = ctrl->bytes_replicated, batches = ctrl->batches;
     uint64_t auto_heads = ctrl->auto_heads;
     uint64_t last_progress = globaltimer_ns();
-    bool pending_gap = false;   // a gap tile was stored and awaits the next publish
     bool prev_head = false;     // the last entry appended is a HEAD entry of the pruning rule
 
     for (;;) {
@@ -364,7 +434,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
                 if (avail) {
                     uint64_t room = cx->target - consumed;
                     if (avail > room) avail = room;
-                    n = avail > APUS_MAX_TILE_ENTRIES ? APUS_MAX_TILE_ENTRIES : (uint32_t)avail;
+                    n = avail > MAXB ? MAXB : (uint32_t)avail;
                     // do not overrun the in-flight publish ring
                     uint32_t w = 0;
                     while (S->pub_head - S->pub_tail >= PUB_RING - 2) {
@@ -382,48 +452,49 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
                     }
                 }
             }
-            if (n) __threadfence_system();   // acquire: descriptors + payload behind the doorbell
+            if (n) __threadfence_system();   // acquire: slots + payload behind the doorbell
             S->n_fetch = n; S->finish = fin;
             S->t_dequeue = globaltimer_ns();
         }
-        bar_sync(1, N_PRODUCER_THREADS);
+        bar_sync(1, NT);
         if (S->finish) break;
         const uint32_t nf = S->n_fetch;
 
-        // ---- T1: fetch descriptors (coalesced 16 B loads) ----------------------------
-        for (uint32_t k = tid; k < nf; k += N_PRODUCER_THREADS) {
-            uint4 d = ld_relaxed_sys_v4(&cx->sub_desc[(consumed + k) & cx->sub_mask]);
-            S->req_id[k] = (uint64_t)d.x | ((uint64_t)d.y << 32);
-            S->type[k] = (uint8_t)(d.z >> 24);
-            S->pay_off[k] = d.z & 0x00ffffffu;
-            S->len[k] = (uint16_t)(d.w & 0xffffu);
-            S->clt[k] = (uint16_t)(d.w >> 16);
+        // ---- T1: fetch the slots (descriptor + inline payload), coalesced 16 B loads --------
+        {
+            const uint64_t s0 = consumed & cx->sub_mask;
+            const uint64_t nslots = (uint64_t)cx->sub_mask + 1;
+            const uint32_t first = (s0 + nf <= nslots) ? nf : (uint32_t)(nslots - s0);   // ring wrap: two runs
+            cta_fetch_chunks(slots, reinterpret_cast<const uint8_t *>(cx->sub_slots + s0), first * 8u, tid);
+            if (first < nf)
+                cta_fetch_chunks(slots + (size_t)first * APUS_SLOT_BYTES, reinterpret_cast<const uint8_t *>(cx->sub_slots),
+                                 (nf - first) * 8u, tid);
         }
-        bar_sync(1, N_PRODUCER_THREADS);
+        bar_sync(1, NT);
+        const apus_slot_t *sl = reinterpret_cast<const apus_slot_t *>(slots);
 
         // ---- T2: placement (warp 0): log_append_entry's offset rules over the tile ----
         if (warp == 0) {
             uint64_t head = ld_relaxed_sys(&hdr->head);
             const uint64_t pos0 = (end == L) ? 0 : end;               // empty log starts at 0 (dare_log.h:216-219)
-            uint64_t used = (end == L) ? 0 : (end >= head ? end - head : L - (head - end));
+            uint64_t used = (end == L) ? 0 : ring_dist(head, end, L);
             // ---- device-side log pruning (log_pruning / force_log_pruning,
             //      dare_server.c:1996-2122): head := the smallest apply offset in the group,
             //      published through a HEAD entry placed in front of this tile
             uint32_t autoh = 0;
             uint64_t new_head = 0;
-            if ((cx->flags & APUS_FLAG_AUTOPRUNE) && end != L && used >= (L >> 2) && !prev_head &&
-                L - pos0 >= APUS_HDR_BYTES) {
+            if (autoprune && end != L && used >= (L >> 2) && !prev_head && L - pos0 >= APUS_HDR_BYTES) {
                 uint64_t d = 0;                                   // distance apply -> end, per replica
                 if (lane < N) {
                     const uint64_t ap = (lane == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[lane]);
-                    d = (end >= ap) ? end - ap : L - (ap - end);
+                    d = ring_dist(ap, end, L);
                     if (d > used) d = used;                       // never behind the current head
                 }
                 for (int sft = 16; sft > 0; sft >>= 1) {
                     const uint64_t o = __shfl_xor_sync(0xffffffffu, d, sft);
                     d = o > d ? o : d;
                 }
-                if (d == 0) d = (end >= tailpos) ? end - tailpos : L - (tailpos - end);   // leave one entry (:2031-2034)
+                if (d == 0) d = ring_dist(tailpos, end, L);       // leave one entry (dare_server.c:2031-2034)
                 if (d <= used && used - d >= (L >> 3)) {
                     autoh = 1;
                     new_head = (end >= d) ? end - d : L - (d - end);
@@ -434,62 +505,107 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
             const uint64_t hbytes = autoh ? APUS_HDR_BYTES : 0;
             // limits for a contiguous tile starting at pos0
             uint64_t lim = L - pos0;                                   // no entry may cross len
-            const uint64_t imgcap = APUS_IMG_BYTES - 16u - (pos0 & 15u);
+            const uint64_t imgcap = APUS_LEADER_IMG_BYTES - 16u - (pos0 & 15u);
             if (lim > imgcap) lim = imgcap;
             // rule E2: stay strictly before head (keep room for one HEAD entry when pruning on the device)
-            const uint64_t reserve = (cx->flags & APUS_FLAG_AUTOPRUNE) ? APUS_HDR_BYTES : 0;
+            const uint64_t reserve = autoprune ? APUS_HDR_BYTES : 0;
             const uint64_t lim_space = (L - used > 1 + reserve) ? (L - used - 1 - reserve) : 0;
-            // per-lane strip of entries, two-level exclusive scan of strides
+            // per-lane strip of entries; exclusive scans of log strides and of staged payload bytes
             const uint32_t per = (nf + 31u) / 32u;
             const uint32_t k0 = lane * per, k1 = (k0 + per < nf) ? k0 + per : nf;
-            uint32_t sum = 0;
-            for (uint32_t k = k0; k < k1; k++) sum += entry_stride(S->type[k], S->len[k]);
-            uint32_t incl = sum;
-            for (int sft = 1; sft < 32; sft <<= 1) {
-                uint32_t o = __shfl_up_sync(0xffffffffu, incl, sft);
-                if (lane >= sft) incl += o;
+            uint32_t sum = 0, xsum = 0;
+            for (uint32_t k = k0; k < k1; k++) {
+                const uint32_t to = sl[k].type_off, ty = (to >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
+                sum += entry_stride(ty, sl[k].len);
+                if (to & APUS_SLOT_EXT) xsum += (data_bytes(ty, sl[k].len) + 15u) & ~15u;
             }
-            uint64_t run = hbytes + (incl - sum);   // bytes before my strip (behind the optional HEAD entry)
+            uint32_t incl = sum, xincl = xsum;
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, sft);
+                const uint32_t xo = __shfl_up_sync(0xffffffffu, xincl, sft);
+                if (lane >= sft) { incl += o; xincl += xo; }
+            }
+            uint64_t run = hbytes + (incl - sum);   // log bytes before my strip (behind the optional HEAD entry)
+            uint32_t xrun = xincl - xsum;           // staged payload bytes before my strip
             uint32_t first_bad = nf;
             for (uint32_t k = k0; k < k1; k++) {
-                uint32_t es = entry_stride(S->type[k], S->len[k]);
+                const uint32_t to = sl[k].type_off, ty = (to >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
+                const uint32_t es = entry_stride(ty, sl[k].len);
+                const uint32_t xb = (to & APUS_SLOT_EXT) ? ((data_bytes(ty, sl[k].len) + 15u) & ~15u) : 0u;
                 S->rel[k] = (uint32_t)run;
-                if (first_bad == nf && (run + es > lim || run + es > lim_space)) first_bad = k;
-                run += es;
+                S->xoff[k] = xrun;
+                if (first_bad == nf &&
+                    (run + es > lim || run + es > lim_space || xrun + xb > APUS_LEADER_EXT_BYTES ||
+                     (k > 0 && (to & APUS_SLOT_WRAP))))
+                    first_bad = k;
+                run += es; xrun += xb;
             }
             for (int sft = 16; sft > 0; sft >>= 1) {
-                uint32_t o = __shfl_xor_sync(0xffffffffu, first_bad, sft);
+                const uint32_t o = __shfl_xor_sync(0xffffffffu, first_bad, sft);
                 first_bad = o < first_bad ? o : first_bad;
             }
+            const uint32_t m = first_bad;
+            __syncwarp();
+            // staged payload range of the tile: images of consecutive tickets are contiguous in the ring
+            uint32_t ext_total = 0;
+            uint64_t ext_base = 0;
+            {
+                uint32_t f = 0xffffffffu, e = 0;
+                for (uint32_t k = k0; k < k1 && k < m; k++) {
+                    const uint32_t to = sl[k].type_off;
+                    if (to & APUS_SLOT_EXT) {
+                        const uint32_t ty = (to >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
+                        if (f == 0xffffffffu) f = k;
+                        e = S->xoff[k] + ((data_bytes(ty, sl[k].len) + 15u) & ~15u);
+                    }
+                }
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    const uint32_t of = __shfl_xor_sync(0xffffffffu, f, sft);
+                    const uint32_t oe = __shfl_xor_sync(0xffffffffu, e, sft);
+                    f = of < f ? of : f; e = oe > e ? oe : e;
+                }
+                if (f != 0xffffffffu) {
+                    ext_base = (uint64_t)(sl[f].type_off & APUS_SLOT_OFF_MASK) * 16ull;
+                    ext_total = e - S->xoff[f];
+                }
+                // staging offsets are relative to the first staged image
+                if (f != 0xffffffffu && S->xoff[f] != 0) {
+                    const uint32_t base = S->xoff[f];
+                    __syncwarp();
+                    for (uint32_t k = k0; k < k1 && k < m; k++) S->xoff[k] -= base;
+                }
+            }
             if (lane == 0) {
-                uint32_t m = first_bad;
                 S->gap = 0; S->ghost = 0;
                 if (m == 0 && !autoh) {
                     // entry 0 does not fit at pos0: wrap (dare_log.h:502-504, 526-538) or no space
-                    const uint32_t es0 = entry_stride(S->type[0], S->len[0]);
+                    const uint32_t ty0 = (sl[0].type_off >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
+                    const uint32_t es0 = entry_stride(ty0, sl[0].len);
                     const uint64_t left = L - pos0;
                     if (es0 > left && used + left + es0 + reserve < L) {
                         S->gap = 1;
-                        S->ghost = (left >= APUS_HDR_BYTES && has_cmd(S->type[0])) ? 1u : 0u;   // header fits: ghost stays behind
+                        S->ghost = (left >= APUS_HDR_BYTES && has_cmd(ty0)) ? 1u : 0u;   // header fits: ghost stays behind
                         S->a = pos0; S->b = L;
                     } else {
                         S->a = S->b = pos0;   // back-pressure: wait for head to advance
                     }
                 } else {
+                    const uint32_t tyl = m ? (sl[m - 1].type_off >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK : 0;
                     S->a = pos0;
-                    S->b = pos0 + (m ? S->rel[m - 1] + entry_stride(S->type[m - 1], S->len[m - 1]) : hbytes);
+                    S->b = pos0 + (m ? S->rel[m - 1] + entry_stride(tyl, sl[m - 1].len) : hbytes);
                 }
                 S->m = m;
+                S->ext_bytes = ext_total; S->ext_base = ext_base;
                 S->auto_head = autoh; S->auto_head_val = new_head;
                 if (autoh) st_relaxed_sys(&hdr->head, new_head);
                 S->idx0 = next_idx;
                 S->fresh = (S->a >= hwm) ? 1u : 0u;
             }
         }
-        bar_sync(1, N_PRODUCER_THREADS);
+        bar_sync(1, NT);
         const uint32_t m = S->m, gap = S->gap;
         const uint64_t a = S->a, b = S->b;
-        if (a == b) {   // no space before head: poll again (stop / watchdog handled in T0)
+        if (a == b) {   // no space before head: poll again
             if (tid == 0) {
                 if (ld_relaxed_sys_u32(&hw->stop) || S->abort_flag) S->finish = 1;
                 else if (cx->target != ~0ull && globaltimer_ns() - last_progress > WATCHDOG_NS) {
@@ -497,59 +613,56 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
                     S->abort_flag = 1; S->finish = 1;
                 }
             }
-            bar_sync(1, N_PRODUCER_THREADS);
+            bar_sync(1, NT);
             if (S->finish) break;
             continue;
         }
         const uint64_t a16 = a & ~15ull;
         const uint32_t nchunks = (uint32_t)(((b + 15ull) & ~15ull) - a16) >> 4;
 
-        // ---- T3: prefill the image: zeros when the range is fresh, else the bytes the
-        //      local log holds (holes of an entry keep what was there, like the reference)
+        // ---- T3: prefill the image (zeros when the range is fresh, else the bytes the local
+        //      log holds: holes of an entry keep what was there, like the reference) and
+        //      stage the payload-ring range of the tile; all loads in flight together
         if (S->fresh) {
-            for (uint32_t c = tid; c < nchunks; c += N_PRODUCER_THREADS)
-                reinterpret_cast<uint4 *>(img)[c] = make_uint4(0, 0, 0, 0);
+            for (uint32_t c = tid; c < nchunks; c += NT) reinterpret_cast<uint4 *>(img)[c] = make_uint4(0, 0, 0, 0);
         } else {
-            for (uint32_t c = tid; c < nchunks; c += N_PRODUCER_THREADS)
-                reinterpret_cast<uint4 *>(img)[c] = ld_relaxed_sys_v4(entries + a16 + 16ull * c);
+            cta_fetch_chunks(img, entries + a16, nchunks, tid);
         }
-        bar_sync(1, N_PRODUCER_THREADS);
+        if (!gap && S->ext_bytes) cta_fetch_chunks(ext, cx->sub_pay + S->ext_base, S->ext_bytes >> 4, tid);
+        bar_sync(1, NT);
 
         // ---- T4: compose entries into the image -----------------------------------------
         if (gap) {
             if (S->ghost && warp == 0) {
                 // header of entry 0 without payload, sender untouched (dare_log.h:496-503, 521)
                 uint8_t *e = img + (a - a16);
-                const uint32_t ty = S->type[0];
-                for (uint32_t j = lane; j < 41; j += 32)
-                    if (j != E_SENDER)
-                        e[j] = (uint8_t)hdr_byte(j, next_idx, cx->term, S->req_id[0], S->clt[0], ty, 0);
-                if (lane == 0) { e[E_DATA] = (uint8_t)(S->len[0] & 0xff); e[E_DATA + 1] = (uint8_t)(S->len[0] >> 8); }
+                const uint32_t ty0 = (sl[0].type_off >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
+                warp_write_header(e, lane, next_idx, cx->term, sl[0].req_id, sl[0].clt_id, ty0, 0, true);
+                if (lane == 8) { e[E_DATA] = (uint8_t)(sl[0].len & 0xff); e[E_DATA + 1] = (uint8_t)(sl[0].len >> 8); }
             }
         } else {
             const uint32_t autoh = S->auto_head;
             if (autoh && warp == N_PRODUCER_WARPS - 1) {
                 // <HEAD, head_offset> entry (dare_log.h:29-32, dare_server.c:2043-2046)
                 uint8_t *e = img + (a - a16);
-                for (uint32_t j = lane; j < 41; j += 32)
-                    e[j] = (uint8_t)hdr_byte(j, S->idx0, cx->term, 0, 0, T_HEAD, me);
-                if (lane < 8) e[E_DATA + lane] = (uint8_t)(S->auto_head_val >> (8 * lane));
+                warp_write_header(e, lane, S->idx0, cx->term, 0, 0, T_HEAD, me, false);
+                if (lane >= 8 && lane < 16) e[E_DATA + lane - 8] = (uint8_t)(S->auto_head_val >> (8 * (lane - 8)));
             }
             for (uint32_t k = warp; k < m; k += N_PRODUCER_WARPS) {
                 uint8_t *e = img + (a - a16) + S->rel[k];
-                const uint32_t ty = S->type[k], ln = S->len[k];
-                const uint64_t rq = S->req_id[k];
-                const uint32_t cl = S->clt[k];
-                for (uint32_t j = lane; j < 41; j += 32)
-                    e[j] = (uint8_t)hdr_byte(j, S->idx0 + autoh + k, cx->term, rq, cl, ty, me);
-                const uint32_t nb = data_bytes(ty, ln);
-                if (nb) warp_copy_to_smem(e + E_DATA, cx->sub_pay + 16ull * S->pay_off[k], nb, lane);
+                const uint32_t to = sl[k].type_off, ty = (to >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
+                warp_write_header(e, lane, S->idx0 + autoh + k, cx->term, sl[k].req_id, sl[k].clt_id, ty, me, false);
+                const uint32_t nb = data_bytes(ty, sl[k].len);
+                if (nb) {
+                    const uint8_t *src = (to & APUS_SLOT_EXT) ? ext + S->xoff[k] : sl[k].inl;
+                    warp_copy_smem(e + E_DATA, src, nb, lane);
+                }
             }
         }
-        bar_sync(1, N_PRODUCER_THREADS);
+        bar_sync(1, NT);
 
         // ---- T5: push the byte range [a,b) to the local log and to every follower ------
-        for (uint32_t c = tid; c < nchunks; c += N_PRODUCER_THREADS) {
+        for (uint32_t c = tid; c < nchunks; c += NT) {
             const uint64_t lo = a16 + 16ull * c;
             const uint4 v = reinterpret_cast<const uint4 *>(img)[c];
             if (lo >= a && lo + 16 <= b) {
@@ -569,16 +682,15 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
                 }
             }
         }
-        bar_sync(1, N_PRODUCER_THREADS);
+        bar_sync(1, NT);
 
         // ---- T6: bookkeeping + publish the tail (data before tail, invariant I1) --------
         if (gap) {
             // nothing is published after a gap tile: the next tile (at offset 0) carries it
-            end = 0; hwm = L; pending_gap = true;
+            end = 0; hwm = L;
             bytes_rep += (b - a) * (uint64_t)(N - 1);
             if (tid == 0) { ctrl->hwm = hwm; ctrl->bytes_replicated = bytes_rep; }
-            // the entry that wrapped stays first in the ring: re-run placement from offset 0
-            // (descriptors are re-fetched; consumed is unchanged)
+            // the entry that wrapped stays first in the ring: placement re-runs from offset 0
             continue;
         }
         uint64_t new_end = b;
@@ -592,11 +704,11 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
         if (b > hwm) hwm = b;
         bytes_rep += (b - a) * (uint64_t)(N - 1);
         batches++;
-        pending_gap = false;
         if (warp == 0) {
             if (lane < N && lane != me && cx->peer[lane]) {
                 __threadfence_system();
-                st_relaxed_sys(&reinterpret_cast<apus_loghdr_t *>(cx->peer[lane] + APUS_CTRL_BYTES)->end, new_end);
+                apus_ctrl_t *pc = reinterpret_cast<apus_ctrl_t *>(cx->peer[lane]);
+                st_relaxed_sys_2x64(&pc->pub_end, new_end, published);
             }
             if (lane == 0) {
                 hdr->end = new_end; hdr->tail = tailpos; hdr->old_end = new_end;
@@ -616,22 +728,16 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
         }
         last_progress = globaltimer_ns();
     }
-    (void)pending_gap;
     if (tid == 0) { __threadfence_block(); S->producers_done = 1; }
 }
 
 // ---------------------------------------------------------------------------------
 // FOLLOWER
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t ring_dist(uint64_t from, uint64_t to, uint64_t L)
-{
-    return to >= from ? to - from : L - (from - to);
-}
-
 __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
 {
     FollowerShared *S = reinterpret_cast<FollowerShared *>(smem_raw);
-    uint8_t *win = smem_raw + ((sizeof(FollowerShared) + 127u) & ~127u);
+    uint8_t *win = smem_raw + FS_BYTES;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int me = cx->idx, ldr = cx->leader_idx;
     apus_ctrl_t *ctrl = reinterpret_cast<apus_ctrl_t *>(cx->region);
@@ -645,7 +751,7 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
     const bool fenced = (cx->flags & APUS_FLAG_FENCED_ACK) != 0;
 
     uint64_t old_end = hdr->old_end;     // walk position (dare_server.c:1795)
-    uint64_t acked = ctrl->acked;
+    uint64_t acked = ctrl->acked;        // entries walked (reply byte set) so far
     uint64_t applied = hdr->apply;       // apply offset (== commit as far as I hold the entries)
     uint64_t pend_val = ctrl->pend_head_val, pend_end = ctrl->pend_head_end;
     uint64_t last_progress = globaltimer_ns();
@@ -653,19 +759,19 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
 
     for (;;) {
         if (tid == 0) {
-            uint64_t e, c;
+            uint64_t e, cum, c;
             uint32_t done = 0;
             for (;;) {
-                e = ld_acquire_sys(&hdr->end);
+                ld_relaxed_sys_2x64(&ctrl->pub_end, e, cum);        // {end, entries} written as one 16 B store
                 c = ld_relaxed_sys(&hdr->commit);
-                const bool new_entries = (e != L) && (e != old_end);
+                const bool new_entries = cum > acked;
                 // commit moved, and I hold entries beyond what I applied
                 const bool new_commit = (c != applied) && (old_end != L) && (applied != old_end);
-                if (new_entries || new_commit) break;
+                if (new_entries || new_commit) { __threadfence_system(); break; }   // acquire
                 // bounded launch: the leader says how many entries exist in total
                 if (cx->target != ~0ull && ld_acquire_sys(&ctrl->fin_target) == cx->target) {
                     const uint64_t fe = ld_relaxed_sys(&ctrl->fin_entries);
-                    if (acked >= fe && (e == L || (applied == old_end && c == old_end))) { done = 1; break; }
+                    if (acked >= fe && (old_end == L || (applied == old_end && c == old_end))) { done = 1; break; }
                 }
                 if ((++spins & 0xffu) == 0) {
                     if (ld_relaxed_sys_u32(&hw->stop)) { done = 1; break; }
@@ -675,83 +781,107 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
                     }
                 }
             }
-            S->end_seen = e; S->commit_seen = c; S->done = done;
+            // early ack: the tail publish was observed and fenced, so every entry up to it is
+            // resident and visible here (invariant I2); the reply bytes follow behind the
+            // ack word unless APUS_F_FENCED_ACK asks for them first
+            if (!done && !fenced && cum > acked) st_relaxed_sys(&lctrl->ack[me], cum);
+            S->end_seen = e; S->cum_seen = cum; S->commit_seen = c; S->done = done;
         }
         __syncthreads();
         if (S->done) break;
-        const uint64_t end_seen = S->end_seen, commit_seen = S->commit_seen;
+        const uint64_t end_seen = S->end_seen, cum_seen = S->cum_seen, commit_seen = S->commit_seen;
 
         // ---- persist + ack every new entry in [old_end, end_seen) -----------------------
-        while (end_seen != L && old_end != end_seen) {
-            // window: contiguous bytes from old_end up to end_seen or the end of the ring
-            if (tid == 0) {
-                uint64_t lo = old_end;
-                if (L - lo < APUS_HDR_BYTES) lo = 0;                 // log_get_entry: header does not fit -> 0
-                uint64_t hi = (end_seen > lo) ? end_seen : L;       // wrapped: first run to the ring's end
-                if (lo == end_seen) hi = lo;
-                if (hi - (lo & ~15ull) > APUS_IMG_BYTES) hi = (lo & ~15ull) + APUS_IMG_BYTES;
-                S->win_lo = lo; S->win_hi = hi;
-            }
-            __syncthreads();
-            const uint64_t lo = S->win_lo, hi = S->win_hi;
-            if (lo == hi) { old_end = lo; break; }
-            const uint64_t lo16 = lo & ~15ull;
-            const uint32_t nch = (uint32_t)(((hi + 15ull) & ~15ull) - lo16) >> 4;
-            for (uint32_t c = tid; c < nch; c += nthr)
-                reinterpret_cast<uint4 *>(win)[c] = ld_relaxed_sys_v4(entries + lo16 + 16ull * c);
-            __syncthreads();
-            // serial walk over headers in shared memory (log_get_entry / log_fit_entry / log_entry_len)
-            if (tid == 0) {
-                uint64_t off = lo;
-                uint32_t n = 0;
-                uint64_t next = off;
-                bool wrapped = false;
-                uint64_t hv = 0, he = L;
-                while (off < hi) {
-                    if (L - off < APUS_HDR_BYTES) { next = 0; wrapped = true; break; }   // jump to 0
-                    if (hi - off < APUS_HDR_BYTES) { next = off; break; }                // header not in window yet
-                    const uint8_t *e = win + (off - lo16);
-                    const uint32_t ty = e[E_TYPE];
-                    const uint32_t ln = (uint32_t)e[E_DATA] | ((uint32_t)e[E_DATA + 1] << 8);
-                    const uint32_t es = entry_stride(ty, ln);
-                    if (L - off < es) { next = 0; wrapped = true; break; }              // ghost: entry continues at 0
-                    if (off + es > hi) { next = off; break; }                            // entry crosses the window
-                    if (ty == T_HEAD) {                                                  // poll_config_entries (dare_server.c:2163-2170)
-                        hv = 0;
-                        for (int q = 7; q >= 0; q--) hv = (hv << 8) | e[E_DATA + q];
-                        he = (off + es == L) ? 0 : off + es;
-                    }
-                    S->off[n++] = (uint32_t)(off - lo);
-                    off += es;
-                    next = off;
+        if (cum_seen > acked) {
+            uint64_t walked = 0;
+            while (old_end != end_seen) {
+                // window: contiguous bytes from old_end up to end_seen or the end of the ring
+                if (tid == 0) {
+                    uint64_t lo = (old_end == L) ? 0 : old_end;
+                    if (L - lo < APUS_HDR_BYTES) lo = 0;                 // log_get_entry: header does not fit -> 0
+                    uint64_t hi = (end_seen > lo) ? end_seen : L;       // wrapped: first run to the ring's end
+                    if (lo == end_seen) hi = lo;
+                    if (hi - (lo & ~15ull) > APUS_FOLLOWER_WIN_BYTES) hi = (lo & ~15ull) + APUS_FOLLOWER_WIN_BYTES;
+                    S->win_lo = lo; S->win_hi = hi;
                 }
-                if (!wrapped && next == L) next = 0;      // rule E1 on walker offsets
-                S->n = n; S->next = next;
-                S->head_val = hv; S->head_end = he;
+                __syncthreads();
+                const uint64_t lo = S->win_lo, hi = S->win_hi;
+                if (lo == hi) { old_end = lo; break; }
+                const uint64_t lo16 = lo & ~15ull;
+                const uint32_t nch = (uint32_t)(((hi + 15ull) & ~15ull) - lo16) >> 4;
+                {
+                    uint32_t c = tid;
+                    const uint8_t *src = entries + lo16;
+                    for (; c + 3u * nthr < nch; c += 4u * nthr) {
+                        const uint4 v0 = ld_relaxed_sys_v4(src + 16ull * c);
+                        const uint4 v1 = ld_relaxed_sys_v4(src + 16ull * (c + nthr));
+                        const uint4 v2 = ld_relaxed_sys_v4(src + 16ull * (c + 2u * nthr));
+                        const uint4 v3 = ld_relaxed_sys_v4(src + 16ull * (c + 3u * nthr));
+                        reinterpret_cast<uint4 *>(win)[c] = v0;
+                        reinterpret_cast<uint4 *>(win)[c + nthr] = v1;
+                        reinterpret_cast<uint4 *>(win)[c + 2u * nthr] = v2;
+                        reinterpret_cast<uint4 *>(win)[c + 3u * nthr] = v3;
+                    }
+                    for (; c < nch; c += nthr) reinterpret_cast<uint4 *>(win)[c] = ld_relaxed_sys_v4(src + 16ull * c);
+                }
+                __syncthreads();
+                // serial walk over headers in shared memory (log_get_entry / log_fit_entry / log_entry_len)
+                if (tid == 0) {
+                    uint64_t off = lo;
+                    uint32_t n = 0;
+                    uint64_t next = off;
+                    bool wrapped = false;
+                    uint64_t hv = 0, he = L;
+                    while (off < hi) {
+                        if (L - off < APUS_HDR_BYTES) { next = 0; wrapped = true; break; }   // jump to 0
+                        if (hi - off < APUS_HDR_BYTES) { next = off; break; }                // header not in window yet
+                        const uint8_t *e = win + (off - lo16);
+                        const uint32_t ty = e[E_TYPE];
+                        const uint32_t ln = (uint32_t)e[E_DATA] | ((uint32_t)e[E_DATA + 1] << 8);
+                        const uint32_t es = entry_stride(ty, ln);
+                        if (L - off < es) { next = 0; wrapped = true; break; }              // ghost: entry continues at 0
+                        if (off + es > hi) { next = off; break; }                            // entry crosses the window
+                        if (ty == T_HEAD) {                                                  // poll_config_entries (dare_server.c:2163-2170)
+                            hv = 0;
+                            for (int q = 7; q >= 0; q--) hv = (hv << 8) | e[E_DATA + q];
+                            he = (off + es == L) ? 0 : off + es;
+                        }
+                        S->off[n++] = (uint32_t)(off - lo);
+                        off += es;
+                        next = off;
+                    }
+                    if (!wrapped && next == L) next = 0;      // rule E1 on walker offsets
+                    S->n = n; S->next = next;
+                    S->head_val = hv; S->head_end = he;
+                }
+                __syncthreads();
+                const uint32_t n = S->n;
+                // reply[me] = 1 in my copy and in the leader's copy (dare_ibv_rc.c:1833-1854)
+                for (uint32_t k = tid; k < n; k += nthr) {
+                    const uint64_t at = lo + S->off[k] + E_REPLY + (uint64_t)me;
+                    st_relaxed_sys_u8(entries + at, 1);
+                    st_relaxed_sys_u8(lentries + at, 1);
+                }
+                __syncthreads();
+                const uint64_t next = S->next;
+                if (n == 0 && next == old_end) {
+                    // no progress possible inside this window: protocol error
+                    if (tid == 0) st_relaxed_sys(&hw->error, APUS_KERR_BAD_ENTRY);
+                    old_end = end_seen;
+                    break;
+                }
+                if (S->head_end != L) { pend_val = S->head_val; pend_end = S->head_end; }
+                walked += n;
+                old_end = next;
             }
-            __syncthreads();
-            const uint32_t n = S->n;
-            // reply[me] = 1 in my copy and in the leader's copy (dare_ibv_rc.c:1833-1854)
-            for (uint32_t k = tid; k < n; k += nthr) {
-                const uint64_t at = lo + S->off[k] + E_REPLY + (uint64_t)me;
-                st_relaxed_sys_u8(entries + at, 1);
-                st_relaxed_sys_u8(lentries + at, 1);
-            }
-            __syncthreads();
-            const uint64_t next = S->next;
-            if (n == 0 && next == old_end) {
-                // no progress possible inside this window: protocol error (entry larger than the window)
-                if (tid == 0) st_relaxed_sys(&hw->error, APUS_KERR_BAD_ENTRY);
-                old_end = end_seen;
-                break;
-            }
-            if (S->head_end != L) { pend_val = S->head_val; pend_end = S->head_end; }
-            acked += n;
-            old_end = next;
+            if (acked + walked != cum_seen && tid == 0) st_relaxed_sys(&hw->error, APUS_KERR_COUNT_MISMATCH);
+            acked = cum_seen;
             if (tid == 0) {
-                if (fenced) __threadfence_system();     // reply bytes before the ack word
-                st_relaxed_sys(&lctrl->ack[me], acked); // the word the leader's quorum ballot polls
-                hdr->old_end = old_end;
+                if (fenced) {
+                    __threadfence_system();                  // reply bytes before the ack word
+                    st_relaxed_sys(&lctrl->ack[me], acked);  // the word the leader's quorum ranking polls
+                }
+                hdr->end = end_seen; hdr->old_end = old_end;
                 ctrl->acked = acked;
                 ctrl->pend_head_val = pend_val; ctrl->pend_head_end = pend_end;
             }
@@ -760,16 +890,19 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
 
         // ---- follow the commit offset (invariant I4: never beyond what I hold) ----------
         if (old_end != L && applied != old_end && commit_seen != applied) {
-            const uint64_t from = (applied == L) ? 0 : applied;
-            const uint64_t held = ring_dist(from, old_end, L);          // entries I hold beyond `applied`
+            const uint64_t from = applied;
+            const uint64_t held = ring_dist(from, old_end, L);          // bytes I hold beyond `applied`
             uint64_t want = ring_dist(from, commit_seen, L);
             uint64_t to = commit_seen;
             if (want > held) { want = held; to = old_end; }             // the leader clamps the same way (dare_ibv_rc.c:1783-1787)
             if (want) {
-                if (pend_end != L && ring_dist(from, pend_end, L) <= want && ring_dist(from, pend_end, L) > 0) {
-                    // the HEAD entry is committed: adopt the head it carries (dare_server.c:2166-2169, 2182-2186)
-                    if (tid == 0) { hdr->head = pend_val; ctrl->pend_head_end = L; }
-                    pend_end = L;
+                if (pend_end != L) {
+                    const uint64_t dh = ring_dist(from, pend_end, L);
+                    if (dh > 0 && dh <= want) {
+                        // the HEAD entry is committed: adopt the head it carries (dare_server.c:2166-2169, 2182-2186)
+                        if (tid == 0) { hdr->head = pend_val; ctrl->pend_head_end = L; }
+                        pend_end = L;
+                    }
                 }
                 applied = to;
                 if (tid == 0) {
@@ -794,8 +927,7 @@ apus_replica_kernel(const apus_role_t *__restrict__ roles)
 
 extern "C" size_t apus_kernel_smem_bytes(void)
 {
-    size_t a = ((sizeof(LeaderShared) + 127u) & ~127u) + APUS_IMG_BYTES + 16;
-    size_t b = ((sizeof(FollowerShared) + 127u) & ~127u) + APUS_IMG_BYTES + 16;
+    size_t a = L_TOTAL, b = F_TOTAL;
     return a > b ? a : b;
 }
 

@@ -78,19 +78,33 @@ typedef struct apus_ctrl {
     uint64_t pend_head_val;      /* follower: head carried by the last HEAD entry seen ... */
     uint64_t pend_head_end;      /* ... and the offset right after that entry (len = none) */
     uint64_t pad0[3];
-    /* --- written by the LEADER into each follower's region at the end of a launch --- */
-    uint64_t fin_entries;        /* entries the leader has published in total */
-    uint64_t fin_target;         /* the launch (its ticket target) this refers to */
+    /* --- written by the LEADER into each follower's region --- */
+    uint64_t fin_entries;        /* end of a launch: entries the leader has published in total */
+    uint64_t fin_target;         /* ... and the launch (its ticket target) this refers to */
     uint64_t pad1[14];
+    uint64_t pub_end;            /* tail publish: the follower's new `end` (dare_ibv_rc.c:1549-1573) ... */
+    uint64_t pub_cum;            /* ... and the entries that exist up to it; one 16 B store */
+    uint64_t pad2[14];
 } apus_ctrl_t;
 
-/* submission descriptor, 16 B: the fields of tailq_entry_t (message.h:11-17) */
-typedef struct apus_desc {
+/* submission slot, 128 B: the fields of tailq_entry_t (message.h:11-17).  Requests
+ * whose data image (sm_cmd_t {u16 len; cmd[]}, dare_cid_t or head offset) is at most
+ * 112 B travel inline, so that one coalesced read brings descriptor and payload;
+ * larger images live in the payload byte ring at pay_off16 * 16. */
+#define APUS_SLOT_BYTES   128u
+#define APUS_SLOT_INLINE  112u
+#define APUS_SLOT_OFF_MASK 0x00ffffffu
+#define APUS_SLOT_TYPE_SHIFT 24
+#define APUS_SLOT_TYPE_MASK 0x1fu
+#define APUS_SLOT_EXT   (1u << 29)   /* image is in the payload ring */
+#define APUS_SLOT_WRAP  (1u << 30)   /* the payload ring restarted at 0 with this image */
+typedef struct apus_slot {
     uint64_t req_id;
-    uint32_t type_off;           /* type << 24 | payload offset in 16 B units */
+    uint32_t type_off;           /* WRAP | EXT | type << 24 | payload offset in 16 B units */
     uint16_t len;                /* cmd length (CSM-like) */
     uint16_t clt_id;             /* connection_id */
-} apus_desc_t;
+    uint8_t  inl[APUS_SLOT_INLINE];
+} apus_slot_t;
 
 /* words in pinned, mapped host memory shared with the kernels */
 typedef struct apus_hostwords {
@@ -125,7 +139,7 @@ typedef struct apus_devctx {
     uint8_t *region;                      /* own region */
     uint8_t *peer[APUS_MAX_SERVERS];      /* peers' regions as mapped here (NULL = absent) */
     /* leader submission ring */
-    const apus_desc_t *sub_desc;
+    const apus_slot_t *sub_slots;
     const uint8_t     *sub_pay;
     uint32_t           sub_mask;          /* slots - 1 */
     uint32_t           pad;
@@ -140,10 +154,10 @@ typedef struct apus_role {
     apus_devctx_t *ctx;
 } apus_role_t;
 
-#define APUS_LEADER_THREADS   512
-#define APUS_FOLLOWER_THREADS 512
-#define APUS_MAX_TILE_ENTRIES 512u
-#define APUS_IMG_BYTES        (96u * 1024u)
-#define APUS_KERNEL_THREADS   512
+#define APUS_KERNEL_THREADS    512
+#define APUS_MAX_TILE_ENTRIES  256u             /* slots fetched per tile (32 KiB of shared memory) */
+#define APUS_LEADER_IMG_BYTES  (80u * 1024u)    /* log bytes composed per tile (>= one maximal entry) */
+#define APUS_LEADER_EXT_BYTES  (66u * 1024u)    /* payload-ring bytes staged per tile (>= one maximal image) */
+#define APUS_FOLLOWER_WIN_BYTES (96u * 1024u)   /* log bytes a follower walks per window */
 
 #endif /* APUS_LAYOUT_H */

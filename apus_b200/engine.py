@@ -53,7 +53,7 @@ EXPORTS = [
     "apus_replica_destroy", "apus_replica_export", "apus_replica_connect", "apus_replicas_launch",
     "apus_replica_wait", "apus_replica_last_launch_ms", "apus_replicas_stop", "apus_submit",
     "apus_submit_batch", "apus_submit_defer", "apus_submit_flush", "apus_committed_tickets",
-    "apus_wait_committed", "apus_log_offsets", "apus_log_read", "apus_get_stats",
+    "apus_wait_committed", "apus_closed_loop", "apus_log_offsets", "apus_log_read", "apus_get_stats",
     "apus_latency_samples", "apus_set_head", "apus_remote_apply_offsets",
 ]
 
@@ -87,6 +87,7 @@ def load_library(path=LIB_PATH):
     L.apus_committed_tickets.argtypes = [vp]
     L.apus_committed_tickets.restype = u64
     L.apus_wait_committed.argtypes = [vp, u64, i64]
+    L.apus_closed_loop.argtypes = [vp, u32, u16, u16, u64, vp]
     L.apus_log_offsets.argtypes = [vp, C.POINTER(LogOffsets)]
     L.apus_log_read.argtypes = [vp, u64, u64, vp]
     L.apus_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -186,6 +187,12 @@ class Replica:
 
     def wait_committed(self, ticket, timeout_us=10_000_000):
         _ck(lib().apus_wait_committed(self.h, ticket, timeout_us), "apus_wait_committed")
+
+    def closed_loop(self, n, payload_len, conn, first_req_id):
+        """n requests, one in flight; returns host-clock latencies in ns (uint32 array)."""
+        out = np.empty(n, dtype=np.uint32)
+        _ck(lib().apus_closed_loop(self.h, n, payload_len, conn, first_req_id, out.ctypes.data), "apus_closed_loop")
+        return out
 
     def offsets(self):
         o = LogOffsets()

@@ -302,7 +302,8 @@ def run_ours(args):
     stride = 64 + payload
     if batch * stride * 4 > L * 3:
         raise SystemExit("batch too large for the log ring")
-    img = (2 + payload + 15) // 16 * 16
+    inline = (2 + payload) <= 112                      # APUS_SLOT_INLINE: image rides in the 128 B slot
+    img = 0 if inline else (2 + payload + 15) // 16 * 16
     total_req = (K + W) * batch + 64
     slots = 1 << max(16, (total_req - 1).bit_length())
     ring_bytes = ((total_req * img + (1 << 20)) + 4095) // 4096 * 4096
@@ -315,6 +316,24 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    gloo = dist.new_group(backend="gloo") if world > 1 else None
+
+    def host_barrier():
+        # while the resident kernels run, nothing may synchronise the whole device
+        if world > 1:
+            dist.barrier(group=gloo)
+
+    def log(msg):
+        if rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+    def max_over_ranks_host(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=gloo)
+        return float(t.item())
 
     def max_over_ranks(x):
         if world == 1:
@@ -361,6 +380,7 @@ def run_ours(args):
     st = cell.leader.stats()
     assert st["tickets_committed"] == targets[-1], (st, targets[-1])
     value = world * K * batch / elapsed
+    log(f"value: {value:.0f} ops/s, {1e3 * elapsed / K:.3f} ms/step, kernel {kernel_ms / K:.3f} ms/launch")
     launches = K * len(cell.devices) * world
     lat_dev = cell.leader.latency_ns()
     auto_heads = st["auto_heads"]
@@ -377,7 +397,8 @@ def run_ours(args):
         e_bytes = ((2 * batch * img + (1 << 20)) + 4095) // 4096 * 4096
         cell = Cell(A, E, args, mode, e_slots, e_bytes, flags, dist, rank, world, local)
         barrier()
-        cell.launch(UINT64_MAX)
+        cell.launch(UINT64_MAX)     # resident kernels: from here on no device-wide synchronisation
+        log("e2e: resident kernels launched")
         if n > 1:
             cell.submit(E.CONFIG, 0, 0, E.cid_image(n))
         t = cell.submit(CONNECT, conn, 1, b"")
@@ -386,38 +407,35 @@ def run_ours(args):
         for s in range(W):
             t = cell.submit_uniform(batch, payload, conn, req, payloads); req += batch
             cell.leader.wait_committed(t, 60_000_000)
-        barrier()
+        host_barrier()
         t0 = time.perf_counter()
         for s in range(K):
             t = cell.submit_uniform(batch, payload, conn, req, payloads); req += batch
             cell.leader.wait_committed(t, 60_000_000)
         t1 = time.perf_counter()
-        e_elapsed = max_over_ranks(t1 - t0)
+        host_barrier()
+        e_elapsed = max_over_ranks_host(t1 - t0)
         e2e = {"value": round(world * K * batch / e_elapsed, 1), "unit": "ops/s",
-               "h2d_bytes_per_step": batch * (16 + img), "d2h_bytes_per_step": 8,
+               "h2d_bytes_per_step": batch * (128 + img), "d2h_bytes_per_step": 8,
                "path": f"apus_submit_batch(host numpy buffers) -> {args.e2e_ring} submission ring -> resident kernels "
                        f"-> apus_wait_committed (pinned commit word)"}
         # closed loop, one request in flight: host-view commit latency (proxy.c:160 spin)
         if rank == 0 and args.lat_requests > 0:
-            one = payloads[:max(payload, 1)].tobytes()[:payload]
-            lats = []
-            for i in range(args.lat_requests):
-                a = time.perf_counter_ns()
-                t = cell.submit(SEND, conn, req, one); req += 1
-                cell.leader.wait_committed(t, 5_000_000)
-                lats.append(time.perf_counter_ns() - a)
-            lats = np.sort(np.array(lats[args.lat_requests // 10:], dtype=np.float64)) / 1e3
+            lats = cell.leader.closed_loop(args.lat_requests, payload, conn, req)
+            req += args.lat_requests
+            lats = np.sort(lats[args.lat_requests // 10:].astype(np.float64)) / 1e3
             lat_host = {"p50_us": round(float(lats[len(lats) // 2]), 2), "p99_us": round(float(lats[int(len(lats) * 0.99)]), 2),
-                        "n": int(len(lats)), "what": "apus_submit -> apus_wait_committed, one request in flight "
-                                                      "(includes ~1-2 us of ctypes call overhead)"}
+                        "n": int(len(lats)), "what": "apus_closed_loop (C ABI): enqueue one request, spin on the pinned "
+                                                      "commit word until it is committed; host clock, one request in flight"}
             d = cell.leader.latency_ns(args.lat_requests - args.lat_requests // 10)
             if len(d):
                 d = np.sort(d.astype(np.float64)) / 1e3
                 lat_host["device_p50_us"] = round(float(d[len(d) // 2]), 2)
                 lat_host["device_p99_us"] = round(float(d[int(len(d) * 0.99)]), 2)
-        barrier()
+        host_barrier()
         cell.stop()
         cell.close()
+        log(f"e2e done: {e2e}")
 
     # =========================== CPU baseline, JSON line ==================================
     if rank != 0:
@@ -444,7 +462,7 @@ def run_ours(args):
                           ("replica r on GPU r % visible GPUs, one process" if world == 1 else
                            f"group g led by GPU g, replica r on GPU (g + r) % {world}, one process per GPU, CUDA IPC")),
             "log_ring_bytes": L, "log_pruning": "device-side HEAD entries (APUS_F_AUTOPRUNE)",
-            "cache": f"inputs larger than L2: {(K + W) * batch * (16 + img) >> 20} MiB of requests stream through once; "
+            "cache": f"inputs larger than L2: {(K + W) * batch * (128 + img) >> 20} MiB of requests stream through once; "
                      f"log writes cover the 64 MiB ring x {n} replicas",
         },
         "clocks": clocks,

@@ -162,6 +162,11 @@ uint64_t apus_committed_tickets(apus_replica_t *leader);
 /* spin until ticket is committed; APUS_RETRY on timeout */
 int  apus_wait_committed(apus_replica_t *leader, uint64_t ticket, int64_t timeout_us);
 
+/* n requests of payload_len bytes, ONE in flight at a time: submit, spin until committed
+ * (what a proxy thread does, proxy.c:108-161); lat_ns[i] = host-clock nanoseconds of request i */
+int  apus_closed_loop(apus_replica_t *leader, uint32_t n, uint16_t payload_len, uint16_t connection_id,
+                      uint64_t first_req_id, uint32_t *lat_ns);
+
 /* ---- inspection (parity tests, snapshots) --------------------------------------- */
 int  apus_log_offsets(apus_replica_t *r, apus_log_offsets_t *out);
 /* copy entries[off, off+len) of this replica's log image to host memory */
