@@ -72,6 +72,8 @@ static_assert(sizeof(peer_blob) <= sizeof(apus_peer_handle_t), "peer handle too 
 struct apus_replica {
     apus_config_t cfg;
     uint64_t log_len;
+    uint64_t entries_off;
+    uint32_t idx_cap;
     uint8_t *region;
     size_t   region_bytes;
     apus_devctx_t  h_ctx;
@@ -131,9 +133,14 @@ extern "C" int apus_replica_create(const apus_config_t *cfg, apus_replica_t **ou
     apus_replica *r = (apus_replica *)calloc(1, sizeof(*r));
     if (!r) return fail("out of memory");
     r->cfg = *cfg;
-    if (!(r->cfg.flags & 0x80000000u)) r->cfg.flags |= APUS_F_FENCED_ACK | APUS_F_DEVICE_STATS;
+    if (!(r->cfg.flags & APUS_F_EXPLICIT)) r->cfg.flags |= APUS_F_DEVICE_STATS;
     r->log_len = log_len;
-    r->region_bytes = APUS_ENTRIES_OFF + log_len;
+    if (log_len > (1ull << 31)) return fail("log_size above 2 GiB is not supported (32-bit offset index)");
+    uint32_t cap = 1024;
+    while ((uint64_t)cap * 64ull < log_len) cap <<= 1;
+    r->idx_cap = cap;
+    r->entries_off = (APUS_INDEX_OFF + (uint64_t)cap * 4ull + 4095ull) & ~4095ull;
+    r->region_bytes = r->entries_off + log_len;
     CK(cudaMalloc(&r->region, r->region_bytes));
     CK(cudaMemset(r->region, 0, r->region_bytes));
     /* log_new(): end = tail = old_end = len (dare_log.h:129-134) */
@@ -264,6 +271,7 @@ static void fill_ctx(apus_replica *r, uint64_t target)
     c->quorum = (uint8_t)(r->cfg.group_size / 2 + 1);        /* dare_ibv_rc.c:1741 */
     c->flags = r->cfg.flags & 0x7fffffffu;
     c->term = r->cfg.term; c->log_len = r->log_len; c->target = target;
+    c->entries_off = r->entries_off; c->idx_mask = r->idx_cap - 1;
     c->region = r->region;
     for (int i = 0; i < APUS_MAX_SERVER_COUNT; i++)
         c->peer[i] = (i == r->cfg.server_idx) ? NULL : (uint8_t *)r->peer_ptr[i];
@@ -572,7 +580,7 @@ extern "C" int apus_log_read(apus_replica_t *r, uint64_t off, uint64_t len, void
     if (!r || !dst) return fail("null argument");
     if (off + len > r->log_len) return fail("range beyond the log");
     DeviceGuard g(r->cfg.device);
-    CK(cudaMemcpyAsync(dst, r->region + APUS_ENTRIES_OFF + off, len, cudaMemcpyDeviceToHost, r->copy_stream));
+    CK(cudaMemcpyAsync(dst, r->region + r->entries_off + off, len, cudaMemcpyDeviceToHost, r->copy_stream));
     CK(cudaStreamSynchronize(r->copy_stream));
     return APUS_OK;
 }

@@ -160,6 +160,7 @@ struct LeaderShared {
     uint64_t idx0;             // idx of the tile's first entry
     uint64_t t_dequeue;
     uint8_t *peer_entries[APUS_MAX_SERVERS];
+    uint32_t *peer_index[APUS_MAX_SERVERS];
     // publishes in flight: producer -> commit warp
     uint64_t pub_cum[PUB_RING];      // entries published up to and including this tile
     uint64_t pub_end[PUB_RING];      // `end` after this tile
@@ -185,6 +186,7 @@ struct FollowerShared {
     uint64_t win_lo, win_hi, next;           // window bounds in the log, next walk offset
     uint64_t head_val, head_end;             // last HEAD entry of the window (head_end == len: none)
     uint64_t end_seen, cum_seen, commit_seen;
+    uint32_t head_j;                         // index mode: 1 + position of the last HEAD entry of the batch
 };
 #define FS_BYTES ((sizeof(FollowerShared) + 127u) & ~127u)
 #define F_TOTAL (FS_BYTES + APUS_FOLLOWER_WIN_BYTES + 16)
@@ -314,7 +316,7 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx, LeaderS
         }
         const uint64_t Q = cand;
         if (Q > committed) {
-            __threadfence_system();   // acquire side of the followers' ack publication
+            // (no acquire fence: the commit rule consumes nothing but the ack words themselves)
             // map the entry count to the log offset recorded at publish time
             uint64_t tail = S->pub_tail, head = S->pub_head;
             uint64_t off = 0, tickets = committed_tickets, t0 = 0;
@@ -389,7 +391,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
     const int N = cx->group_size, me = cx->idx;
     apus_ctrl_t *ctrl = reinterpret_cast<apus_ctrl_t *>(cx->region);
     apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_CTRL_BYTES);
-    uint8_t *entries = cx->region + APUS_ENTRIES_OFF;
+    uint8_t *entries = cx->region + cx->entries_off;
     apus_hostwords_t *hw = cx->hw;
     const uint64_t L = cx->log_len;
     const bool autoprune = (cx->flags & APUS_FLAG_AUTOPRUNE) != 0;
@@ -399,7 +401,10 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
         S->published = ctrl->published;
         S->producers_done = 0; S->abort_flag = 0; S->finish = 0;
         for (int i = 0; i < APUS_MAX_SERVERS; i++)
-            S->peer_entries[i] = (i < N && i != me && cx->peer[i]) ? cx->peer[i] + APUS_ENTRIES_OFF : nullptr;
+        {
+            S->peer_entries[i] = (i < N && i != me && cx->peer[i]) ? cx->peer[i] + cx->entries_off : nullptr;
+            S->peer_index[i] = (i < N && i != me && cx->peer[i]) ? reinterpret_cast<uint32_t *>(cx->peer[i] + APUS_INDEX_OFF) : nullptr;
+        }
         // entries published by an earlier launch but not yet committed come back as one record
         if (ctrl->published != ctrl->committed) {
             S->pub_cum[0] = ctrl->published; S->pub_end[0] = hdr->end;
@@ -682,6 +687,24 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
                 }
             }
         }
+        // entry-offset index: the c-th entry ever appended sits at index[c & idx_mask]
+        if (!gap) {
+            const uint32_t autoh_i = S->auto_head;
+            uint32_t *lindex = reinterpret_cast<uint32_t *>(cx->region + APUS_INDEX_OFF);
+            for (uint32_t j = tid; j < m + autoh_i; j += NT) {
+                uint32_t w;
+                if (autoh_i && j == 0) w = (uint32_t)a | APUS_IDX_HEAD_FLAG;
+                else {
+                    const uint32_t k = j - autoh_i;
+                    const uint32_t ty = (sl[k].type_off >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
+                    w = (uint32_t)(a + S->rel[k]) | (ty == T_HEAD ? APUS_IDX_HEAD_FLAG : 0u);
+                }
+                const uint32_t at = (uint32_t)(published + 1 + j) & cx->idx_mask;
+                lindex[at] = w;
+                for (int f = 0; f < N; f++)
+                    if (S->peer_index[f]) S->peer_index[f][at] = w;
+            }
+        }
         bar_sync(1, NT);
 
         // ---- T6: bookkeeping + publish the tail (data before tail, invariant I1) --------
@@ -742,13 +765,15 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
     const int me = cx->idx, ldr = cx->leader_idx;
     apus_ctrl_t *ctrl = reinterpret_cast<apus_ctrl_t *>(cx->region);
     apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_CTRL_BYTES);
-    uint8_t *entries = cx->region + APUS_ENTRIES_OFF;
+    uint8_t *entries = cx->region + cx->entries_off;
     apus_hostwords_t *hw = cx->hw;
     uint8_t *lregion = cx->peer[ldr];
     apus_ctrl_t *lctrl = reinterpret_cast<apus_ctrl_t *>(lregion);
-    uint8_t *lentries = lregion + APUS_ENTRIES_OFF;
+    uint8_t *lentries = lregion + cx->entries_off;
     const uint64_t L = cx->log_len;
     const bool fenced = (cx->flags & APUS_FLAG_FENCED_ACK) != 0;
+    const bool walk = (cx->flags & APUS_FLAG_WALK) != 0;
+    const uint32_t *index = reinterpret_cast<const uint32_t *>(cx->region + APUS_INDEX_OFF);
 
     uint64_t old_end = hdr->old_end;     // walk position (dare_server.c:1795)
     uint64_t acked = ctrl->acked;        // entries walked (reply byte set) so far
@@ -792,7 +817,44 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
         const uint64_t end_seen = S->end_seen, cum_seen = S->cum_seen, commit_seen = S->commit_seen;
 
         // ---- persist + ack every new entry in [old_end, end_seen) -----------------------
-        if (cum_seen > acked) {
+        if (cum_seen > acked && !walk) {
+            // entry boundaries come from the offset index the leader wrote next to the bytes
+            const uint64_t n = cum_seen - acked;
+            if (tid == 0) S->head_j = 0;
+            __syncthreads();
+            for (uint64_t j = tid; j < n; j += nthr) {
+                const uint32_t w = ld_relaxed_sys_u32(&index[(uint32_t)(acked + 1 + j) & cx->idx_mask]);
+                const uint64_t at = (uint64_t)(w & ~APUS_IDX_HEAD_FLAG) + E_REPLY + (uint64_t)me;
+                st_relaxed_sys_u8(entries + at, 1);         // reply[me] = 1 in my copy and in the
+                st_relaxed_sys_u8(lentries + at, 1);        // leader's (dare_ibv_rc.c:1833-1854)
+                if (w & APUS_IDX_HEAD_FLAG) atomicMax(&S->head_j, (uint32_t)(j + 1));
+            }
+            __syncthreads();
+            if (S->head_j) {
+                // poll_config_entries (dare_server.c:2163-2170): remember the head this entry carries
+                const uint32_t w = ld_relaxed_sys_u32(&index[(uint32_t)(acked + S->head_j) & cx->idx_mask]);
+                const uint64_t off = (uint64_t)(w & ~APUS_IDX_HEAD_FLAG);
+                pend_val = ld_relaxed_sys(entries + ((off + E_DATA) & ~7ull));
+                if ((off + E_DATA) & 7ull) {
+                    uint64_t hv = 0;
+                    for (int q = 7; q >= 0; q--) hv = (hv << 8) | (uint64_t)(ld_relaxed_sys_u32(entries + ((off + E_DATA + q) & ~3ull)) >> (8 * ((off + E_DATA + q) & 3ull)) & 0xffu);
+                    pend_val = hv;
+                }
+                pend_end = (off + APUS_HDR_BYTES == L) ? 0 : off + APUS_HDR_BYTES;
+            }
+            acked = cum_seen;
+            old_end = end_seen;
+            if (tid == 0) {
+                if (fenced) {
+                    __threadfence_system();                  // reply bytes before the ack word
+                    st_relaxed_sys(&lctrl->ack[me], acked);
+                }
+                hdr->end = end_seen; hdr->old_end = old_end;
+                ctrl->acked = acked;
+                ctrl->pend_head_val = pend_val; ctrl->pend_head_end = pend_end;
+            }
+            last_progress = globaltimer_ns();
+        } else if (cum_seen > acked) {
             uint64_t walked = 0;
             while (old_end != end_seen) {
                 // window: contiguous bytes from old_end up to end_seen or the end of the ring

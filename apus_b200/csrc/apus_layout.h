@@ -9,7 +9,13 @@
  *                                   (dare_log.h:77-103: head 0, apply 8, commit 16,
  *                                   end 24, tail 32, old_end 40, old_commit 48, len 56,
  *                                   nc_buf 64 .. 319656), padded to 320 KiB
- *   +APUS_ENTRIES_OFF  entries[log_len]   the reference's circular byte log
+ *   +APUS_INDEX_OFF    u32 index[idx_cap]  entry-offset ring: offset of the c-th entry
+ *                                   ever appended at index[c & (idx_cap-1)], written by
+ *                                   the leader next to the entry bytes so that a follower
+ *                                   can ack without re-parsing the byte stream; idx_cap =
+ *                                   pow2 >= log_len/64, so it can never be overrun while
+ *                                   the log itself is not (head <= every apply offset)
+ *   +entries_off       entries[log_len]   the reference's circular byte log
  *
  * entries[] starts 4 KiB-aligned so that a log offset and its address agree
  * modulo 16 (vectorised 16 B peer stores need that).
@@ -17,7 +23,8 @@
  * Who writes what (all cross-GPU traffic is stores; nothing on the hot path reads
  * over NVLink):
  *   leader  -> follower.entries[range]       entry bytes           (replaces RDMA WRITE dare_ibv_rc.c:1606)
- *   leader  -> follower.hdr.end              tail publish, 8 B     (dare_ibv_rc.c:1549-1573)
+ *   leader  -> follower.index[..]            entry offsets, 4 B per entry
+ *   leader  -> follower.ctrl.pub_{end,cum}   tail publish, 16 B    (dare_ibv_rc.c:1549-1573)
  *   leader  -> follower.hdr.commit           commit publish, 8 B   (dare_ibv_rc.c:1810)
  *   follower-> leader.entries[e+28+idx]      reply byte, 1 B       (dare_ibv_rc.c:1833-1854)
  *   follower-> leader.ctrl.ack[idx]          ack word, 8 B         (the word the quorum ballot polls)
@@ -33,7 +40,8 @@
 #define APUS_CTRL_BYTES       4096u
 #define APUS_LOGHDR_REF_BYTES 319656u                 /* offsetof(dare_log_t, entries) */
 #define APUS_LOGHDR_BYTES     (320u * 1024u)
-#define APUS_ENTRIES_OFF      (APUS_CTRL_BYTES + APUS_LOGHDR_BYTES)
+#define APUS_INDEX_OFF        (APUS_CTRL_BYTES + APUS_LOGHDR_BYTES)
+#define APUS_IDX_HEAD_FLAG    0x80000000u             /* index word: the entry is a HEAD entry */
 
 /* entry field offsets (dare_log.h:33-48) */
 #define E_IDX     0
@@ -123,6 +131,7 @@ typedef struct apus_hostwords {
 #define APUS_FLAG_FENCED_ACK 0x1u
 #define APUS_FLAG_STATS      0x2u
 #define APUS_FLAG_AUTOPRUNE  0x4u
+#define APUS_FLAG_WALK       0x8u   /* follower parses the byte stream itself (reference behaviour) */
 
 #define APUS_ROLE_NONE     0
 #define APUS_ROLE_LEADER   1
@@ -135,6 +144,9 @@ typedef struct apus_devctx {
     uint32_t flags;
     uint64_t term;
     uint64_t log_len;
+    uint64_t entries_off;                 /* byte offset of entries[] inside a region */
+    uint32_t idx_mask;                    /* index ring capacity - 1 */
+    uint32_t pad_i;
     uint64_t target;                      /* cumulative ticket / entry target of this launch */
     uint8_t *region;                      /* own region */
     uint8_t *peer[APUS_MAX_SERVERS];      /* peers' regions as mapped here (NULL = absent) */

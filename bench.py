@@ -309,7 +309,7 @@ def run_ours(args):
     ring_bytes = ((total_req * img + (1 << 20)) + 4095) // 4096 * 4096
     if ring_bytes // 16 > 0xFFFFFF:
         raise SystemExit("steps*batch*payload too large for the device submission ring (256 MiB)")
-    flags = E.F_FENCED_ACK | E.F_DEVICE_STATS | E.F_AUTOPRUNE
+    flags = E.F_DEVICE_STATS | E.F_AUTOPRUNE
 
     def barrier():
         torch.cuda.synchronize()

@@ -64,11 +64,15 @@ extern "C" {
 #define APUS_RING_DEVICE      1   /* HBM; the host fills it with cudaMemcpyAsync batches */
 
 /* apus_config_t.flags */
-#define APUS_F_FENCED_ACK   0x1u  /* follower: reply bytes visible before the ack word (default on) */
+#define APUS_F_FENCED_ACK   0x1u  /* follower: reply bytes visible before the ack word; off = ack as soon as
+                                     the tail publish is observed, reply bytes follow (default off) */
 #define APUS_F_DEVICE_STATS 0x2u  /* leader: record per-batch device-side commit latency */
 #define APUS_F_AUTOPRUNE    0x4u  /* leader: device-side log pruning (force_log_pruning rule,
                                      dare_server.c:2069-2122): when the ring is a quarter full the
                                      kernel appends a HEAD entry carrying min(apply offsets) */
+#define APUS_F_FOLLOWER_WALK 0x8u /* follower: find entry boundaries by walking the byte stream
+                                     (log_get_entry/log_entry_len, as the reference follower does)
+                                     instead of reading the leader-written offset index */
 #define APUS_F_EXPLICIT     0x80000000u /* flags are exactly as given (no defaults OR-ed in) */
 
 typedef struct apus_replica apus_replica_t;

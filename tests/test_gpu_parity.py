@@ -29,9 +29,18 @@ def devices_for(eng, n):
     return [i % nd for i in range(n)]
 
 
-def run_and_compare(eng, orc, n, L, stream, ring_mode=0, prologue=True, exact=True, devices=None, chunks=1):
+MODES = {
+    "index_earlyack": 0x2,               # default: offset index, ack on tail observation
+    "walk_fenced": 0x2 | 0x1 | 0x8,      # reference-like follower: parse the bytes, reply bytes before the ack
+    "index_fenced": 0x2 | 0x1,
+    "walk_earlyack": 0x2 | 0x8,
+}
+
+
+def run_and_compare(eng, orc, n, L, stream, ring_mode=0, prologue=True, exact=True, devices=None, chunks=1,
+                    mode="index_earlyack"):
     devices = devices or devices_for(eng, n)
-    with eng.Group(n, devices=devices, log_size=L, ring_mode=ring_mode) as g:
+    with eng.Group(n, devices=devices, log_size=L, ring_mode=ring_mode, flags=MODES[mode]) as g:
         if prologue:
             g.prologue()
         per = (len(stream) + chunks - 1) // chunks
@@ -65,10 +74,11 @@ def test_uniform_64B(eng, orc, n):
     run_and_compare(eng, orc, n, 1 << 21, S.uniform_stream(6000, 64, conns=4))
 
 
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("n,seed", [(3, 11), (5, 12), (7, 13), (13, 14)])
-def test_ragged_lengths(eng, orc, n, seed):
+def test_ragged_lengths(eng, orc, n, seed, mode):
     """0-length, odd and unaligned payloads: entries start at arbitrary byte offsets (H1)."""
-    run_and_compare(eng, orc, n, 1 << 21, S.ragged_stream(3000, 300, conns=5, seed=seed, close_every=70))
+    run_and_compare(eng, orc, n, 1 << 21, S.ragged_stream(3000, 300, conns=5, seed=seed, close_every=70), mode=mode)
 
 
 def test_device_ring_mode(eng, orc):
@@ -79,13 +89,42 @@ def test_multiple_launches_carry_state(eng, orc):
     run_and_compare(eng, orc, 3, 1 << 21, S.ragged_stream(2000, 128, seed=22), chunks=5)
 
 
-def test_large_payloads(eng, orc):
+@pytest.mark.parametrize("mode", ["index_earlyack", "walk_fenced"])
+def test_large_payloads(eng, orc, mode):
     stream = [(S.CONNECT, 1, 1, b"")] + [(S.SEND, 1, 2 + i, bytes([(i * 7 + k) & 0xFF for k in range(256)]) * 16)
                                           for i in range(40)]
     stream += [(S.SEND, 1, 100 + i, np.random.default_rng(i).integers(0, 256, 65535, dtype=np.uint8).tobytes())
                for i in range(6)]
     stream += [(S.SEND, 1, 200, b""), (S.CLOSE, 1, 201, b"")]
-    run_and_compare(eng, orc, 3, 1 << 21, stream)
+    run_and_compare(eng, orc, 3, 1 << 21, stream, mode=mode)
+
+
+def test_payload_ring_wraps(eng, orc):
+    """External payload images wrap the (small) payload byte ring several times inside one run."""
+    rng = np.random.default_rng(3)
+    stream = [(S.CONNECT, 7, 1, b"")]
+    for i in range(600):
+        ln = int(rng.integers(100, 3000))
+        stream.append((S.SEND, 7, 2 + i, rng.integers(0, 256, ln, dtype=np.uint8).tobytes()))
+    n, L = 3, 1 << 21
+    with eng.Group(n, devices=devices_for(eng, n), log_size=L, ring_slots=1 << 16, ring_bytes=1 << 17) as g:
+        g.launch(target=(1 << 64) - 1)          # resident: the ring drains while we submit
+        g.prologue()
+        for typ, clt, rid, payload in stream:
+            while True:
+                try:
+                    t = g.submit(typ, clt, rid, payload)
+                    break
+                except BlockingIOError:
+                    pass
+        g.leader.wait_committed(t, 20_000_000)
+        g.stop()
+        c = EU.oracle_cluster(orc, n, L, stream)
+        lo = g.leader.offsets()
+        assert lo["end"] == c.offsets(0)["end"]
+        ents = O.walk_entries(c.image(0), 0, lo["end"], L)
+        assert np.array_equal(O.mask_replies(g.leader.image(), ents), O.mask_replies(c.image(0), ents))
+        c.close()
 
 
 def test_default_log_size_64MiB(eng, orc):
@@ -139,8 +178,9 @@ def prune_both(g, c):
 eng_HEAD = 3
 
 
+@pytest.mark.parametrize("mode", ["index_earlyack", "walk_fenced"])
 @pytest.mark.parametrize("n,L,seed", [(3, 16384, 77), (5, 32768, 78), (3, 8192, 79)])
-def test_wrap_laps_with_pruning(eng, orc, n, L, seed):
+def test_wrap_laps_with_pruning(eng, orc, n, L, seed, mode):
     """Several laps around a small ring: ghost headers, header-does-not-fit jumps,
     stale bytes in entry holes, HEAD entries.  Pruning happens at quiescent points
     so that the stream of appends is identical on both sides."""
@@ -148,7 +188,7 @@ def test_wrap_laps_with_pruning(eng, orc, n, L, seed):
     orc.set_rules(O.RULES_ENGINE)
     c = O.Cluster(orc, n, leader=0, term=1, length=L)
     c.prologue()
-    with eng.Group(n, devices=devices_for(eng, n), log_size=L) as g:
+    with eng.Group(n, devices=devices_for(eng, n), log_size=L, flags=MODES[mode]) as g:
         g.prologue()
         step = 12
         total = 1
@@ -274,7 +314,7 @@ def test_sustained_autoprune_many_laps(eng, n, L, payload):
     """Device-side pruning (APUS_F_AUTOPRUNE): 40+ laps around a small ring in a few
     launches, no host-side HEAD submission."""
     from apus_b200 import engine as E
-    flags = E.F_FENCED_ACK | E.F_DEVICE_STATS | E.F_AUTOPRUNE
+    flags = E.F_DEVICE_STATS | E.F_AUTOPRUNE
     per, rounds = 20000, 4
     with eng.Group(n, devices=devices_for(eng, n), log_size=L, ring_mode=eng.RING_DEVICE,
                    ring_slots=1 << 17, ring_bytes=64 << 20, flags=flags) as g:

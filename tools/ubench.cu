@@ -1,0 +1,119 @@
+// tools/ubench.cu -- latency micro-benchmarks that size the replication protocol:
+// how long a system-scope fence, a poll on local/peer/host memory and a flag
+// ping-pong take on this machine (the o/L/G idea of the reference's LogGP probes,
+// dare_ibv_rc.c:3323-3702, applied to NVLink/PCIe).  Build: make -C tools
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+#include <algorithm>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+
+__device__ __forceinline__ uint64_t gt() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ uint64_t ldr(const volatile void *p) { uint64_t v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void str(volatile void *p, uint64_t v) { asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void st16(void *p, uint4 v) { asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+
+// mode 0: dependent loads (poll latency); 1: fence only; 2: warp stores 512 B then fence; 3: store 8 B + fence
+__global__ void k_single(volatile uint64_t *target, uint8_t *buf, int mode, int iters, uint64_t *out_ns, long long *out_clk)
+{
+    uint64_t acc = 0;
+    long long c0 = clock64();
+    uint64_t t0 = gt();
+    for (int i = 0; i < iters; i++) {
+        if (mode == 0) { acc += ldr(target + (acc & 1)); }
+        else if (mode == 1) { __threadfence_system(); }
+        else if (mode == 2) { st16(buf + ((i & 63) * 512) + threadIdx.x * 16, make_uint4(i, i, i, i)); __threadfence_system(); }
+        else if (mode == 3) { if (threadIdx.x == 0) str((volatile uint64_t *)buf + (i & 63) * 16, i); __threadfence_system(); }
+    }
+    uint64_t t1 = gt();
+    long long c1 = clock64();
+    if (threadIdx.x == 0) { out_ns[0] = t1 - t0 + (acc == 0xdeadbeef); out_clk[0] = c1 - c0; }
+}
+
+// ping-pong: block A writes flagB=i (optionally after data stores + fence), waits flagA==i
+__global__ void k_ping(volatile uint64_t *my_flag, volatile uint64_t *peer_flag, uint8_t *peer_buf, int iters, int data_bytes, int fence, int first, uint64_t *out_ns)
+{
+    uint64_t t0 = gt();
+    for (int i = 1; i <= iters; i++) {
+        if (first) {
+            if (data_bytes) { for (int b = threadIdx.x * 16; b < data_bytes; b += blockDim.x * 16) st16(peer_buf + b, make_uint4(i, i, i, i)); __syncthreads(); }
+            if (threadIdx.x == 0) { if (fence) __threadfence_system(); str(peer_flag, i); while (ldr(my_flag) < (uint64_t)i) ; }
+            __syncthreads();
+        } else {
+            if (threadIdx.x == 0) { while (ldr(my_flag) < (uint64_t)i) ; if (fence) __threadfence_system(); str(peer_flag, i); }
+            __syncthreads();
+        }
+    }
+    uint64_t t1 = gt();
+    if (threadIdx.x == 0) out_ns[0] = t1 - t0;
+}
+
+static double run_single(volatile uint64_t *target, uint8_t *buf, int mode, int iters, int threads)
+{
+    uint64_t *ns; long long *clk;
+    CK(cudaMallocManaged(&ns, 8)); CK(cudaMallocManaged(&clk, 8));
+    k_single<<<1, threads>>>(target, buf, mode, 10, ns, clk); CK(cudaDeviceSynchronize());
+    k_single<<<1, threads>>>(target, buf, mode, iters, ns, clk); CK(cudaDeviceSynchronize());
+    double r = (double)ns[0] / iters;
+    printf("    (%.0f clk/iter)\n", (double)clk[0] / iters);
+    cudaFree(ns); cudaFree(clk);
+    return r;
+}
+
+int main()
+{
+    int ndev = 0; CK(cudaGetDeviceCount(&ndev));
+    printf("devices: %d\n", ndev);
+    CK(cudaSetDevice(0));
+    uint64_t *dflag; uint8_t *dbuf; CK(cudaMalloc(&dflag, 4096)); CK(cudaMemset(dflag, 0, 4096)); CK(cudaMalloc(&dbuf, 1 << 20));
+    uint64_t *hflag; CK(cudaHostAlloc(&hflag, 4096, cudaHostAllocMapped)); hflag[0] = 0; hflag[1] = 0;
+    uint64_t *hflag_d; CK(cudaHostGetDevicePointer(&hflag_d, hflag, 0));
+    printf("poll local L2 (dependent ld.relaxed.sys): "); printf("%.1f ns\n", run_single(dflag, dbuf, 0, 20000, 32));
+    printf("poll host-mapped (dependent ld.relaxed.sys over PCIe): "); printf("%.1f ns\n", run_single(hflag_d, dbuf, 0, 5000, 32));
+    printf("fence.sys, nothing outstanding: "); printf("%.1f ns\n", run_single(dflag, dbuf, 1, 20000, 32));
+    printf("warp 512 B local stores + fence.sys: "); printf("%.1f ns\n", run_single(dflag, dbuf, 2, 20000, 32));
+    printf("8 B local store + fence.sys: "); printf("%.1f ns\n", run_single(dflag, dbuf, 3, 20000, 32));
+    printf("8 B host-mapped store + fence.sys: "); printf("%.1f ns\n", run_single(dflag, (uint8_t *)hflag_d + 1024, 3, 5000, 32));
+    // same-GPU ping-pong between two CTAs
+    for (int cfg = 0; cfg < 3; cfg++) {
+        int data = cfg == 0 ? 0 : (cfg == 1 ? 128 : 32768), fence = cfg == 0 ? 0 : 1;
+        CK(cudaMemset(dflag, 0, 4096));
+        uint64_t *ns; CK(cudaMallocManaged(&ns, 16));
+        cudaStream_t s1, s2; CK(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        int iters = 20000;
+        k_ping<<<1, 256, 0, s1>>>(dflag, dflag + 64, dbuf, iters, data, fence, 1, ns);
+        k_ping<<<1, 256, 0, s2>>>(dflag + 64, dflag, dbuf, iters, 0, fence, 0, ns + 1);
+        CK(cudaDeviceSynchronize());
+        printf("same-GPU ping-pong, %d B data, fence=%d: %.1f ns round trip\n", data, fence, (double)ns[0] / iters);
+        cudaFree(ns);
+    }
+    if (ndev >= 2) {
+        int can = 0; CK(cudaDeviceCanAccessPeer(&can, 0, 1));
+        printf("peer access 0->1: %d\n", can);
+        if (can) {
+            CK(cudaDeviceEnablePeerAccess(1, 0));
+            CK(cudaSetDevice(1)); CK(cudaDeviceEnablePeerAccess(0, 0));
+            uint64_t *pflag; uint8_t *pbuf; CK(cudaMalloc(&pflag, 4096)); CK(cudaMemset(pflag, 0, 4096)); CK(cudaMalloc(&pbuf, 1 << 20));
+            CK(cudaSetDevice(0));
+            printf("poll PEER memory over NVLink (dependent loads): "); printf("%.1f ns\n", run_single(pflag, dbuf, 0, 5000, 32));
+            printf("warp 512 B PEER stores + fence.sys: "); printf("%.1f ns\n", run_single(dflag, pbuf, 2, 5000, 32));
+            printf("8 B PEER store + fence.sys: "); printf("%.1f ns\n", run_single(dflag, pbuf, 3, 5000, 32));
+            for (int cfg = 0; cfg < 4; cfg++) {
+                int data = cfg == 0 ? 0 : (cfg == 1 ? 128 : (cfg == 2 ? 4096 : 32768)), fence = cfg == 0 ? 0 : 1;
+                CK(cudaSetDevice(0)); CK(cudaMemset(dflag, 0, 4096));
+                CK(cudaSetDevice(1)); CK(cudaMemset(pflag, 0, 4096)); CK(cudaDeviceSynchronize());
+                uint64_t *ns; CK(cudaMallocManaged(&ns, 16));
+                int iters = 10000;
+                CK(cudaSetDevice(1)); k_ping<<<1, 256>>>(pflag, dflag, dbuf, iters, 0, fence, 0, ns + 1);
+                CK(cudaSetDevice(0)); k_ping<<<1, 256>>>(dflag, pflag, pbuf, iters, data, fence, 1, ns);
+                CK(cudaSetDevice(0)); CK(cudaDeviceSynchronize()); CK(cudaSetDevice(1)); CK(cudaDeviceSynchronize());
+                printf("NVLink ping-pong GPU0<->GPU1, %d B data, fence=%d: %.1f ns round trip\n", data, fence, (double)ns[0] / iters);
+                cudaFree(ns);
+            }
+        }
+    }
+    return 0;
+}
