@@ -427,6 +427,10 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
     uint64_t auto_heads = ctrl->auto_heads;
     uint64_t last_progress = globaltimer_ns();
     bool prev_head = false;     // the last entry appended is a HEAD entry of the pruning rule
+    const bool prof = (cx->flags & APUS_FLAG_STATS) != 0 && tid == 0;
+    uint64_t ph[8], tprev = globaltimer_ns();
+    for (int i = 0; i < 8; i++) ph[i] = ctrl->phase_ns[i];
+#define PHASE(i) do { if (prof) { const uint64_t _t = globaltimer_ns(); ph[i] += _t - tprev; tprev = _t; } } while (0)
 
     for (;;) {
         // ---- T0: wait for requests (thread 0) ---------------------------------------
@@ -464,6 +468,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
         bar_sync(1, NT);
         if (S->finish) break;
         const uint32_t nf = S->n_fetch;
+        PHASE(0);
 
         // ---- T1: fetch the slots (descriptor + inline payload), coalesced 16 B loads --------
         {
@@ -476,6 +481,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
                                  (nf - first) * 8u, tid);
         }
         bar_sync(1, NT);
+        PHASE(1);
         const apus_slot_t *sl = reinterpret_cast<const apus_slot_t *>(slots);
 
         // ---- T2: placement (warp 0): log_append_entry's offset rules over the tile ----
@@ -608,6 +614,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
             }
         }
         bar_sync(1, NT);
+        PHASE(2);
         const uint32_t m = S->m, gap = S->gap;
         const uint64_t a = S->a, b = S->b;
         if (a == b) {   // no space before head: poll again
@@ -635,6 +642,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
         }
         if (!gap && S->ext_bytes) cta_fetch_chunks(ext, cx->sub_pay + S->ext_base, S->ext_bytes >> 4, tid);
         bar_sync(1, NT);
+        PHASE(3);
 
         // ---- T4: compose entries into the image -----------------------------------------
         if (gap) {
@@ -665,6 +673,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
             }
         }
         bar_sync(1, NT);
+        PHASE(4);
 
         // ---- T5: push the byte range [a,b) to the local log and to every follower ------
         for (uint32_t c = tid; c < nchunks; c += NT) {
@@ -706,6 +715,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
             }
         }
         bar_sync(1, NT);
+        PHASE(5);
 
         // ---- T6: bookkeeping + publish the tail (data before tail, invariant I1) --------
         if (gap) {
@@ -750,7 +760,9 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
             }
         }
         last_progress = globaltimer_ns();
+        if (prof) { PHASE(6); ph[7]++; }
     }
+    if (prof) for (int i = 0; i < 8; i++) ctrl->phase_ns[i] = ph[i];
     if (tid == 0) { __threadfence_block(); S->producers_done = 1; }
 }
 

@@ -93,6 +93,9 @@ typedef struct apus_ctrl {
     uint64_t pub_end;            /* tail publish: the follower's new `end` (dare_ibv_rc.c:1549-1573) ... */
     uint64_t pub_cum;            /* ... and the entries that exist up to it; one 16 B store */
     uint64_t pad2[14];
+    /* --- leader profiling (APUS_F_DEVICE_STATS): ns spent per phase of the tile loop --- */
+    uint64_t phase_ns[8];        /* [0] wait for requests, [1..6] T1..T6, [7] tiles */
+    uint64_t pad3[8];
 } apus_ctrl_t;
 
 /* submission slot, 128 B: the fields of tailq_entry_t (message.h:11-17).  Requests

@@ -43,7 +43,7 @@ class LogOffsets(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(k, u64) for k in ("tickets_submitted", "tickets_consumed", "tickets_committed",
                                    "entries_acked", "bytes_replicated", "batches", "kernel_launches",
-                                   "lat_samples", "auto_heads", "entries_published")]
+                                   "lat_samples", "auto_heads", "entries_published")] + [("phase_ns", u64 * 8)]
 
 
 _lib = None
@@ -209,7 +209,9 @@ class Replica:
     def stats(self):
         s = Stats()
         _ck(lib().apus_get_stats(self.h, C.byref(s)), "apus_get_stats")
-        return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+        d = {k: int(getattr(s, k)) for k, _ in Stats._fields_ if k != "phase_ns"}
+        d["phase_ns"] = [int(x) for x in s.phase_ns]
+        return d
 
     def latency_ns(self, max_samples=65536):
         out = np.empty(max_samples, dtype=np.uint32)

@@ -384,6 +384,7 @@ def run_ours(args):
     launches = K * len(cell.devices) * world
     lat_dev = cell.leader.latency_ns()
     auto_heads = st["auto_heads"]
+    log(f"leader phases (ns, cumulative): {st['phase_ns']}")
     batches = st["batches"]
     off = cell.leader.offsets()
     cell.close()
@@ -479,7 +480,9 @@ def run_ours(args):
                                           "n": int(len(dl)), "what": "per replicate step: dequeue -> majority observed (%globaltimer), "
                                                                      "open-loop run (queueing included)"}),
                     "closed_loop": lat_host},
-        "engine": {"replicate_steps": batches, "auto_head_entries": auto_heads, "final_offsets": off},
+        "engine": {"replicate_steps": batches, "auto_head_entries": auto_heads, "final_offsets": off,
+                   "leader_phase_ns": dict(zip(["wait", "T1_fetch", "T2_place", "T3_prefill", "T4_compose", "T5_store",
+                                                "T6_publish", "tiles"], st["phase_ns"]))},
     }
     print(json.dumps(out), flush=True)
 

@@ -113,6 +113,7 @@ typedef struct apus_stats {
     uint64_t lat_samples;         /* device-side latency samples available */
     uint64_t auto_heads;          /* leader: HEAD entries appended by the device-side pruning rule */
     uint64_t entries_published;   /* leader: entries appended (tickets + auto HEAD entries) */
+    uint64_t phase_ns[8];         /* leader profiling: ns waiting for requests, in T1..T6, and tile count */
 } apus_stats_t;
 
 /* ---- library ------------------------------------------------------------------- */

@@ -60,4 +60,4 @@ def test_config_struct_matches_header(built):
     assert C.sizeof(built.Config) == 40
     assert C.sizeof(built.PeerHandle) == 128
     assert C.sizeof(built.LogOffsets) == 64
-    assert C.sizeof(built.Stats) == 80
+    assert C.sizeof(built.Stats) == 144

@@ -27,6 +27,15 @@ __global__ void k_single(volatile uint64_t *target, uint8_t *buf, int mode, int 
         else if (mode == 1) { __threadfence_system(); }
         else if (mode == 2) { st16(buf + ((i & 63) * 512) + threadIdx.x * 16, make_uint4(i, i, i, i)); __threadfence_system(); }
         else if (mode == 3) { if (threadIdx.x == 0) str((volatile uint64_t *)buf + (i & 63) * 16, i); __threadfence_system(); }
+        else if (mode == 4) { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+        else if (mode == 5) { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+        else if (mode == 6) { asm volatile("fence.sc.gpu;" ::: "memory"); }
+        else if (mode == 7) { st16(buf + ((i & 63) * 512) + threadIdx.x * 16, make_uint4(i, i, i, i)); asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+        else if (mode == 8) { st16(buf + ((i & 63) * 512) + threadIdx.x * 16, make_uint4(i, i, i, i)); if (threadIdx.x == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(target + 8), "l"((uint64_t)i) : "memory"); }
+        else if (mode == 9) { uint64_t v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(target + (acc & 1)) : "memory"); acc += v; }
+        else if (mode == 10) { st16(buf + ((i & 63) * 512) + threadIdx.x * 16, make_uint4(i, i, i, i)); asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+        else if (mode == 11) { st16(buf + ((i & 63) * 512) + threadIdx.x * 16, make_uint4(i, i, i, i)); if (threadIdx.x == 0) asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(target + 8), "l"((uint64_t)1) : "memory"); }
+        else if (mode == 12) { st16(buf + ((i & 63) * 512) + threadIdx.x * 16, make_uint4(i, i, i, i)); }
     }
     uint64_t t1 = gt();
     long long c1 = clock64();
@@ -40,10 +49,16 @@ __global__ void k_ping(volatile uint64_t *my_flag, volatile uint64_t *peer_flag,
     for (int i = 1; i <= iters; i++) {
         if (first) {
             if (data_bytes) { for (int b = threadIdx.x * 16; b < data_bytes; b += blockDim.x * 16) st16(peer_buf + b, make_uint4(i, i, i, i)); __syncthreads(); }
-            if (threadIdx.x == 0) { if (fence) __threadfence_system(); str(peer_flag, i); while (ldr(my_flag) < (uint64_t)i) ; }
+            if (threadIdx.x == 0) {
+                if (fence == 1) __threadfence_system();
+                if (fence == 2) asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(peer_flag), "l"((uint64_t)i) : "memory");
+                else if (fence == 3) { asm volatile("fence.acq_rel.sys;" ::: "memory"); str(peer_flag, i); }
+                else str(peer_flag, i);
+                while (ldr(my_flag) < (uint64_t)i) ;
+            }
             __syncthreads();
         } else {
-            if (threadIdx.x == 0) { while (ldr(my_flag) < (uint64_t)i) ; if (fence) __threadfence_system(); str(peer_flag, i); }
+            if (threadIdx.x == 0) { while (ldr(my_flag) < (uint64_t)i) ; if (fence == 1) __threadfence_system(); str(peer_flag, i); }
             __syncthreads();
         }
     }
@@ -77,9 +92,18 @@ int main()
     printf("warp 512 B local stores + fence.sys: "); printf("%.1f ns\n", run_single(dflag, dbuf, 2, 20000, 32));
     printf("8 B local store + fence.sys: "); printf("%.1f ns\n", run_single(dflag, dbuf, 3, 20000, 32));
     printf("8 B host-mapped store + fence.sys: "); printf("%.1f ns\n", run_single(dflag, (uint8_t *)hflag_d + 1024, 3, 5000, 32));
+    printf("fence.acq_rel.sys, nothing outstanding: "); printf("%.1f ns\n", run_single(dflag, dbuf, 4, 20000, 32));
+    printf("fence.acq_rel.gpu, nothing outstanding: "); printf("%.1f ns\n", run_single(dflag, dbuf, 5, 20000, 32));
+    printf("fence.sc.gpu, nothing outstanding: "); printf("%.1f ns\n", run_single(dflag, dbuf, 6, 20000, 32));
+    printf("warp 512 B local stores + fence.acq_rel.sys: "); printf("%.1f ns\n", run_single(dflag, dbuf, 7, 20000, 32));
+    printf("warp 512 B local stores + st.release.sys flag: "); printf("%.1f ns\n", run_single(dflag, dbuf, 8, 20000, 32));
+    printf("ld.acquire.sys local (dependent): "); printf("%.1f ns\n", run_single(dflag, dbuf, 9, 20000, 32));
+    printf("warp 512 B local stores + fence.acq_rel.gpu: "); printf("%.1f ns\n", run_single(dflag, dbuf, 10, 20000, 32));
+    printf("warp 512 B local stores + red.release.sys: "); printf("%.1f ns\n", run_single(dflag, dbuf, 11, 20000, 32));
+    printf("warp 512 B local stores only (issue rate): "); printf("%.1f ns\n", run_single(dflag, dbuf, 12, 20000, 32));
     // same-GPU ping-pong between two CTAs
-    for (int cfg = 0; cfg < 3; cfg++) {
-        int data = cfg == 0 ? 0 : (cfg == 1 ? 128 : 32768), fence = cfg == 0 ? 0 : 1;
+    for (int cfg = 0; cfg < 5; cfg++) {
+        int data = cfg == 0 ? 0 : (cfg == 1 ? 128 : (cfg == 2 ? 32768 : 128)), fence = cfg == 0 ? 0 : (cfg <= 2 ? 1 : (cfg == 3 ? 2 : 3));
         CK(cudaMemset(dflag, 0, 4096));
         uint64_t *ns; CK(cudaMallocManaged(&ns, 16));
         cudaStream_t s1, s2; CK(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
@@ -101,8 +125,12 @@ int main()
             printf("poll PEER memory over NVLink (dependent loads): "); printf("%.1f ns\n", run_single(pflag, dbuf, 0, 5000, 32));
             printf("warp 512 B PEER stores + fence.sys: "); printf("%.1f ns\n", run_single(dflag, pbuf, 2, 5000, 32));
             printf("8 B PEER store + fence.sys: "); printf("%.1f ns\n", run_single(dflag, pbuf, 3, 5000, 32));
-            for (int cfg = 0; cfg < 4; cfg++) {
-                int data = cfg == 0 ? 0 : (cfg == 1 ? 128 : (cfg == 2 ? 4096 : 32768)), fence = cfg == 0 ? 0 : 1;
+            printf("warp 512 B PEER stores + fence.acq_rel.sys: "); printf("%.1f ns\n", run_single(dflag, pbuf, 7, 5000, 32));
+            printf("warp 512 B PEER stores + st.release.sys PEER flag: "); printf("%.1f ns\n", run_single(pflag, pbuf, 8, 5000, 32));
+            printf("warp 512 B PEER stores only (issue rate): "); printf("%.1f ns\n", run_single(dflag, pbuf, 12, 5000, 32));
+            for (int cfg = 0; cfg < 7; cfg++) {
+                int data = cfg == 0 ? 0 : (cfg == 1 ? 128 : (cfg == 2 ? 4096 : (cfg == 3 ? 32768 : (cfg == 4 ? 128 : (cfg == 5 ? 128 : 32768)))));
+                int fence = cfg == 0 ? 0 : (cfg <= 3 ? 1 : (cfg == 4 ? 2 : 3));
                 CK(cudaSetDevice(0)); CK(cudaMemset(dflag, 0, 4096));
                 CK(cudaSetDevice(1)); CK(cudaMemset(pflag, 0, 4096)); CK(cudaDeviceSynchronize());
                 uint64_t *ns; CK(cudaMallocManaged(&ns, 16));
