@@ -147,7 +147,7 @@ extern "C" int apus_replica_create(const apus_config_t *cfg, apus_replica_t **ou
     apus_loghdr_t h;
     memset(&h, 0, sizeof h);
     h.len = log_len; h.end = log_len; h.tail = log_len; h.old_end = log_len;
-    CK(cudaMemcpy(r->region + APUS_CTRL_BYTES, &h, sizeof h, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(r->region + APUS_HDR_OFF, &h, sizeof h, cudaMemcpyHostToDevice));
     apus_ctrl_t c;
     memset(&c, 0, sizeof c);
     c.next_idx = 1;
@@ -272,6 +272,9 @@ static void fill_ctx(apus_replica *r, uint64_t target)
     c->flags = r->cfg.flags & 0x7fffffffu;
     c->term = r->cfg.term; c->log_len = r->log_len; c->target = target;
     c->entries_off = r->entries_off; c->idx_mask = r->idx_cap - 1;
+    c->n_workers = r->cfg.leader_ctas ? r->cfg.leader_ctas : 4;
+    if (c->n_workers > 32) c->n_workers = 32;
+    c->epoch = (uint32_t)(r->launches + 1);
     c->region = r->region;
     for (int i = 0; i < APUS_MAX_SERVER_COUNT; i++)
         c->peer[i] = (i == r->cfg.server_idx) ? NULL : (uint8_t *)r->peer_ptr[i];
@@ -295,20 +298,27 @@ extern "C" int apus_replicas_launch(apus_replica_t **rs, int n, uint64_t target)
     }
     DeviceGuard g(owner->cfg.device);
     apus_role_t roles[64];
+    int nroles = 0;
     for (int i = 0; i < n; i++) {
         apus_replica *r = rs[i];
         fill_ctx(r, target);
         r->hw->stop = 0; r->hw->error = 0;
         CK(cudaMemcpyAsync(r->d_ctx, &r->h_ctx, sizeof(apus_devctx_t), cudaMemcpyHostToDevice, owner->stream));
-        roles[i].kind = is_leader(r) ? APUS_ROLE_LEADER : APUS_ROLE_FOLLOWER;
-        roles[i].pad = 0;
-        roles[i].ctx = r->d_ctx;
+        if (is_leader(r)) {
+            for (uint32_t w = 0; w < r->h_ctx.n_workers; w++) {
+                if (nroles >= 64) return fail("too many roles in one launch");
+                roles[nroles].kind = APUS_ROLE_LEADER; roles[nroles].worker = w; roles[nroles].ctx = r->d_ctx; nroles++;
+            }
+        } else {
+            if (nroles >= 64) return fail("too many roles in one launch");
+            roles[nroles].kind = APUS_ROLE_FOLLOWER; roles[nroles].worker = 0; roles[nroles].ctx = r->d_ctx; nroles++;
+        }
     }
-    CK(cudaMemcpyAsync(owner->d_roles, roles, sizeof(apus_role_t) * n, cudaMemcpyHostToDevice, owner->stream));
+    CK(cudaMemcpyAsync(owner->d_roles, roles, sizeof(apus_role_t) * nroles, cudaMemcpyHostToDevice, owner->stream));
     /* roles[] is on the stack: the copy above must have read it before we return */
     CK(cudaStreamSynchronize(owner->stream));
     CK(cudaEventRecord(owner->ev_start, owner->stream));
-    CK(apus_launch_roles(owner->d_roles, n, owner->stream));
+    CK(apus_launch_roles(owner->d_roles, nroles, owner->stream));
     CK(cudaEventRecord(owner->ev_stop, owner->stream));
     for (int i = 0; i < n; i++) {
         rs[i]->launch_owner = owner;
@@ -568,7 +578,7 @@ extern "C" int apus_log_offsets(apus_replica_t *r, apus_log_offsets_t *out)
     if (!r || !out) return fail("null argument");
     DeviceGuard g(r->cfg.device);
     apus_loghdr_t h;
-    CK(cudaMemcpyAsync(&h, r->region + APUS_CTRL_BYTES, sizeof h, cudaMemcpyDeviceToHost, r->copy_stream));
+    CK(cudaMemcpyAsync(&h, r->region + APUS_HDR_OFF, sizeof h, cudaMemcpyDeviceToHost, r->copy_stream));
     CK(cudaStreamSynchronize(r->copy_stream));
     out->head = h.head; out->apply = h.apply; out->commit = h.commit; out->end = h.end;
     out->tail = h.tail; out->old_end = h.old_end; out->old_commit = h.old_commit; out->len = h.len;
@@ -635,7 +645,7 @@ extern "C" int apus_set_head(apus_replica_t *r, uint64_t head)
     DeviceGuard g(r->cfg.device);
     static __thread uint64_t stage;
     stage = head;
-    CK(cudaMemcpyAsync(r->region + APUS_CTRL_BYTES + offsetof(apus_loghdr_t, head), &stage, 8,
+    CK(cudaMemcpyAsync(r->region + APUS_HDR_OFF + offsetof(apus_loghdr_t, head), &stage, 8,
                        cudaMemcpyHostToDevice, r->copy_stream));
     CK(cudaStreamSynchronize(r->copy_stream));
     return APUS_OK;

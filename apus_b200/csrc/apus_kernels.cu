@@ -136,41 +136,30 @@ __device__ __forceinline__ uint64_t ring_dist(uint64_t from, uint64_t to, uint64
 // ---------------------------------------------------------------------------------
 // shared memory
 // ---------------------------------------------------------------------------------
-#define PUB_RING 256u
 #define N_PRODUCER_WARPS 15
 #define NT (N_PRODUCER_WARPS * 32)      // producer threads
 #define MAXB APUS_MAX_TILE_ENTRIES
+#define PUBMASK (APUS_PUBRING_RECORDS - 1)
 
 struct LeaderShared {
-    // tile table (one row per entry of the tile)
-    uint32_t rel[MAXB];        // entry start - tile start (bytes)
-    uint32_t xoff[MAXB];       // offset of the entry's image in the ext staging (EXT entries)
-    // tile control (written by thread 0 / warp 0, read by all producers)
-    uint32_t n_fetch;          // slots fetched this round
-    uint32_t m;                // entries in the tile
-    uint32_t gap;              // 1: wrap-gap tile (range [a, len), optional ghost of entry 0)
-    uint32_t ghost;            // 1: ghost header is composed at a
-    uint32_t fresh;            // 1: the range was never written (holes are zero)
-    uint32_t finish;           // producers are done
-    uint32_t auto_head;        // 1: the tile starts with a HEAD entry appended by the pruning rule
-    uint32_t ext_bytes;        // payload-ring bytes to stage for this tile
-    uint64_t ext_base;         // ... starting at this payload-ring offset
-    uint64_t auto_head_val;    // head offset carried by the auto HEAD entry
-    uint64_t a, b;             // byte range of the tile in the log
-    uint64_t idx0;             // idx of the tile's first entry
-    uint64_t t_dequeue;
-    uint8_t *peer_entries[APUS_MAX_SERVERS];
+    // per fetched slot (filled while fetching: no strided re-reads of the 128 B slots)
+    uint32_t es[MAXB];         // log stride of the entry (64 + len, or 64)
+    uint32_t xb[MAXB];         // payload-ring bytes to stage for it (0 when inline)
+    uint32_t rel[MAXB];        // entry start - sub-tile start (bytes)
+    uint32_t xoff[MAXB];       // offset of the entry's image in the ext staging
+    uint8_t  ty[MAXB];
+    uint8_t  flg[MAXB];        // bit0 EXT, bit1 WRAP
+    // claim
+    uint32_t n_fetch, finish;
+    uint64_t slot0, my_seq, t_dequeue;
+    // placement state while this CTA holds the place turn (mirrors apus_seq_t.p_*)
+    uint64_t st_end, st_tail, st_next_idx, st_hwm, st_placed, st_auto_heads;
+    uint32_t st_prev_head, pad0;
+    // current sub-tile
+    uint32_t kbase, m, gap, ghost, fresh, auto_head, ext_bytes, last, blocked, pad1;
+    uint64_t ext_base, auto_head_val, a, b, idx0, cum_after, new_end, tail_after, hwm_after, auto_heads_after;
+    uint8_t  *peer_entries[APUS_MAX_SERVERS];
     uint32_t *peer_index[APUS_MAX_SERVERS];
-    // publishes in flight: producer -> commit warp
-    uint64_t pub_cum[PUB_RING];      // entries published up to and including this tile
-    uint64_t pub_end[PUB_RING];      // `end` after this tile
-    uint64_t pub_tickets[PUB_RING];  // tickets consumed up to and including this tile
-    uint64_t pub_t0[PUB_RING];
-    volatile uint64_t pub_head;      // next slot the producer writes
-    volatile uint64_t pub_tail;      // next slot the commit warp reads
-    volatile uint64_t published;     // entries published (the leader's own "ack")
-    volatile uint32_t producers_done;
-    volatile uint32_t abort_flag;
 };
 
 #define LS_BYTES ((sizeof(LeaderShared) + 127u) & ~127u)
@@ -193,6 +182,18 @@ struct FollowerShared {
 
 extern __shared__ __align__(16) uint8_t smem_raw[];
 
+// gpu-scope handoffs between the leader's worker CTAs
+__device__ __forceinline__ uint64_t ld_acquire_gpu(const volatile void *p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(volatile void *p, uint64_t v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // ---------------------------------------------------------------------------------
 // LEADER
 // ---------------------------------------------------------------------------------
@@ -210,16 +211,16 @@ __device__ __forceinline__ uint32_t hdr_byte(uint32_t j, uint64_t idx, uint64_t 
     return 0;   // reply[13]
 }
 
-// bytes 0..40 of an entry header into shared memory at any alignment
-__device__ __forceinline__ void warp_write_header(uint8_t *e, int lane, uint64_t idx, uint64_t term, uint64_t req_id,
-                                                  uint32_t clt, uint32_t type, uint32_t sender, bool skip_sender)
+// bytes 0..40 of an entry header into shared memory at any alignment, by `gl` lanes (sub = lane in group)
+__device__ __forceinline__ void group_write_header(uint8_t *e, int sub, int gl, uint64_t idx, uint64_t term, uint64_t req_id,
+                                                   uint32_t clt, uint32_t type, uint32_t sender, bool skip_sender)
 {
     if ((((uint32_t)(uintptr_t)e) & 7u) == 0) {
         // aligned entry: 8-byte stores for bytes 0..39, byte 40 separately; bytes 41..47 stay (hole)
-        if (lane == 0) *reinterpret_cast<uint64_t *>(e + 0) = idx;
-        else if (lane == 1) *reinterpret_cast<uint64_t *>(e + 8) = term;
-        else if (lane == 2) *reinterpret_cast<uint64_t *>(e + 16) = req_id;
-        else if (lane == 3) {
+        if (sub == 0) *reinterpret_cast<uint64_t *>(e + 0) = idx;
+        else if (sub == 1) *reinterpret_cast<uint64_t *>(e + 8) = term;
+        else if (sub == 2) *reinterpret_cast<uint64_t *>(e + 16) = req_id;
+        else if (sub == 3) {
             if (skip_sender) {
                 e[24] = (uint8_t)clt; e[25] = (uint8_t)(clt >> 8); e[26] = (uint8_t)type;
                 e[28] = 0; e[29] = 0; e[30] = 0; e[31] = 0;
@@ -227,20 +228,20 @@ __device__ __forceinline__ void warp_write_header(uint8_t *e, int lane, uint64_t
                 *reinterpret_cast<uint64_t *>(e + 24) =
                     (uint64_t)(clt & 0xffffu) | ((uint64_t)type << 16) | ((uint64_t)sender << 24);
             }
-        } else if (lane == 4) *reinterpret_cast<uint64_t *>(e + 32) = 0;
-        else if (lane == 5) e[40] = 0;
+        } else if (sub == 4) *reinterpret_cast<uint64_t *>(e + 32) = 0;
+        else if (sub == 5) e[40] = 0;
     } else {
-        for (uint32_t j = lane; j < 41; j += 32)
+        for (uint32_t j = sub; j < 41; j += gl)
             if (!(skip_sender && j == E_SENDER)) e[j] = (uint8_t)hdr_byte(j, idx, term, req_id, clt, type, sender);
     }
 }
 
 // copy nbytes from a 16 B-aligned shared source to an arbitrarily aligned shared destination
-__device__ __forceinline__ void warp_copy_smem(uint8_t *dst, const uint8_t *src, uint32_t nbytes, int lane)
+__device__ __forceinline__ void group_copy_smem(uint8_t *dst, const uint8_t *src, uint32_t nbytes, int sub, int gl)
 {
     const uint32_t nchunks = (nbytes + 15u) >> 4;
     const uint32_t dalign = (uint32_t)(uintptr_t)dst & 15u;
-    for (uint32_t c = lane; c < nchunks; c += 32) {
+    for (uint32_t c = sub; c < nchunks; c += gl) {
         const uint4 v = *reinterpret_cast<const uint4 *>(src + 16u * c);
         uint8_t *d = dst + 16u * c;
         const uint32_t left = nbytes - 16u * c;
@@ -281,27 +282,70 @@ __device__ __forceinline__ void cta_fetch_chunks(uint8_t *dst, const uint8_t *sr
     for (; c < nchunks; c += NT) reinterpret_cast<uint4 *>(dst)[c] = ld_relaxed_sys_v4(src + 16ull * c);
 }
 
-__device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx, LeaderShared *S)
+// the descriptor chunk of a slot -> compact per-entry arrays
+__device__ __forceinline__ void note_desc(LeaderShared *S, uint32_t k, const uint4 v)
+{
+    const uint32_t to = v.z, ty = (to >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK, len = v.w & 0xffffu;
+    S->ty[k] = (uint8_t)ty;
+    S->flg[k] = (uint8_t)(((to & APUS_SLOT_EXT) ? 1u : 0u) | ((to & APUS_SLOT_WRAP) ? 2u : 0u));
+    S->es[k] = entry_stride(ty, len);
+    S->xb[k] = (to & APUS_SLOT_EXT) ? ((data_bytes(ty, len) + 15u) & ~15u) : 0u;
+}
+
+// fetch `cnt` slots starting at ring slot `s` into shared slot `k0` onward
+__device__ __forceinline__ void cta_fetch_slots(LeaderShared *S, uint8_t *slots, const apus_slot_t *ring, uint64_t s, uint32_t k0,
+                                                uint32_t cnt, int tid)
+{
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(ring + s);
+    uint8_t *dst = slots + (size_t)k0 * APUS_SLOT_BYTES;
+    const uint32_t nchunks = cnt * 8u;
+    uint32_t c = tid;
+    for (; c + 3u * NT < nchunks; c += 4u * NT) {
+        const uint4 v0 = ld_relaxed_sys_v4(src + 16ull * c);
+        const uint4 v1 = ld_relaxed_sys_v4(src + 16ull * (c + NT));
+        const uint4 v2 = ld_relaxed_sys_v4(src + 16ull * (c + 2u * NT));
+        const uint4 v3 = ld_relaxed_sys_v4(src + 16ull * (c + 3u * NT));
+        reinterpret_cast<uint4 *>(dst)[c] = v0;
+        reinterpret_cast<uint4 *>(dst)[c + NT] = v1;
+        reinterpret_cast<uint4 *>(dst)[c + 2u * NT] = v2;
+        reinterpret_cast<uint4 *>(dst)[c + 3u * NT] = v3;
+        if ((c & 7u) == 0) note_desc(S, k0 + (c >> 3), v0);
+        if (((c + NT) & 7u) == 0) note_desc(S, k0 + ((c + NT) >> 3), v1);
+        if (((c + 2u * NT) & 7u) == 0) note_desc(S, k0 + ((c + 2u * NT) >> 3), v2);
+        if (((c + 3u * NT) & 7u) == 0) note_desc(S, k0 + ((c + 3u * NT) >> 3), v3);
+    }
+    for (; c < nchunks; c += NT) {
+        const uint4 v = ld_relaxed_sys_v4(src + 16ull * c);
+        reinterpret_cast<uint4 *>(dst)[c] = v;
+        if ((c & 7u) == 0) note_desc(S, k0 + (c >> 3), v);
+    }
+}
+
+__device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
 {
     const int lane = threadIdx.x & 31;
     const int N = cx->group_size, me = cx->idx, quorum = cx->quorum;
     apus_ctrl_t *ctrl = reinterpret_cast<apus_ctrl_t *>(cx->region);
-    apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_CTRL_BYTES);
+    apus_seq_t *seq = reinterpret_cast<apus_seq_t *>(cx->region + APUS_SEQ_OFF);
+    const apus_pubrec_t *ring = reinterpret_cast<const apus_pubrec_t *>(cx->region + APUS_PUBRING_OFF);
+    apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_HDR_OFF);
     apus_hostwords_t *hw = cx->hw;
     uint64_t committed = ctrl->committed;
     uint64_t committed_tickets = ctrl->committed_tickets;
     uint64_t lat_count = ctrl->lat_count;
+    uint64_t tail = ld_relaxed_sys(&seq->pub_tail);
     uint64_t last_progress = globaltimer_ns();
     uint32_t spins = 0;
     volatile uint64_t *peer_commit = nullptr;
     if (lane < N && lane != me && cx->peer[lane])
-        peer_commit = &reinterpret_cast<apus_loghdr_t *>(cx->peer[lane] + APUS_CTRL_BYTES)->commit;
+        peer_commit = &reinterpret_cast<apus_loghdr_t *>(cx->peer[lane] + APUS_HDR_OFF)->commit;
 
     for (;;) {
         // lane i holds what replica i has acked (entries, monotone); the leader's own
         // vote is everything it has published (dare_ibv_rc.c:1736 "i == idx")
         uint64_t v = 0;
-        if (lane < N) v = (lane == me) ? S->published : ld_relaxed_sys(&ctrl->ack[lane]);
+        if (lane < N) v = (lane == me) ? ld_relaxed_sys(&ctrl->published) : ld_relaxed_sys(&ctrl->ack[lane]);
+        const uint64_t published_now = __shfl_sync(0xffffffffu, v, me);
         // rank: how many replicas hold at least what I hold
         int cnt = 0;
         for (int j = 0; j < N; j++) {
@@ -316,21 +360,24 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx, LeaderS
         }
         const uint64_t Q = cand;
         if (Q > committed) {
-            // (no acquire fence: the commit rule consumes nothing but the ack words themselves)
+            // (no acquire fence on the followers' side of things: the commit rule consumes
+            //  nothing but the ack words themselves)
             // map the entry count to the log offset recorded at publish time
-            uint64_t tail = S->pub_tail, head = S->pub_head;
-            uint64_t off = 0, tickets = committed_tickets, t0 = 0;
+            const uint64_t head = ld_acquire_gpu(&seq->pub_head);
+            uint64_t off = 0, tickets = committed_tickets;
             bool any = false;
-            while (tail != head && S->pub_cum[tail & (PUB_RING - 1)] <= Q) {
-                off = S->pub_end[tail & (PUB_RING - 1)];
-                tickets = S->pub_tickets[tail & (PUB_RING - 1)];
-                t0 = S->pub_t0[tail & (PUB_RING - 1)];
+            while (tail != head) {
+                const apus_pubrec_t *r = &ring[tail & PUBMASK];
+                const uint64_t cum = ld_relaxed_sys(&r->cum);
+                if (cum > Q) break;
+                off = ld_relaxed_sys(&r->end);
+                tickets = ld_relaxed_sys(&r->tickets);
                 if ((cx->flags & APUS_FLAG_STATS) && cx->lat_ns && lane == 0) {
-                    uint64_t d = globaltimer_ns() - t0;
+                    const uint64_t d = globaltimer_ns() - ld_relaxed_sys(&r->t0);
                     cx->lat_ns[lat_count & (APUS_LAT_RING - 1)] = d > 0xffffffffull ? 0xffffffffu : (uint32_t)d;
                 }
                 lat_count++;
-                committed = S->pub_cum[tail & (PUB_RING - 1)];
+                committed = cum;
                 tail++;
                 any = true;
             }
@@ -345,23 +392,25 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx, LeaderS
                     ctrl->lat_count = lat_count;
                     st_relaxed_sys(&hw->commit_off, off);
                     st_relaxed_sys(&hw->committed_tickets, tickets);        // releases proxy.c:160 spinners
-                    S->pub_tail = tail;
+                    st_release_gpu(&seq->pub_tail, tail);
                 }
                 committed_tickets = tickets;
                 last_progress = globaltimer_ns();
                 __syncwarp();
             }
         }
-        // exit: producers finished and nothing is in flight
+        // exit: every worker finished and nothing is in flight
         int ex = 0;
         if (lane == 0) {
-            if (S->producers_done && committed == S->published) ex = 1;
+            if (ld_acquire_gpu(&seq->workers_done) == cx->n_workers && committed == ld_relaxed_sys(&ctrl->published)) ex = 1;
             else if ((++spins & 0x3ffu) == 0) {
-                if (ld_relaxed_sys_u32(&hw->stop) || S->abort_flag) ex = 2;
-                else if (cx->target != ~0ull && globaltimer_ns() - last_progress > WATCHDOG_NS &&
-                         committed != S->published) {
+                if (ld_relaxed_sys(&seq->abort_flag)) ex = 2;
+                else if (ld_relaxed_sys_u32(&hw->stop) && committed == published_now &&
+                         ld_acquire_gpu(&seq->workers_done) == cx->n_workers) ex = 2;
+                else if (globaltimer_ns() - last_progress > WATCHDOG_NS && committed != published_now &&
+                         (cx->target != ~0ull || ld_relaxed_sys_u32(&hw->stop))) {
                     st_relaxed_sys(&hw->error, APUS_KERR_WATCHDOG_COMMIT);
-                    S->abort_flag = 1;
+                    st_relaxed_sys(&seq->abort_flag, 1);
                     ex = 2;
                 }
             }
@@ -381,7 +430,130 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx, LeaderS
     }
 }
 
-__device__ void leader_main(const apus_devctx_t *__restrict__ cx)
+// T2: place the next sub-tile of the fetched batch (entries kbase..nf) -- log_append_entry's offset
+// rules, free-space rule E2 and the pruning rule, all on the placement state this CTA holds.
+__device__ void leader_place(const apus_devctx_t *__restrict__ cx, LeaderShared *S, const apus_slot_t *sl, int lane)
+{
+    const int N = cx->group_size, me = cx->idx;
+    apus_ctrl_t *ctrl = reinterpret_cast<apus_ctrl_t *>(cx->region);
+    apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_HDR_OFF);
+    const uint64_t L = cx->log_len;
+    const bool autoprune = (cx->flags & APUS_FLAG_AUTOPRUNE) != 0;
+    const uint32_t kbase = S->kbase, nf = S->n_fetch;
+    const uint64_t end = S->st_end;
+
+    uint64_t head = ld_relaxed_sys(&hdr->head);
+    const uint64_t pos0 = (end == L) ? 0 : end;               // empty log starts at 0 (dare_log.h:216-219)
+    uint64_t used = (end == L) ? 0 : ring_dist(head, end, L);
+    // ---- device-side log pruning (log_pruning / force_log_pruning, dare_server.c:1996-2122):
+    //      head := the smallest apply offset in the group, published through a HEAD entry
+    uint32_t autoh = 0;
+    uint64_t new_head = 0;
+    if (autoprune && end != L && used >= (L >> 2) && !S->st_prev_head && L - pos0 >= APUS_HDR_BYTES) {
+        uint64_t d = 0;                                   // distance apply -> end, per replica
+        if (lane < N) {
+            const uint64_t ap = (lane == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[lane]);
+            d = ring_dist(ap, end, L);
+            if (d > used) d = used;                       // never behind the current head
+        }
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            const uint64_t o = __shfl_xor_sync(0xffffffffu, d, sft);
+            d = o > d ? o : d;
+        }
+        if (d == 0) d = ring_dist(S->st_tail, end, L);    // leave one entry (dare_server.c:2031-2034)
+        if (d <= used && used - d >= (L >> 3)) {
+            autoh = 1;
+            new_head = (end >= d) ? end - d : L - (d - end);
+            used = d;                                     // the head moves before the append (:2041)
+            head = new_head;
+        }
+    }
+    const uint32_t hbytes = autoh ? APUS_HDR_BYTES : 0;
+    // limits for a contiguous sub-tile starting at pos0
+    uint64_t lim = L - pos0;                                   // no entry may cross len
+    const uint64_t imgcap = APUS_LEADER_IMG_BYTES - 16u - (pos0 & 15u);
+    if (lim > imgcap) lim = imgcap;
+    // rule E2: stay strictly before head (keep room for one HEAD entry when pruning on the device)
+    const uint64_t reserve = autoprune ? APUS_HDR_BYTES : 0;
+    const uint64_t lim_space = (L - used > 1 + reserve) ? (L - used - 1 - reserve) : 0;
+    const uint64_t limit = lim < lim_space ? lim : lim_space;
+
+    // rounds of 32 entries: inclusive scans of log strides and of staged payload bytes
+    uint32_t carry = hbytes, xcarry = 0, m = nf - kbase, first_ext = 0xffffffffu;
+    for (uint32_t r = kbase; r < nf; r += 32) {
+        const uint32_t k = r + lane;
+        const bool in = k < nf;
+        const uint32_t es = in ? S->es[k] : 0u, xb = in ? S->xb[k] : 0u;
+        uint32_t inc = es, xinc = xb;
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, sft);
+            const uint32_t xo = __shfl_up_sync(0xffffffffu, xinc, sft);
+            if (lane >= sft) { inc += o; xinc += xo; }
+        }
+        const uint32_t run = carry + inc - es, xrun = xcarry + xinc - xb;     // exclusive
+        const bool bad = in && ((uint64_t)run + es > limit || xrun + xb > APUS_LEADER_EXT_BYTES ||
+                                (k > kbase && (S->flg[k] & 2u)));
+        const uint32_t badmask = __ballot_sync(0xffffffffu, bad);
+        const uint32_t good = badmask ? (uint32_t)(__ffs(badmask) - 1) : 32u;   // lanes below `good` are placed
+        if (in && (uint32_t)lane < good) { S->rel[k] = run; S->xoff[k] = xrun; }
+        if (first_ext == 0xffffffffu) {
+            const uint32_t extmask = __ballot_sync(0xffffffffu, in && (uint32_t)lane < good && (S->flg[k] & 1u));
+            if (extmask) first_ext = r + (uint32_t)(__ffs(extmask) - 1);
+        }
+        if (badmask) { m = r + good - kbase; xcarry = __shfl_sync(0xffffffffu, xrun, good); carry = __shfl_sync(0xffffffffu, run, good); break; }
+        carry = __shfl_sync(0xffffffffu, run + es, 31);
+        xcarry = __shfl_sync(0xffffffffu, xrun + xb, 31);
+    }
+    // carry = log bytes of the sub-tile (HEAD entry included), xcarry = staged payload bytes
+    if (lane == 0) {
+        S->gap = 0; S->ghost = 0; S->blocked = 0; S->last = 0;
+        uint64_t a = pos0, b = pos0;
+        if (m == 0 && !autoh) {
+            // entry kbase does not fit at pos0: wrap (dare_log.h:502-504, 526-538) or no space
+            const uint32_t es0 = S->es[kbase];
+            const uint64_t left = L - pos0;
+            if (es0 > left && used + left + es0 + reserve < L) {
+                S->gap = 1;
+                S->ghost = (left >= APUS_HDR_BYTES && has_cmd(S->ty[kbase])) ? 1u : 0u;   // header fits: ghost stays behind
+                b = L;
+            } else {
+                S->blocked = 1;        // back-pressure: wait for head to advance
+            }
+        } else {
+            b = pos0 + carry;
+        }
+        S->a = a; S->b = b; S->m = m;
+        S->ext_bytes = (m && first_ext != 0xffffffffu) ? xcarry : 0u;
+        S->ext_base = (first_ext != 0xffffffffu) ? (uint64_t)(sl[first_ext].type_off & APUS_SLOT_OFF_MASK) * 16ull : 0ull;
+        S->auto_head = autoh; S->auto_head_val = new_head;
+        S->idx0 = S->st_next_idx;
+        S->fresh = (a >= S->st_hwm) ? 1u : 0u;
+        if (!S->blocked) {
+            // commit the placement to the state this CTA carries
+            if (autoh) st_relaxed_sys(&hdr->head, new_head);
+            if (S->gap) {
+                S->st_end = 0; S->st_hwm = L;
+            } else {
+                uint64_t ne = b; if (ne == L) ne = 0;                   // rule E1
+                S->new_end = ne;
+                S->st_end = ne;
+                S->st_tail = m ? a + S->rel[kbase + m - 1] : a;
+                S->tail_after = S->st_tail;
+                S->st_next_idx += m + autoh;
+                S->st_placed += m + autoh;
+                S->cum_after = S->st_placed;
+                S->st_auto_heads += autoh;
+                S->auto_heads_after = S->st_auto_heads;
+                S->st_prev_head = (autoh && m == 0) ? 1u : 0u;         // never two HEAD entries in a row (dare_log.h:477-480)
+                if (b > S->st_hwm) S->st_hwm = b;
+                S->last = (kbase + m == nf) ? 1u : 0u;
+            }
+            S->hwm_after = S->st_hwm;
+        }
+    }
+}
+
+__device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t wid)
 {
     LeaderShared *S = reinterpret_cast<LeaderShared *>(smem_raw);
     uint8_t *slots = smem_raw + L_SLOTS_OFF;
@@ -390,78 +562,93 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = cx->group_size, me = cx->idx;
     apus_ctrl_t *ctrl = reinterpret_cast<apus_ctrl_t *>(cx->region);
-    apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_CTRL_BYTES);
+    apus_seq_t *seq = reinterpret_cast<apus_seq_t *>(cx->region + APUS_SEQ_OFF);
+    apus_pubrec_t *pubring = reinterpret_cast<apus_pubrec_t *>(cx->region + APUS_PUBRING_OFF);
+    apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_HDR_OFF);
     uint8_t *entries = cx->region + cx->entries_off;
+    uint32_t *lindex = reinterpret_cast<uint32_t *>(cx->region + APUS_INDEX_OFF);
     apus_hostwords_t *hw = cx->hw;
-    const uint64_t L = cx->log_len;
-    const bool autoprune = (cx->flags & APUS_FLAG_AUTOPRUNE) != 0;
 
+    // ---- sequencer reset handshake: worker 0 prepares the shared words of this launch ----
     if (tid == 0) {
-        S->pub_head = 0; S->pub_tail = 0;
-        S->published = ctrl->published;
-        S->producers_done = 0; S->abort_flag = 0; S->finish = 0;
-        for (int i = 0; i < APUS_MAX_SERVERS; i++)
-        {
+        if (wid == 0) {
+            seq->claim_ticket = 0; seq->claim_serving = 0;
+            seq->claimed_slots = ctrl->consumed; seq->tile_seq = 0; seq->claims_closed = 0;
+            seq->place_seq = 0; seq->pub_seq = 0; seq->workers_done = 0; seq->abort_flag = 0;
+            seq->p_end = hdr->end; seq->p_tail = hdr->tail; seq->p_next_idx = ctrl->next_idx; seq->p_hwm = ctrl->hwm;
+            seq->p_placed = ctrl->published; seq->p_prev_head = 0; seq->p_auto_heads = ctrl->auto_heads;
+            // entries published by an earlier launch but not yet committed come back as one record
+            seq->pub_head = 0; seq->pub_tail = 0;
+            if (ctrl->published != ctrl->committed) {
+                pubring[0].cum = ctrl->published; pubring[0].end = hdr->end;
+                pubring[0].tickets = ctrl->consumed; pubring[0].t0 = globaltimer_ns();
+                seq->pub_head = 1;
+            }
+            __threadfence();
+            st_release_gpu(&seq->ready_epoch, cx->epoch);
+        } else {
+            while (ld_acquire_gpu(&seq->ready_epoch) != cx->epoch) { }
+        }
+        S->finish = 0;
+        for (int i = 0; i < APUS_MAX_SERVERS; i++) {
             S->peer_entries[i] = (i < N && i != me && cx->peer[i]) ? cx->peer[i] + cx->entries_off : nullptr;
             S->peer_index[i] = (i < N && i != me && cx->peer[i]) ? reinterpret_cast<uint32_t *>(cx->peer[i] + APUS_INDEX_OFF) : nullptr;
-        }
-        // entries published by an earlier launch but not yet committed come back as one record
-        if (ctrl->published != ctrl->committed) {
-            S->pub_cum[0] = ctrl->published; S->pub_end[0] = hdr->end;
-            S->pub_tickets[0] = ctrl->consumed; S->pub_t0[0] = globaltimer_ns();
-            S->pub_head = 1;
         }
     }
     __syncthreads();
 
-    if (warp == N_PRODUCER_WARPS) {   // warp 15
-        leader_commit_warp(cx, S);
+    if (warp == N_PRODUCER_WARPS) {   // warp 15: the commit warp lives in worker 0
+        if (wid == 0) leader_commit_warp(cx);
         return;
     }
 
     // ---- producer warps 0..14 ------------------------------------------------------
-    // state mirrored in registers of every producer thread (updated uniformly)
-    uint64_t end = hdr->end, tailpos = hdr->tail, next_idx = ctrl->next_idx;
-    uint64_t consumed = ctrl->consumed, published = ctrl->published, hwm = ctrl->hwm;
-    uint64_t bytes_rep = ctrl->bytes_replicated, batches = ctrl->batches;
-    uint64_t auto_heads = ctrl->auto_heads;
     uint64_t last_progress = globaltimer_ns();
-    bool prev_head = false;     // the last entry appended is a HEAD entry of the pruning rule
-    const bool prof = (cx->flags & APUS_FLAG_STATS) != 0 && tid == 0;
+    const bool prof = (cx->flags & APUS_FLAG_STATS) != 0 && tid == 0 && wid == 0;
     uint64_t ph[8], tprev = globaltimer_ns();
     for (int i = 0; i < 8; i++) ph[i] = ctrl->phase_ns[i];
 #define PHASE(i) do { if (prof) { const uint64_t _t = globaltimer_ns(); ph[i] += _t - tprev; tprev = _t; } } while (0)
 
     for (;;) {
-        // ---- T0: wait for requests (thread 0) ---------------------------------------
+        // ---- T0: claim the next slots of the submission ring (ticket lock: one poller at a time) ----
         if (tid == 0) {
             uint32_t n = 0, fin = 0, spins = 0;
-            for (;;) {
-                if (consumed >= cx->target) { fin = 1; break; }
-                uint64_t t = ld_relaxed_sys(cx->sub_tail);
-                uint64_t avail = t - consumed;
+            const uint64_t ticket = atomicAdd(reinterpret_cast<unsigned long long *>(&seq->claim_ticket), 1ull);
+            while (ld_acquire_gpu(&seq->claim_serving) != ticket) {
+                if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
+            }
+            if (ld_relaxed_sys(&seq->claims_closed) || ld_relaxed_sys(&seq->abort_flag)) fin = 1;
+            uint64_t claimed = ld_relaxed_sys(&seq->claimed_slots);
+            while (!fin) {
+                if (claimed >= cx->target) { fin = 1; break; }
+                const uint64_t t = ld_relaxed_sys(cx->sub_tail);
+                uint64_t avail = t - claimed;
                 if (avail) {
-                    uint64_t room = cx->target - consumed;
+                    const uint64_t room = cx->target - claimed;
                     if (avail > room) avail = room;
-                    n = avail > MAXB ? MAXB : (uint32_t)avail;
-                    // do not overrun the in-flight publish ring
-                    uint32_t w = 0;
-                    while (S->pub_head - S->pub_tail >= PUB_RING - 2) {
-                        if (S->abort_flag || ((++w & 0xfffu) == 0 && ld_relaxed_sys_u32(&hw->stop))) {
-                            n = 0; fin = 1; break;
-                        }
-                    }
+                    // share a shallow queue between the workers instead of one big tile
+                    uint64_t want = (avail + cx->n_workers - 1) / cx->n_workers;
+                    if (want < 32) want = avail < 32 ? avail : 32;
+                    n = want > MAXB ? MAXB : (uint32_t)want;
                     break;
                 }
                 if ((++spins & 0xffu) == 0) {
-                    if (ld_relaxed_sys_u32(&hw->stop) || S->abort_flag) { fin = 1; break; }
+                    if (ld_relaxed_sys_u32(&hw->stop) || ld_relaxed_sys(&seq->abort_flag)) { fin = 1; break; }
                     if (cx->target != ~0ull && globaltimer_ns() - last_progress > WATCHDOG_NS) {
                         st_relaxed_sys(&hw->error, APUS_KERR_WATCHDOG_LEADER);
-                        S->abort_flag = 1; fin = 1; break;
+                        st_relaxed_sys(&seq->abort_flag, 1); fin = 1; break;
                     }
                 }
             }
-            if (n) __threadfence_system();   // acquire: slots + payload behind the doorbell
+            if (fin) st_relaxed_sys(&seq->claims_closed, 1);
+            if (n) {
+                S->slot0 = claimed; S->my_seq = ld_relaxed_sys(&seq->tile_seq);
+                st_relaxed_sys(&seq->claimed_slots, claimed + n);
+                st_relaxed_sys(&seq->tile_seq, S->my_seq + 1);
+            }
+            st_release_gpu(&seq->claim_serving, ticket + 1);
+            // (slots are read with ld.relaxed.sys AFTER the doorbell value arrived; the host wrote
+            //  them before ringing it -- message passing without a 1.5 us system fence)
             S->n_fetch = n; S->finish = fin;
             S->t_dequeue = globaltimer_ns();
         }
@@ -472,298 +659,197 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx)
 
         // ---- T1: fetch the slots (descriptor + inline payload), coalesced 16 B loads --------
         {
-            const uint64_t s0 = consumed & cx->sub_mask;
+            const uint64_t s0 = S->slot0 & cx->sub_mask;
             const uint64_t nslots = (uint64_t)cx->sub_mask + 1;
             const uint32_t first = (s0 + nf <= nslots) ? nf : (uint32_t)(nslots - s0);   // ring wrap: two runs
-            cta_fetch_chunks(slots, reinterpret_cast<const uint8_t *>(cx->sub_slots + s0), first * 8u, tid);
-            if (first < nf)
-                cta_fetch_chunks(slots + (size_t)first * APUS_SLOT_BYTES, reinterpret_cast<const uint8_t *>(cx->sub_slots),
-                                 (nf - first) * 8u, tid);
+            cta_fetch_slots(S, slots, cx->sub_slots, s0, 0, first, tid);
+            if (first < nf) cta_fetch_slots(S, slots, cx->sub_slots, 0, first, nf - first, tid);
+        }
+        // ---- wait for the place turn, take over the placement state ----
+        if (tid == 0) {
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(&seq->place_seq) != S->my_seq) {
+                if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
+            }
+            S->st_end = seq->p_end; S->st_tail = seq->p_tail; S->st_next_idx = seq->p_next_idx; S->st_hwm = seq->p_hwm;
+            S->st_placed = seq->p_placed; S->st_prev_head = (uint32_t)seq->p_prev_head; S->st_auto_heads = seq->p_auto_heads;
+            S->kbase = 0;
         }
         bar_sync(1, NT);
         PHASE(1);
         const apus_slot_t *sl = reinterpret_cast<const apus_slot_t *>(slots);
+        bool have_pub_turn = false, aborted = false;
+        uint64_t gap_bytes = 0;      // bytes of a wrap gap replicated ahead of the next publish
 
-        // ---- T2: placement (warp 0): log_append_entry's offset rules over the tile ----
-        if (warp == 0) {
-            uint64_t head = ld_relaxed_sys(&hdr->head);
-            const uint64_t pos0 = (end == L) ? 0 : end;               // empty log starts at 0 (dare_log.h:216-219)
-            uint64_t used = (end == L) ? 0 : ring_dist(head, end, L);
-            // ---- device-side log pruning (log_pruning / force_log_pruning,
-            //      dare_server.c:1996-2122): head := the smallest apply offset in the group,
-            //      published through a HEAD entry placed in front of this tile
-            uint32_t autoh = 0;
-            uint64_t new_head = 0;
-            if (autoprune && end != L && used >= (L >> 2) && !prev_head && L - pos0 >= APUS_HDR_BYTES) {
-                uint64_t d = 0;                                   // distance apply -> end, per replica
-                if (lane < N) {
-                    const uint64_t ap = (lane == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[lane]);
-                    d = ring_dist(ap, end, L);
-                    if (d > used) d = used;                       // never behind the current head
-                }
-                for (int sft = 16; sft > 0; sft >>= 1) {
-                    const uint64_t o = __shfl_xor_sync(0xffffffffu, d, sft);
-                    d = o > d ? o : d;
-                }
-                if (d == 0) d = ring_dist(tailpos, end, L);       // leave one entry (dare_server.c:2031-2034)
-                if (d <= used && used - d >= (L >> 3)) {
-                    autoh = 1;
-                    new_head = (end >= d) ? end - d : L - (d - end);
-                    used = d;                                     // the head moves before the append (:2041)
-                    head = new_head;
-                }
-            }
-            const uint64_t hbytes = autoh ? APUS_HDR_BYTES : 0;
-            // limits for a contiguous tile starting at pos0
-            uint64_t lim = L - pos0;                                   // no entry may cross len
-            const uint64_t imgcap = APUS_LEADER_IMG_BYTES - 16u - (pos0 & 15u);
-            if (lim > imgcap) lim = imgcap;
-            // rule E2: stay strictly before head (keep room for one HEAD entry when pruning on the device)
-            const uint64_t reserve = autoprune ? APUS_HDR_BYTES : 0;
-            const uint64_t lim_space = (L - used > 1 + reserve) ? (L - used - 1 - reserve) : 0;
-            // per-lane strip of entries; exclusive scans of log strides and of staged payload bytes
-            const uint32_t per = (nf + 31u) / 32u;
-            const uint32_t k0 = lane * per, k1 = (k0 + per < nf) ? k0 + per : nf;
-            uint32_t sum = 0, xsum = 0;
-            for (uint32_t k = k0; k < k1; k++) {
-                const uint32_t to = sl[k].type_off, ty = (to >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
-                sum += entry_stride(ty, sl[k].len);
-                if (to & APUS_SLOT_EXT) xsum += (data_bytes(ty, sl[k].len) + 15u) & ~15u;
-            }
-            uint32_t incl = sum, xincl = xsum;
-            for (int sft = 1; sft < 32; sft <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, sft);
-                const uint32_t xo = __shfl_up_sync(0xffffffffu, xincl, sft);
-                if (lane >= sft) { incl += o; xincl += xo; }
-            }
-            uint64_t run = hbytes + (incl - sum);   // log bytes before my strip (behind the optional HEAD entry)
-            uint32_t xrun = xincl - xsum;           // staged payload bytes before my strip
-            uint32_t first_bad = nf;
-            for (uint32_t k = k0; k < k1; k++) {
-                const uint32_t to = sl[k].type_off, ty = (to >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
-                const uint32_t es = entry_stride(ty, sl[k].len);
-                const uint32_t xb = (to & APUS_SLOT_EXT) ? ((data_bytes(ty, sl[k].len) + 15u) & ~15u) : 0u;
-                S->rel[k] = (uint32_t)run;
-                S->xoff[k] = xrun;
-                if (first_bad == nf &&
-                    (run + es > lim || run + es > lim_space || xrun + xb > APUS_LEADER_EXT_BYTES ||
-                     (k > 0 && (to & APUS_SLOT_WRAP))))
-                    first_bad = k;
-                run += es; xrun += xb;
-            }
-            for (int sft = 16; sft > 0; sft >>= 1) {
-                const uint32_t o = __shfl_xor_sync(0xffffffffu, first_bad, sft);
-                first_bad = o < first_bad ? o : first_bad;
-            }
-            const uint32_t m = first_bad;
-            __syncwarp();
-            // staged payload range of the tile: images of consecutive tickets are contiguous in the ring
-            uint32_t ext_total = 0;
-            uint64_t ext_base = 0;
-            {
-                uint32_t f = 0xffffffffu, e = 0;
-                for (uint32_t k = k0; k < k1 && k < m; k++) {
-                    const uint32_t to = sl[k].type_off;
-                    if (to & APUS_SLOT_EXT) {
-                        const uint32_t ty = (to >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
-                        if (f == 0xffffffffu) f = k;
-                        e = S->xoff[k] + ((data_bytes(ty, sl[k].len) + 15u) & ~15u);
-                    }
-                }
-                for (int sft = 16; sft > 0; sft >>= 1) {
-                    const uint32_t of = __shfl_xor_sync(0xffffffffu, f, sft);
-                    const uint32_t oe = __shfl_xor_sync(0xffffffffu, e, sft);
-                    f = of < f ? of : f; e = oe > e ? oe : e;
-                }
-                if (f != 0xffffffffu) {
-                    ext_base = (uint64_t)(sl[f].type_off & APUS_SLOT_OFF_MASK) * 16ull;
-                    ext_total = e - S->xoff[f];
-                }
-                // staging offsets are relative to the first staged image
-                if (f != 0xffffffffu && S->xoff[f] != 0) {
-                    const uint32_t base = S->xoff[f];
-                    __syncwarp();
-                    for (uint32_t k = k0; k < k1 && k < m; k++) S->xoff[k] -= base;
-                }
-            }
-            if (lane == 0) {
-                S->gap = 0; S->ghost = 0;
-                if (m == 0 && !autoh) {
-                    // entry 0 does not fit at pos0: wrap (dare_log.h:502-504, 526-538) or no space
-                    const uint32_t ty0 = (sl[0].type_off >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
-                    const uint32_t es0 = entry_stride(ty0, sl[0].len);
-                    const uint64_t left = L - pos0;
-                    if (es0 > left && used + left + es0 + reserve < L) {
-                        S->gap = 1;
-                        S->ghost = (left >= APUS_HDR_BYTES && has_cmd(ty0)) ? 1u : 0u;   // header fits: ghost stays behind
-                        S->a = pos0; S->b = L;
-                    } else {
-                        S->a = S->b = pos0;   // back-pressure: wait for head to advance
-                    }
-                } else {
-                    const uint32_t tyl = m ? (sl[m - 1].type_off >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK : 0;
-                    S->a = pos0;
-                    S->b = pos0 + (m ? S->rel[m - 1] + entry_stride(tyl, sl[m - 1].len) : hbytes);
-                }
-                S->m = m;
-                S->ext_bytes = ext_total; S->ext_base = ext_base;
-                S->auto_head = autoh; S->auto_head_val = new_head;
-                if (autoh) st_relaxed_sys(&hdr->head, new_head);
-                S->idx0 = next_idx;
-                S->fresh = (S->a >= hwm) ? 1u : 0u;
-            }
-        }
-        bar_sync(1, NT);
-        PHASE(2);
-        const uint32_t m = S->m, gap = S->gap;
-        const uint64_t a = S->a, b = S->b;
-        if (a == b) {   // no space before head: poll again
-            if (tid == 0) {
-                if (ld_relaxed_sys_u32(&hw->stop) || S->abort_flag) S->finish = 1;
-                else if (cx->target != ~0ull && globaltimer_ns() - last_progress > WATCHDOG_NS) {
-                    st_relaxed_sys(&hw->error, APUS_KERR_WATCHDOG_LEADER);
-                    S->abort_flag = 1; S->finish = 1;
+        while (S->kbase < nf) {
+            // ---- T2: placement of the next sub-tile (warp 0) ----
+            if (warp == 0) {
+                leader_place(cx, S, sl, lane);
+                if (lane == 0 && S->last) {
+                    // all my slots are placed: hand the placement state to the next claim
+                    seq->p_end = S->st_end; seq->p_tail = S->st_tail; seq->p_next_idx = S->st_next_idx; seq->p_hwm = S->st_hwm;
+                    seq->p_placed = S->st_placed; seq->p_prev_head = S->st_prev_head; seq->p_auto_heads = S->st_auto_heads;
+                    st_release_gpu(&seq->place_seq, S->my_seq + 1);
                 }
             }
             bar_sync(1, NT);
-            if (S->finish) break;
-            continue;
-        }
-        const uint64_t a16 = a & ~15ull;
-        const uint32_t nchunks = (uint32_t)(((b + 15ull) & ~15ull) - a16) >> 4;
-
-        // ---- T3: prefill the image (zeros when the range is fresh, else the bytes the local
-        //      log holds: holes of an entry keep what was there, like the reference) and
-        //      stage the payload-ring range of the tile; all loads in flight together
-        if (S->fresh) {
-            for (uint32_t c = tid; c < nchunks; c += NT) reinterpret_cast<uint4 *>(img)[c] = make_uint4(0, 0, 0, 0);
-        } else {
-            cta_fetch_chunks(img, entries + a16, nchunks, tid);
-        }
-        if (!gap && S->ext_bytes) cta_fetch_chunks(ext, cx->sub_pay + S->ext_base, S->ext_bytes >> 4, tid);
-        bar_sync(1, NT);
-        PHASE(3);
-
-        // ---- T4: compose entries into the image -----------------------------------------
-        if (gap) {
-            if (S->ghost && warp == 0) {
-                // header of entry 0 without payload, sender untouched (dare_log.h:496-503, 521)
-                uint8_t *e = img + (a - a16);
-                const uint32_t ty0 = (sl[0].type_off >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
-                warp_write_header(e, lane, next_idx, cx->term, sl[0].req_id, sl[0].clt_id, ty0, 0, true);
-                if (lane == 8) { e[E_DATA] = (uint8_t)(sl[0].len & 0xff); e[E_DATA + 1] = (uint8_t)(sl[0].len >> 8); }
-            }
-        } else {
-            const uint32_t autoh = S->auto_head;
-            if (autoh && warp == N_PRODUCER_WARPS - 1) {
-                // <HEAD, head_offset> entry (dare_log.h:29-32, dare_server.c:2043-2046)
-                uint8_t *e = img + (a - a16);
-                warp_write_header(e, lane, S->idx0, cx->term, 0, 0, T_HEAD, me, false);
-                if (lane >= 8 && lane < 16) e[E_DATA + lane - 8] = (uint8_t)(S->auto_head_val >> (8 * (lane - 8)));
-            }
-            for (uint32_t k = warp; k < m; k += N_PRODUCER_WARPS) {
-                uint8_t *e = img + (a - a16) + S->rel[k];
-                const uint32_t to = sl[k].type_off, ty = (to >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
-                warp_write_header(e, lane, S->idx0 + autoh + k, cx->term, sl[k].req_id, sl[k].clt_id, ty, me, false);
-                const uint32_t nb = data_bytes(ty, sl[k].len);
-                if (nb) {
-                    const uint8_t *src = (to & APUS_SLOT_EXT) ? ext + S->xoff[k] : sl[k].inl;
-                    warp_copy_smem(e + E_DATA, src, nb, lane);
+            PHASE(2);
+            if (S->blocked) {   // no space before head: poll again
+                if (tid == 0) {
+                    if (ld_relaxed_sys_u32(&hw->stop) || ld_relaxed_sys(&seq->abort_flag)) { st_relaxed_sys(&seq->abort_flag, 1); S->finish = 1; }
+                    else if (cx->target != ~0ull && globaltimer_ns() - last_progress > WATCHDOG_NS) {
+                        st_relaxed_sys(&hw->error, APUS_KERR_WATCHDOG_LEADER);
+                        st_relaxed_sys(&seq->abort_flag, 1); S->finish = 1;
+                    }
                 }
+                bar_sync(1, NT);
+                if (S->finish) { aborted = true; break; }
+                continue;
             }
-        }
-        bar_sync(1, NT);
-        PHASE(4);
+            const uint32_t kbase = S->kbase, m = S->m, gap = S->gap, autoh = S->auto_head;
+            const uint64_t a = S->a, b = S->b;
+            const uint64_t a16 = a & ~15ull;
+            const uint32_t nchunks = (uint32_t)(((b + 15ull) & ~15ull) - a16) >> 4;
 
-        // ---- T5: push the byte range [a,b) to the local log and to every follower ------
-        for (uint32_t c = tid; c < nchunks; c += NT) {
-            const uint64_t lo = a16 + 16ull * c;
-            const uint4 v = reinterpret_cast<const uint4 *>(img)[c];
-            if (lo >= a && lo + 16 <= b) {
-                st_v4(entries + lo, v);
-#pragma unroll 1
-                for (int f = 0; f < N; f++)
-                    if (S->peer_entries[f]) st_v4(S->peer_entries[f] + lo, v);
+            // ---- T3: prefill the image (zeros when the range is fresh, else the bytes the local
+            //      log holds: holes of an entry keep what was there, like the reference) and
+            //      stage the payload-ring range of the sub-tile; all loads in flight together
+            if (S->fresh) {
+                for (uint32_t c = tid; c < nchunks; c += NT) reinterpret_cast<uint4 *>(img)[c] = make_uint4(0, 0, 0, 0);
             } else {
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                for (uint32_t j = 0; j < 16; j++) {
-                    const uint64_t o = lo + j;
-                    if (o < a || o >= b) continue;
-                    const uint32_t byte = (w[j >> 2] >> (8 * (j & 3))) & 0xff;
-                    st_u8(entries + o, byte);
-                    for (int f = 0; f < N; f++)
-                        if (S->peer_entries[f]) st_u8(S->peer_entries[f] + o, byte);
-                }
+                cta_fetch_chunks(img, entries + a16, nchunks, tid);
             }
-        }
-        // entry-offset index: the c-th entry ever appended sits at index[c & idx_mask]
-        if (!gap) {
-            const uint32_t autoh_i = S->auto_head;
-            uint32_t *lindex = reinterpret_cast<uint32_t *>(cx->region + APUS_INDEX_OFF);
-            for (uint32_t j = tid; j < m + autoh_i; j += NT) {
-                uint32_t w;
-                if (autoh_i && j == 0) w = (uint32_t)a | APUS_IDX_HEAD_FLAG;
-                else {
-                    const uint32_t k = j - autoh_i;
-                    const uint32_t ty = (sl[k].type_off >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK;
-                    w = (uint32_t)(a + S->rel[k]) | (ty == T_HEAD ? APUS_IDX_HEAD_FLAG : 0u);
-                }
-                const uint32_t at = (uint32_t)(published + 1 + j) & cx->idx_mask;
-                lindex[at] = w;
-                for (int f = 0; f < N; f++)
-                    if (S->peer_index[f]) S->peer_index[f][at] = w;
-            }
-        }
-        bar_sync(1, NT);
-        PHASE(5);
+            if (!gap && S->ext_bytes) cta_fetch_chunks(ext, cx->sub_pay + S->ext_base, S->ext_bytes >> 4, tid);
+            bar_sync(1, NT);
+            PHASE(3);
 
-        // ---- T6: bookkeeping + publish the tail (data before tail, invariant I1) --------
-        if (gap) {
-            // nothing is published after a gap tile: the next tile (at offset 0) carries it
-            end = 0; hwm = L;
-            bytes_rep += (b - a) * (uint64_t)(N - 1);
-            if (tid == 0) { ctrl->hwm = hwm; ctrl->bytes_replicated = bytes_rep; }
-            // the entry that wrapped stays first in the ring: placement re-runs from offset 0
-            continue;
-        }
-        uint64_t new_end = b;
-        if (new_end == L) new_end = 0;                     // rule E1
-        const uint32_t autoh = S->auto_head;
-        tailpos = m ? a + S->rel[m - 1] : a;
-        end = new_end;
-        next_idx += m + autoh; consumed += m; published += m + autoh;
-        auto_heads += autoh;
-        prev_head = (autoh && m == 0);                     // never two HEAD entries in a row (dare_log.h:477-480)
-        if (b > hwm) hwm = b;
-        bytes_rep += (b - a) * (uint64_t)(N - 1);
-        batches++;
-        if (warp == 0) {
-            if (lane < N && lane != me && cx->peer[lane]) {
-                __threadfence_system();
-                apus_ctrl_t *pc = reinterpret_cast<apus_ctrl_t *>(cx->peer[lane]);
-                st_relaxed_sys_2x64(&pc->pub_end, new_end, published);
+            // ---- T4: compose entries into the image ----
+            if (gap) {
+                if (S->ghost && warp == 0) {
+                    // header of the wrapping entry without payload, sender untouched (dare_log.h:496-503, 521)
+                    uint8_t *e = img + (a - a16);
+                    group_write_header(e, lane, 32, S->idx0, cx->term, sl[kbase].req_id, sl[kbase].clt_id, S->ty[kbase], 0, true);
+                    if (lane == 8) { e[E_DATA] = (uint8_t)(sl[kbase].len & 0xff); e[E_DATA + 1] = (uint8_t)(sl[kbase].len >> 8); }
+                }
+            } else {
+                if (autoh && warp == N_PRODUCER_WARPS - 1) {
+                    // <HEAD, head_offset> entry (dare_log.h:29-32, dare_server.c:2043-2046)
+                    uint8_t *e = img + (a - a16);
+                    group_write_header(e, lane, 32, S->idx0, cx->term, 0, 0, T_HEAD, me, false);
+                    if (lane >= 8 && lane < 16) e[E_DATA + lane - 8] = (uint8_t)(S->auto_head_val >> (8 * (lane - 8)));
+                }
+                // small entries: 8 lanes per entry (4 entries per warp step); large ones: the whole warp
+                const bool small = (b - a) <= (uint64_t)(m + autoh) * 256ull;
+                const int gl = small ? 8 : 32;
+                const int grp = small ? (lane >> 3) : 0, sub = small ? (lane & 7) : lane;
+                const uint32_t per_step = small ? 4u * N_PRODUCER_WARPS : N_PRODUCER_WARPS;
+                for (uint32_t j = (small ? warp * 4u + grp : warp); j < m; j += per_step) {
+                    const uint32_t k = kbase + j;
+                    uint8_t *e = img + (a - a16) + S->rel[k];
+                    const uint32_t ty = S->ty[k];
+                    group_write_header(e, sub, gl, S->idx0 + autoh + j, cx->term, sl[k].req_id, sl[k].clt_id, ty, me, false);
+                    const uint32_t nb = data_bytes(ty, sl[k].len);
+                    if (nb) group_copy_smem(e + E_DATA, (S->flg[k] & 1u) ? ext + S->xoff[k] : sl[k].inl, nb, sub, gl);
+                }
             }
-            if (lane == 0) {
-                hdr->end = new_end; hdr->tail = tailpos; hdr->old_end = new_end;
-                ctrl->next_idx = next_idx; ctrl->consumed = consumed; ctrl->published = published;
-                ctrl->hwm = hwm; ctrl->bytes_replicated = bytes_rep; ctrl->batches = batches;
-                ctrl->auto_heads = auto_heads;
-                const uint64_t h = S->pub_head;
-                S->pub_cum[h & (PUB_RING - 1)] = published;
-                S->pub_end[h & (PUB_RING - 1)] = new_end;
-                S->pub_tickets[h & (PUB_RING - 1)] = consumed;
-                S->pub_t0[h & (PUB_RING - 1)] = S->t_dequeue;
-                __threadfence_block();
-                S->pub_head = h + 1;
-                S->published = published;
-                st_relaxed_sys(&hw->consumed, consumed);
+            bar_sync(1, NT);
+            PHASE(4);
+
+            // ---- T5: push the byte range [a,b) to the local log and to every follower ----
+            for (uint32_t c = tid; c < nchunks; c += NT) {
+                const uint64_t lo = a16 + 16ull * c;
+                const uint4 v = reinterpret_cast<const uint4 *>(img)[c];
+                if (lo >= a && lo + 16 <= b) {
+                    st_v4(entries + lo, v);
+#pragma unroll 1
+                    for (int f = 0; f < N; f++)
+                        if (S->peer_entries[f]) st_v4(S->peer_entries[f] + lo, v);
+                } else {
+#pragma unroll 1
+                    for (uint32_t j = 0; j < 16; j++) {
+                        const uint64_t o = lo + j;
+                        if (o < a || o >= b) continue;
+                        const uint32_t w = (j < 4) ? v.x : (j < 8) ? v.y : (j < 12) ? v.z : v.w;
+                        const uint32_t byte = (w >> (8 * (j & 3))) & 0xff;
+                        st_u8(entries + o, byte);
+#pragma unroll 1
+                        for (int f = 0; f < N; f++)
+                            if (S->peer_entries[f]) st_u8(S->peer_entries[f] + o, byte);
+                    }
+                }
             }
+            // entry-offset index: the c-th entry ever appended sits at index[c & idx_mask]
+            if (!gap) {
+                const uint64_t cum0 = S->cum_after - (m + autoh);
+                for (uint32_t j = tid; j < m + autoh; j += NT) {
+                    uint32_t w;
+                    if (autoh && j == 0) w = (uint32_t)a | APUS_IDX_HEAD_FLAG;
+                    else {
+                        const uint32_t k = kbase + j - autoh;
+                        w = (uint32_t)(a + S->rel[k]) | (S->ty[k] == T_HEAD ? APUS_IDX_HEAD_FLAG : 0u);
+                    }
+                    const uint32_t at = (uint32_t)(cum0 + 1 + j) & cx->idx_mask;
+                    lindex[at] = w;
+#pragma unroll 1
+                    for (int f = 0; f < N; f++)
+                        if (S->peer_index[f]) S->peer_index[f][at] = w;
+                }
+            }
+            bar_sync(1, NT);
+            PHASE(5);
+
+            // ---- T6: publish the tail in claim order (data before tail, invariant I1) ----
+            if (gap) {
+                // nothing is published after a gap: the next sub-tile (at offset 0) carries it
+                gap_bytes += b - a;
+                bar_sync(1, NT);
+                continue;
+            }
+            if (warp == 0) {
+                const bool pubs = lane < N && lane != me && cx->peer[lane];
+                if (pubs || lane == 0) __threadfence_system();          // my CTA's data stores, system wide
+                if (lane == 0 && !have_pub_turn) {
+                    uint32_t spins = 0;
+                    while (ld_acquire_gpu(&seq->pub_seq) != S->my_seq) {
+                        if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
+                    }
+                }
+                __syncwarp();
+                if (pubs) {
+                    apus_ctrl_t *pc = reinterpret_cast<apus_ctrl_t *>(cx->peer[lane]);
+                    st_relaxed_sys_2x64(&pc->pub_end, S->new_end, S->cum_after);
+                }
+                if (lane == 0) {
+                    const uint64_t consumed = S->slot0 + kbase + m;
+                    hdr->end = S->new_end; hdr->tail = S->tail_after; hdr->old_end = S->new_end;
+                    ctrl->next_idx = S->idx0 + m + autoh; ctrl->consumed = consumed;
+                    ctrl->hwm = S->hwm_after; ctrl->auto_heads = S->auto_heads_after;
+                    ctrl->bytes_replicated += (b - a + gap_bytes) * (uint64_t)(N - 1);   // a gap skipped before it counts too
+                    ctrl->batches += 1;
+                    const uint64_t h = ld_relaxed_sys(&seq->pub_head);
+                    uint32_t spins = 0;
+                    while (h - ld_acquire_gpu(&seq->pub_tail) >= APUS_PUBRING_RECORDS - 2) {   // commit warp drains
+                        if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
+                    }
+                    apus_pubrec_t *r = &pubring[h & PUBMASK];
+                    r->cum = S->cum_after; r->end = S->new_end; r->tickets = consumed; r->t0 = S->t_dequeue;
+                    st_relaxed_sys(&ctrl->published, S->cum_after);
+                    st_release_gpu(&seq->pub_head, h + 1);
+                    st_relaxed_sys(&hw->consumed, consumed);
+                    if (S->last) st_release_gpu(&seq->pub_seq, S->my_seq + 1);
+                    S->kbase = kbase + m;
+                }
+            }
+            have_pub_turn = true;
+            gap_bytes = 0;
+            last_progress = globaltimer_ns();
+            bar_sync(1, NT);
+            if (prof) { PHASE(6); ph[7]++; }
         }
-        last_progress = globaltimer_ns();
-        if (prof) { PHASE(6); ph[7]++; }
+        if (aborted) break;
     }
     if (prof) for (int i = 0; i < 8; i++) ctrl->phase_ns[i] = ph[i];
-    if (tid == 0) { __threadfence_block(); S->producers_done = 1; }
+    if (tid == 0) { __threadfence(); atomicAdd(reinterpret_cast<unsigned long long *>(&seq->workers_done), 1ull); }
 }
 
 // ---------------------------------------------------------------------------------
@@ -776,7 +862,7 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int me = cx->idx, ldr = cx->leader_idx;
     apus_ctrl_t *ctrl = reinterpret_cast<apus_ctrl_t *>(cx->region);
-    apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_CTRL_BYTES);
+    apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_HDR_OFF);
     uint8_t *entries = cx->region + cx->entries_off;
     apus_hostwords_t *hw = cx->hw;
     uint8_t *lregion = cx->peer[ldr];
@@ -995,7 +1081,7 @@ extern "C" __global__ void __launch_bounds__(APUS_KERNEL_THREADS, 1)
 apus_replica_kernel(const apus_role_t *__restrict__ roles)
 {
     const apus_role_t r = roles[blockIdx.x];
-    if (r.kind == APUS_ROLE_LEADER) leader_main(r.ctx);
+    if (r.kind == APUS_ROLE_LEADER) leader_main(r.ctx, r.worker);
     else if (r.kind == APUS_ROLE_FOLLOWER) follower_main(r.ctx);
 }
 

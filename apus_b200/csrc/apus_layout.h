@@ -5,7 +5,10 @@
  * One cudaMalloc'd REGION per replica (one IPC handle maps all of it in a peer):
  *
  *   +0        apus_ctrl_t   4 KiB   words written by REMOTE peers and kernel state
- *   +4096     apus_loghdr_t         mirror of dare_log_t up to entries[]
+ *   +4096     apus_seq_t + publish ring   leader only: the sequencer words its worker CTAs
+ *                                   share (claim / place / publish turns) and the ring of
+ *                                   publishes awaiting a majority (60 KiB)
+ *   +65536    apus_loghdr_t         mirror of dare_log_t up to entries[]
  *                                   (dare_log.h:77-103: head 0, apply 8, commit 16,
  *                                   end 24, tail 32, old_end 40, old_commit 48, len 56,
  *                                   nc_buf 64 .. 319656), padded to 320 KiB
@@ -40,7 +43,11 @@
 #define APUS_CTRL_BYTES       4096u
 #define APUS_LOGHDR_REF_BYTES 319656u                 /* offsetof(dare_log_t, entries) */
 #define APUS_LOGHDR_BYTES     (320u * 1024u)
-#define APUS_INDEX_OFF        (APUS_CTRL_BYTES + APUS_LOGHDR_BYTES)
+#define APUS_SEQ_OFF          4096u
+#define APUS_PUBRING_OFF      8192u
+#define APUS_PUBRING_RECORDS  1024u                   /* 32 B each; power of two */
+#define APUS_HDR_OFF          65536u
+#define APUS_INDEX_OFF        (APUS_HDR_OFF + APUS_LOGHDR_BYTES)
 #define APUS_IDX_HEAD_FLAG    0x80000000u             /* index word: the entry is a HEAD entry */
 
 /* entry field offsets (dare_log.h:33-48) */
@@ -98,6 +105,37 @@ typedef struct apus_ctrl {
     uint64_t pad3[8];
 } apus_ctrl_t;
 
+/* Sequencer shared by the leader's worker CTAs (device memory, gpu-scope atomics).
+ * A worker CLAIMS the next slots of the submission ring (ticket lock: one poller at a
+ * time), builds its tile in parallel with the others, but PLACES it in the log and
+ * PUBLISHES its tail strictly in claim order -- log order == submission order. */
+typedef struct apus_seq {
+    uint64_t claim_ticket;   uint64_t pad_a[15];
+    uint64_t claim_serving;  uint64_t pad_b[15];
+    uint64_t claimed_slots;      /* slots handed to workers so far (>= ctrl.consumed) */
+    uint64_t tile_seq;           /* claims with work handed out */
+    uint64_t claims_closed;      /* target reached or stop requested: no more claims */
+    uint64_t pad_c[13];
+    uint64_t place_seq;      uint64_t pad_d[15];   /* next claim allowed to place */
+    uint64_t pub_seq;        uint64_t pad_e[15];   /* next claim allowed to publish */
+    uint64_t pub_head;       uint64_t pad_f[15];   /* publish ring: next record written */
+    uint64_t pub_tail;       uint64_t pad_g[15];   /* ... next record the commit warp reads */
+    uint64_t workers_done;
+    uint64_t abort_flag;
+    uint64_t ready_epoch;        /* == devctx.epoch once worker 0 has reset the block */
+    uint64_t pad_h[13];
+    /* placement state, owned by the worker holding the place turn */
+    uint64_t p_end, p_tail, p_next_idx, p_hwm, p_placed, p_prev_head, p_auto_heads;
+    uint64_t pad_i[9];
+} apus_seq_t;
+
+typedef struct apus_pubrec {
+    uint64_t cum;                /* entries published up to and including this tile */
+    uint64_t end;                /* `end` after this tile */
+    uint64_t tickets;            /* tickets consumed up to and including this tile */
+    uint64_t t0;                 /* dequeue timestamp (ns) */
+} apus_pubrec_t;
+
 /* submission slot, 128 B: the fields of tailq_entry_t (message.h:11-17).  Requests
  * whose data image (sm_cmd_t {u16 len; cmd[]}, dare_cid_t or head offset) is at most
  * 112 B travel inline, so that one coalesced read brings descriptor and payload;
@@ -151,6 +189,8 @@ typedef struct apus_devctx {
     uint32_t idx_mask;                    /* index ring capacity - 1 */
     uint32_t pad_i;
     uint64_t target;                      /* cumulative ticket / entry target of this launch */
+    uint32_t n_workers;                   /* leader CTAs of this launch */
+    uint32_t epoch;                       /* launch counter (sequencer reset handshake) */
     uint8_t *region;                      /* own region */
     uint8_t *peer[APUS_MAX_SERVERS];      /* peers' regions as mapped here (NULL = absent) */
     /* leader submission ring */
@@ -165,7 +205,7 @@ typedef struct apus_devctx {
 
 typedef struct apus_role {
     uint32_t       kind;
-    uint32_t       pad;
+    uint32_t       worker;                /* leader: worker CTA index */
     apus_devctx_t *ctx;
 } apus_role_t;
 

@@ -29,7 +29,7 @@ class ApusError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [("struct_size", u32), ("device", i32), ("server_idx", u8), ("group_size", u8),
                 ("leader_idx", u8), ("ring_mode", u8), ("flags", u32), ("term", u64),
-                ("log_size", u64), ("ring_slots", u32), ("ring_bytes", u32)]
+                ("log_size", u64), ("ring_slots", u32), ("ring_bytes", u32), ("leader_ctas", u32), ("reserved", u32)]
 
 
 class PeerHandle(C.Structure):
@@ -113,8 +113,9 @@ def _ck(rc, what):
 
 class Replica:
     def __init__(self, device, server_idx, group_size, leader_idx=0, term=1, log_size=0,
-                 ring_mode=RING_HOST_MAPPED, ring_slots=0, ring_bytes=0, flags=None):
+                 ring_mode=RING_HOST_MAPPED, ring_slots=0, ring_bytes=0, flags=None, leader_ctas=0):
         cfg = Config()
+        cfg.leader_ctas = leader_ctas
         cfg.struct_size = C.sizeof(Config)
         cfg.device, cfg.server_idx, cfg.group_size, cfg.leader_idx = device, server_idx, group_size, leader_idx
         cfg.ring_mode, cfg.term, cfg.log_size = ring_mode, term, log_size
@@ -237,15 +238,15 @@ class Group:
     """All replicas of one Paxos group inside this process (tests, 1..8 GPUs)."""
 
     def __init__(self, n, devices=None, leader=0, term=1, log_size=0, ring_mode=RING_HOST_MAPPED,
-                 ring_slots=0, ring_bytes=0, flags=None):
+                 ring_slots=0, ring_bytes=0, flags=None, leader_ctas=0):
         ndev = lib().apus_device_count()
         if ndev <= 0:
             raise ApusError("no CUDA device visible: the engine has no CPU fallback")
         if devices is None:
             devices = [i % ndev for i in range(n)]
         self.n, self.leader_idx, self.devices = n, leader, list(devices)
-        self.replicas = [Replica(devices[i], i, n, leader, term, log_size, ring_mode, ring_slots, ring_bytes, flags)
-                         for i in range(n)]
+        self.replicas = [Replica(devices[i], i, n, leader, term, log_size, ring_mode, ring_slots, ring_bytes, flags,
+                                 leader_ctas) for i in range(n)]
         blobs = [r.export() for r in self.replicas]
         for r in self.replicas:
             for j, b in enumerate(blobs):

@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--e2e-ring", default="mapped", choices=["mapped", "device"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--leader-ctas", type=int, default=0, help="leader worker CTAs (0 = engine default)")
     ap.add_argument("--spread", action="store_true",
                     help="single process: place replica r on GPU r %% visible GPUs (NVLink path)")
     return ap.parse_args()
@@ -209,7 +210,7 @@ class Cell:
             nd = A.lib().apus_device_count()
             devs = [r % nd for r in range(n)] if args.spread else [0] * n
             self.group = A.Group(n, devices=devs, log_size=L, ring_mode=ring_mode, ring_slots=slots,
-                                 ring_bytes=ring_bytes, flags=flags)
+                                 ring_bytes=ring_bytes, flags=flags, leader_ctas=args.leader_ctas)
             self.leader = self.group.leader
             self.local = list(self.group.replicas)
             self.devices = sorted(set(devs))
@@ -221,7 +222,7 @@ class Cell:
                 for r in range(n):
                     if (g + r) % world == rank:
                         mine[(g, r)] = E.Replica(local, r, n, 0, 1, L, ring_mode, slots if r == 0 else 0,
-                                                 ring_bytes if r == 0 else 0, flags)
+                                                 ring_bytes if r == 0 else 0, flags, args.leader_ctas)
             blobs = {k: v.export() for k, v in mine.items()}
             allb = [None] * world
             dist.all_gather_object(allb, blobs)

@@ -89,6 +89,8 @@ typedef struct apus_config {
     uint64_t log_size;         /* bytes of entries[]; 0 -> APUS_LOG_SIZE (reference) */
     uint32_t ring_slots;       /* submission descriptors, power of two; 0 -> default */
     uint32_t ring_bytes;       /* payload ring bytes, multiple of 4096; 0 -> default */
+    uint32_t leader_ctas;      /* leader: worker CTAs (SMs) building tiles in parallel; 0 -> default */
+    uint32_t reserved;
 } apus_config_t;
 
 /* Opaque blob a replica publishes so that peers can map its HBM region.

@@ -57,7 +57,7 @@ def test_no_cpu_fallback(built):
 
 def test_config_struct_matches_header(built):
     # struct_size is checked by the library itself; this pins the Python mirror
-    assert C.sizeof(built.Config) == 40
+    assert C.sizeof(built.Config) == 48
     assert C.sizeof(built.PeerHandle) == 128
     assert C.sizeof(built.LogOffsets) == 64
     assert C.sizeof(built.Stats) == 144
