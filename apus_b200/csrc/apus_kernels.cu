@@ -56,9 +56,10 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys_u32(const volatile void *p)
     asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void ld_relaxed_sys_2x64(const volatile void *p, uint64_t &a, uint64_t &b)
+__device__ __forceinline__ void ld_acquire_sys_2x64(const volatile void *p, uint64_t &a, uint64_t &b)
 {
-    asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    // an acquire LOAD costs ~0.26 us here, a system fence ~1.5 us (profiles/r1_ubench_2gpu.txt)
+    asm volatile("ld.acquire.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void st_relaxed_sys(volatile void *p, uint64_t v)
 {
@@ -621,7 +622,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             uint64_t claimed = ld_relaxed_sys(&seq->claimed_slots);
             while (!fin) {
                 if (claimed >= cx->target) { fin = 1; break; }
-                const uint64_t t = ld_relaxed_sys(cx->sub_tail);
+                const uint64_t t = ld_acquire_sys(cx->sub_tail);   // slots + payload were written before it
                 uint64_t avail = t - claimed;
                 if (avail) {
                     const uint64_t room = cx->target - claimed;
@@ -647,8 +648,6 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                 st_relaxed_sys(&seq->tile_seq, S->my_seq + 1);
             }
             st_release_gpu(&seq->claim_serving, ticket + 1);
-            // (slots are read with ld.relaxed.sys AFTER the doorbell value arrived; the host wrote
-            //  them before ringing it -- message passing without a 1.5 us system fence)
             S->n_fetch = n; S->finish = fin;
             S->t_dequeue = globaltimer_ns();
         }
@@ -885,12 +884,12 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
             uint64_t e, cum, c;
             uint32_t done = 0;
             for (;;) {
-                ld_relaxed_sys_2x64(&ctrl->pub_end, e, cum);        // {end, entries} written as one 16 B store
+                ld_acquire_sys_2x64(&ctrl->pub_end, e, cum);        // {end, entries} written as one 16 B store
                 c = ld_relaxed_sys(&hdr->commit);
                 const bool new_entries = cum > acked;
                 // commit moved, and I hold entries beyond what I applied
                 const bool new_commit = (c != applied) && (old_end != L) && (applied != old_end);
-                if (new_entries || new_commit) { __threadfence_system(); break; }   // acquire
+                if (new_entries || new_commit) break;
                 // bounded launch: the leader says how many entries exist in total
                 if (cx->target != ~0ull && ld_acquire_sys(&ctrl->fin_target) == cx->target) {
                     const uint64_t fe = ld_relaxed_sys(&ctrl->fin_entries);
@@ -904,9 +903,9 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
                     }
                 }
             }
-            // early ack: the tail publish was observed and fenced, so every entry up to it is
-            // resident and visible here (invariant I2); the reply bytes follow behind the
-            // ack word unless APUS_F_FENCED_ACK asks for them first
+            // early ack: the tail publish was observed with acquire semantics, so every entry up
+            // to it is resident and visible here (invariant I2); the reply bytes follow behind
+            // the ack word unless APUS_F_FENCED_ACK asks for them first
             if (!done && !fenced && cum > acked) st_relaxed_sys(&lctrl->ack[me], cum);
             S->end_seen = e; S->cum_seen = cum; S->commit_seen = c; S->done = done;
         }
