@@ -152,7 +152,7 @@ struct LeaderShared {
     uint8_t  flg[MAXB];        // bit0 EXT, bit1 WRAP
     // claim
     uint32_t n_fetch, finish;
-    uint64_t slot0, my_seq, t_dequeue;
+    uint64_t slot0, my_seq, t_dequeue, claim_next, st_head;
     // placement state while this CTA holds the place turn (mirrors apus_seq_t.p_*)
     uint64_t st_end, st_tail, st_next_idx, st_hwm, st_placed, st_auto_heads;
     uint32_t st_prev_head, pad0;
@@ -300,7 +300,7 @@ __device__ __forceinline__ void cta_fetch_slots(LeaderShared *S, uint8_t *slots,
     const uint8_t *src = reinterpret_cast<const uint8_t *>(ring + s);
     uint8_t *dst = slots + (size_t)k0 * APUS_SLOT_BYTES;
     const uint32_t nchunks = cnt * 8u;
-    uint32_t c = tid;
+    uint32_t c = (tid >= 32) ? tid - 32 : tid + NT - 32;      // warp 1 takes the first chunks (warp 0 is busy with the locks)
     for (; c + 3u * NT < nchunks; c += 4u * NT) {
         const uint4 v0 = ld_relaxed_sys_v4(src + 16ull * c);
         const uint4 v1 = ld_relaxed_sys_v4(src + 16ull * (c + NT));
@@ -346,7 +346,10 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
         // vote is everything it has published (dare_ibv_rc.c:1736 "i == idx")
         uint64_t v = 0;
         if (lane < N) v = (lane == me) ? ld_relaxed_sys(&ctrl->published) : ld_relaxed_sys(&ctrl->ack[lane]);
+        else if (lane == 31) v = ld_acquire_gpu(&seq->pub_head);   // polled alongside the acks: off the critical path
         const uint64_t published_now = __shfl_sync(0xffffffffu, v, me);
+        const uint64_t head = __shfl_sync(0xffffffffu, v, 31);
+        if (lane == 31) v = 0;
         // rank: how many replicas hold at least what I hold
         int cnt = 0;
         for (int j = 0; j < N; j++) {
@@ -364,7 +367,6 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
             // (no acquire fence on the followers' side of things: the commit rule consumes
             //  nothing but the ack words themselves)
             // map the entry count to the log offset recorded at publish time
-            const uint64_t head = ld_acquire_gpu(&seq->pub_head);
             uint64_t off = 0, tickets = committed_tickets;
             bool any = false;
             while (tail != head) {
@@ -443,7 +445,7 @@ __device__ void leader_place(const apus_devctx_t *__restrict__ cx, LeaderShared 
     const uint32_t kbase = S->kbase, nf = S->n_fetch;
     const uint64_t end = S->st_end;
 
-    uint64_t head = ld_relaxed_sys(&hdr->head);
+    uint64_t head = S->st_head;                                // refreshed by the caller while blocked
     const uint64_t pos0 = (end == L) ? 0 : end;               // empty log starts at 0 (dare_log.h:216-219)
     uint64_t used = (end == L) ? 0 : ring_dist(head, end, L);
     // ---- device-side log pruning (log_pruning / force_log_pruning, dare_server.c:1996-2122):
@@ -531,7 +533,7 @@ __device__ void leader_place(const apus_devctx_t *__restrict__ cx, LeaderShared 
         S->fresh = (a >= S->st_hwm) ? 1u : 0u;
         if (!S->blocked) {
             // commit the placement to the state this CTA carries
-            if (autoh) st_relaxed_sys(&hdr->head, new_head);
+            if (autoh) { st_relaxed_sys(&hdr->head, new_head); S->st_head = new_head; }
             if (S->gap) {
                 S->st_end = 0; S->st_hwm = L;
             } else {
@@ -647,13 +649,16 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                 st_relaxed_sys(&seq->claimed_slots, claimed + n);
                 st_relaxed_sys(&seq->tile_seq, S->my_seq + 1);
             }
-            st_release_gpu(&seq->claim_serving, ticket + 1);
             S->n_fetch = n; S->finish = fin;
             S->t_dequeue = globaltimer_ns();
+            S->claim_next = ticket + 1;
         }
         bar_sync(1, NT);
+        // the other warps start fetching while thread 0 hands the claim lock on
+        if (tid == 0) st_release_gpu(&seq->claim_serving, S->claim_next);
         if (S->finish) break;
         const uint32_t nf = S->n_fetch;
+        const bool lowlat = nf <= 8;          // few requests in flight: favour latency over overlap
         PHASE(0);
 
         // ---- T1: fetch the slots (descriptor + inline payload), coalesced 16 B loads --------
@@ -672,6 +677,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             }
             S->st_end = seq->p_end; S->st_tail = seq->p_tail; S->st_next_idx = seq->p_next_idx; S->st_hwm = seq->p_hwm;
             S->st_placed = seq->p_placed; S->st_prev_head = (uint32_t)seq->p_prev_head; S->st_auto_heads = seq->p_auto_heads;
+            S->st_head = ld_relaxed_sys(&hdr->head);
             S->kbase = 0;
         }
         bar_sync(1, NT);
@@ -684,7 +690,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             // ---- T2: placement of the next sub-tile (warp 0) ----
             if (warp == 0) {
                 leader_place(cx, S, sl, lane);
-                if (lane == 0 && S->last) {
+                if (lane == 0 && S->last && !lowlat) {
                     // all my slots are placed: hand the placement state to the next claim
                     seq->p_end = S->st_end; seq->p_tail = S->st_tail; seq->p_next_idx = S->st_next_idx; seq->p_hwm = S->st_hwm;
                     seq->p_placed = S->st_placed; seq->p_prev_head = S->st_prev_head; seq->p_auto_heads = S->st_auto_heads;
@@ -701,6 +707,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         st_relaxed_sys(&seq->abort_flag, 1); S->finish = 1;
                     }
                 }
+                if (tid == 0) S->st_head = ld_relaxed_sys(&hdr->head);
                 bar_sync(1, NT);
                 if (S->finish) { aborted = true; break; }
                 continue;
@@ -835,6 +842,12 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     st_relaxed_sys(&ctrl->published, S->cum_after);
                     st_release_gpu(&seq->pub_head, h + 1);
                     st_relaxed_sys(&hw->consumed, consumed);
+                    if (S->last && lowlat) {
+                        // deferred hand-over of the placement state (kept off the latency path)
+                        seq->p_end = S->st_end; seq->p_tail = S->st_tail; seq->p_next_idx = S->st_next_idx; seq->p_hwm = S->st_hwm;
+                        seq->p_placed = S->st_placed; seq->p_prev_head = S->st_prev_head; seq->p_auto_heads = S->st_auto_heads;
+                        st_release_gpu(&seq->place_seq, S->my_seq + 1);
+                    }
                     if (S->last) st_release_gpu(&seq->pub_seq, S->my_seq + 1);
                     S->kbase = kbase + m;
                 }
@@ -843,7 +856,10 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             gap_bytes = 0;
             last_progress = globaltimer_ns();
             bar_sync(1, NT);
-            if (prof) { PHASE(6); ph[7]++; }
+            if (prof) {
+                PHASE(6); ph[7]++;
+                for (int i = 0; i < 8; i++) ctrl->phase_ns[i] = ph[i];
+            }
         }
         if (aborted) break;
     }

@@ -118,6 +118,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(n, payload, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the replica kernel per launch, from the committed
+    `ncu --set full` capture (profiles/r1_ncu_v3.json); only valid for the configuration it was taken on."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_v3.json")
+    try:
+        d = json.load(open(p))
+        if n == 5 and payload == 64 and batch == 65536:
+            return float(d["traffic_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -423,7 +436,12 @@ def run_ours(args):
                        f"-> apus_wait_committed (pinned commit word)"}
         # closed loop, one request in flight: host-view commit latency (proxy.c:160 spin)
         if rank == 0 and args.lat_requests > 0:
+            ph0 = cell.leader.stats()["phase_ns"]
             lats = cell.leader.closed_loop(args.lat_requests, payload, conn, req)
+            ph1 = cell.leader.stats()["phase_ns"]
+            tiles = max(1, ph1[7] - ph0[7])
+            log("closed loop, worker 0 ns per tile [wait,T1,T2,T3,T4,T5,T6]: "
+                f"{[round((b - a) / tiles) for a, b in zip(ph0[:7], ph1[:7])]} over {tiles} tiles")
             req += args.lat_requests
             lats = np.sort(lats[args.lat_requests // 10:].astype(np.float64)) / 1e3
             lat_host = {"p50_us": round(float(lats[len(lats) // 2]), 2), "p99_us": round(float(lats[int(len(lats) * 0.99)]), 2),
@@ -471,7 +489,11 @@ def run_ours(args):
         "e2e": e2e,
         "gpu_launches": launches,
         "roofline": {"bound": bound, "achieved": round(ach, 3), "peak": peak, "unit": "GB/s",
-                     "frac": round(ach / peak, 6), "traffic": None, "peak_source": peak_src,
+                     "frac": round(ach / peak, 6),
+                     "traffic": (ncu_traffic(n, payload, batch) if world == 1 and not args.spread else None),
+                     "traffic_note": "bytes per launch (dram read+write), profiles/r1_ncu_v3.json; algorithmic bytes per launch = "
+                                     f"{alg_bytes_per_op * batch}",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_op": alg_bytes_per_op,
                      "kernel": "apus_replica_kernel (one fused launch per step: leader CTA + follower CTAs)",
                      "kernel_ms_per_launch": round(kernel_ms / K, 4)},
