@@ -520,6 +520,17 @@ extern "C" int apus_submit_flush(apus_replica_t *r)
 
 extern "C" uint64_t apus_committed_tickets(apus_replica_t *r) { return r ? r->hw->committed_tickets : 0; }
 
+extern "C" int apus_progress(apus_replica_t *r, uint64_t *offset, uint64_t *count)
+{
+    if (!r) return fail("null argument");
+    /* count first: the kernel writes the offset before the count */
+    const uint64_t c = r->hw->committed_tickets;
+    __sync_synchronize();
+    if (count) *count = c;
+    if (offset) *offset = r->hw->commit_off;
+    return r->hw->error ? fail("kernel reported protocol error %llu", (unsigned long long)r->hw->error) : APUS_OK;
+}
+
 extern "C" int apus_wait_committed(apus_replica_t *r, uint64_t ticket, int64_t timeout_us)
 {
     if (!r) return fail("null argument");

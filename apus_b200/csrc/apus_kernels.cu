@@ -1083,6 +1083,8 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
                 if (tid == 0) {
                     hdr->apply = applied;               // host-side apply (do_action) drains behind this
                     st_relaxed_sys(&lctrl->apply_off[me], applied);
+                    st_relaxed_sys(&hw->commit_off, applied);
+                    st_relaxed_sys(&hw->committed_tickets, acked);
                 }
                 last_progress = globaltimer_ns();
             }

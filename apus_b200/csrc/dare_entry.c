@@ -1,0 +1,230 @@
+/*
+ * dare_entry.c -- libapus_dare.so: the engine-entry symbols APUS's proxy.c links against
+ * (include/apus_dare_entry.h), implemented on the C ABI of include/apus_gpu.h.
+ *
+ * Replaces, from the caller's point of view, the reference's libdare.a entry points
+ * (src/dare/dare_server.c:173-241 dare_server_init, :243-255 dare_server_shutdown,
+ * :2299-2307 is_leader/get_node_id) and the TAILQ globals of message.h:20-22.  The thread
+ * that runs dare_server_init is "the DARE thread": it is the only one that touches the
+ * engine and the only one that invokes proxy callbacks, as in the reference.
+ */
+#define _GNU_SOURCE
+#include <errno.h>
+#include <signal.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "apus_dare_entry.h"
+#include "apus_gpu.h"
+
+/* the one real definition of the reference's header-defined globals (message.h:20-22) */
+struct apus_tailhead_t tailhead;
+pthread_spinlock_t tailq_lock;
+
+static FILE *g_log;
+static apus_replica_t *g_rep;
+static volatile int g_leader, g_started, g_terminate;
+static uint8_t g_idx, g_n, g_leader_idx;
+static dare_server_input_t g_in;
+
+#define LOGT(fmt, ...) do { struct timeval _tv; gettimeofday(&_tv, NULL); \
+    fprintf(g_log, "[%lu:%06lu] " fmt, (unsigned long)_tv.tv_sec, (unsigned long)_tv.tv_usec, ##__VA_ARGS__); fflush(g_log); } while (0)
+
+int is_leader(void) { return g_started && g_leader; }          /* dare_server.c:2299-2302 */
+uint8_t get_node_id(void) { return g_idx; }                    /* dare_server.c:2304-2307 */
+
+static void int_handler(int sig) { (void)sig; g_terminate = 1; }   /* dare_server.c:2309-2315 */
+
+void dare_server_shutdown(void)
+{
+    if (g_rep) {
+        apus_replica_t *rs[1] = { g_rep };
+        apus_replicas_stop(rs, 1);
+        apus_replica_destroy(g_rep);
+        g_rep = NULL;
+    }
+    g_started = 0;
+    if (g_log && g_log != stdout) fclose(g_log);
+    pthread_exit(NULL);
+}
+
+/* ---- peer handle rendezvous: the stand-in for RC_SYN/SYNACK/ACK (dare_ibv_ud.c:1168-1416) ---- */
+static int rendezvous(const char *dir, const apus_peer_handle_t *mine, apus_peer_handle_t *all)
+{
+    char path[512], tmp[560];
+    mkdir(dir, 0777);
+    snprintf(path, sizeof path, "%s/r%u.handle", dir, (unsigned)g_idx);
+    snprintf(tmp, sizeof tmp, "%s.tmp.%d", path, (int)getpid());
+    FILE *f = fopen(tmp, "wb");
+    if (!f) return 1;
+    fwrite(mine, sizeof *mine, 1, f);
+    fclose(f);
+    if (rename(tmp, path)) return 1;
+    all[g_idx] = *mine;
+    for (unsigned i = 0; i < g_n; i++) {
+        if (i == g_idx) continue;
+        snprintf(path, sizeof path, "%s/r%u.handle", dir, i);
+        for (int tries = 0;; tries++) {
+            f = fopen(path, "rb");
+            if (f) {
+                size_t got = fread(&all[i], sizeof all[i], 1, f);
+                fclose(f);
+                if (got == 1) break;
+            }
+            if (g_terminate || tries > 60000) return 1;      /* 60 s */
+            usleep(1000);
+        }
+    }
+    return 0;
+}
+
+static int csm_like(uint8_t type) { return !(type == APUS_NOOP || type == APUS_CONFIG || type == APUS_HEAD); }
+
+/* ---- leader pump ---------------------------------------------------------------------------- */
+#define TK_RING (1u << 20)
+static uint8_t *g_tk_type;        /* type of every ticket in flight, indexed by ticket & (TK_RING-1) */
+
+static void leader_pump(void)
+{
+    uint64_t submitted = 0, applied = 0;
+    uint8_t image[64];
+    if (g_n > 1) {
+        /* the election winner's blank CONFIG entry (dare_server.c:1412-1421) */
+        uint8_t cid[16];
+        memset(cid, 0, sizeof cid);
+        cid[8] = g_n;
+        uint32_t bm = (1u << g_n) - 1u;
+        memcpy(cid + 12, &bm, 4);
+        uint64_t t = 0;
+        if (apus_submit(g_rep, APUS_CONFIG, 0, 0, cid, 0, &t) != APUS_OK) { LOGT("cannot append CONFIG: %s\n", apus_last_error()); return; }
+        g_tk_type[t & (TK_RING - 1)] = APUS_CONFIG;
+        submitted = t;
+    }
+    LOGT("[T%llu] LEADER\n", 1ull);              /* benchmarks/run.sh:52 greps for "] LEADER" */
+    g_leader = 1;
+    apus_submit_defer(g_rep, 1);
+    while (!g_terminate) {
+        /* get_tailq_message (dare_ibv_ud.c:780-790): lock, pop FIFO, append, free */
+        int any = 0;
+        pthread_spin_lock(&tailq_lock);
+        while (!TAILQ_EMPTY(&tailhead) && submitted - applied < TK_RING - 2) {
+            tailq_entry_t *n3 = TAILQ_FIRST(&tailhead);
+            uint64_t t = 0;
+            int rc = apus_submit(g_rep, n3->type, n3->connection_id, n3->req_id, n3->cmd.cmd, n3->cmd.len, &t);
+            if (rc == APUS_RETRY) break;                       /* ring full: flush, drain commits, retry */
+            if (rc != APUS_OK) { LOGT("apus_submit: %s\n", apus_last_error()); g_terminate = 1; break; }
+            g_tk_type[t & (TK_RING - 1)] = n3->type;
+            submitted = t;
+            any = 1;
+            /* persist_new_entries (dare_server.c:1802): store_cmd(&entry->clt_id): the bytes of
+             * the entry from clt_id on, as they are when the leader persists (sender/reply unset) */
+            memset(image, 0, sizeof image);
+            memcpy(image, &n3->connection_id, 2);
+            image[2] = n3->type;
+            memcpy(image + 24, &n3->cmd.len, 2);
+            if (g_in.store_cmd) g_in.store_cmd(image, g_in.up_para);
+            TAILQ_REMOVE(&tailhead, n3, entries);
+            free(n3);
+        }
+        pthread_spin_unlock(&tailq_lock);
+        if (any) apus_submit_flush(g_rep);
+        /* apply_committed_entries, leader branch (dare_server.c:1851-1861, 1951-1952) */
+        uint64_t c = apus_committed_tickets(g_rep);
+        while (applied < c) {
+            applied++;
+            if (csm_like(g_tk_type[applied & (TK_RING - 1)]) && g_in.update_state) g_in.update_state(g_in.up_para);
+        }
+    }
+}
+
+/* ---- follower pump: apply_committed_entries, follower branch (dare_server.c:1815-1967) -------- */
+static void follower_pump(uint64_t L)
+{
+    uint64_t apply = 0;
+    uint8_t *buf = (uint8_t *)malloc(1u << 20);
+    size_t cap = 1u << 20;
+    while (!g_terminate) {
+        uint64_t off = 0, cnt = 0;
+        if (apus_progress(g_rep, &off, &cnt) != APUS_OK) { LOGT("%s\n", apus_last_error()); break; }
+        if (off == apply) { usleep(20); continue; }
+        /* entries [apply, off), possibly wrapped; walk with the reference's rules */
+        while (apply != off && !g_terminate) {
+            if (L - apply < APUS_ENTRY_HDR) { apply = 0; if (apply == off) break; }      /* log_get_entry */
+            uint8_t hdr[64];
+            if (apus_log_read(g_rep, apply, 64, hdr) != APUS_OK) { g_terminate = 1; break; }
+            uint8_t type = hdr[26];
+            uint16_t len; memcpy(&len, hdr + 48, 2);
+            uint32_t stride = csm_like(type) ? 64u + len : 64u;                        /* log_entry_len */
+            if (L - apply < stride) { apply = 0; continue; }                             /* ghost header */
+            if (csm_like(type)) {
+                if (stride > cap) { cap = stride; buf = (uint8_t *)realloc(buf, cap); }
+                if (apus_log_read(g_rep, apply, stride, buf) != APUS_OK) { g_terminate = 1; break; }
+                uint16_t clt; memcpy(&clt, buf + 24, 2);
+                if (g_in.store_cmd) g_in.store_cmd(buf + 24, g_in.up_para);
+                if (g_in.do_action) g_in.do_action(clt, type, len, buf + 50, g_in.up_para);
+                uint64_t idx; memcpy(&idx, buf, 8);
+                if (idx % 10000 == 0) { uint64_t term; memcpy(&term, buf + 8, 8);
+                    LOGT("APPLY LOG ENTRY: (%llu; %llu)\n", (unsigned long long)idx, (unsigned long long)term); }
+            }
+            apply += stride;
+            if (apply == L) apply = 0;
+        }
+    }
+    free(buf);
+}
+
+void *dare_server_init(void *arg)
+{
+    dare_server_input_t *input = (dare_server_input_t *)arg;
+    g_in = *input;
+    g_log = input->log ? input->log : stdout;
+    free(input);                                       /* dare_server.c:208 */
+    signal(SIGINT, int_handler);                       /* dare_server.c:186-187 */
+
+    g_idx = g_in.server_idx; g_n = g_in.group_size;
+    const char *s;
+    g_leader_idx = (s = getenv("apus_leader")) ? (uint8_t)atoi(s) : 0;
+    if (g_in.srv_type != SRV_TYPE_START) { LOGT("server_type=join is not supported by the GPU engine yet\n"); return NULL; }
+    if (g_n < 1 || g_n > APUS_MAX_SERVER_COUNT || g_idx >= g_n) { LOGT("bad group_size/server_idx\n"); return NULL; }
+
+    apus_config_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = sizeof cfg;
+    int ndev = apus_device_count();
+    if (ndev < 1) { LOGT("no CUDA device: the engine has no CPU fallback\n"); return NULL; }
+    cfg.device = (s = getenv("apus_gpu")) ? atoi(s) : (int)(g_idx % (unsigned)ndev);
+    cfg.server_idx = g_idx; cfg.group_size = g_n; cfg.leader_idx = g_leader_idx;
+    cfg.ring_mode = APUS_RING_HOST_MAPPED;
+    cfg.flags = APUS_F_EXPLICIT | APUS_F_DEVICE_STATS | APUS_F_AUTOPRUNE;
+    cfg.term = 1;                                      /* term of a clean first election */
+    cfg.log_size = (s = getenv("apus_log_size")) ? strtoull(s, NULL, 0) : 0;
+    cfg.leader_ctas = 2;
+    if (apus_replica_create(&cfg, &g_rep) != APUS_OK) { LOGT("apus_replica_create: %s\n", apus_last_error()); return NULL; }
+
+    apus_peer_handle_t mine, all[APUS_MAX_SERVER_COUNT];
+    char dir[256];
+    if ((s = getenv("apus_rendezvous"))) snprintf(dir, sizeof dir, "%s", s);
+    else snprintf(dir, sizeof dir, "/tmp/apus-rdv-%u", (unsigned)getuid());
+    if (apus_replica_export(g_rep, &mine) != APUS_OK || rendezvous(dir, &mine, all)) {
+        LOGT("peer rendezvous failed in %s\n", dir); dare_server_shutdown();
+    }
+    for (unsigned i = 0; i < g_n; i++)
+        if (i != g_idx && apus_replica_connect(g_rep, (uint8_t)i, &all[i]) != APUS_OK) {
+            LOGT("apus_replica_connect(%u): %s\n", i, apus_last_error()); dare_server_shutdown();
+        }
+    apus_replica_t *rs[1] = { g_rep };
+    if (apus_replicas_launch(rs, 1, UINT64_MAX) != APUS_OK) { LOGT("launch: %s\n", apus_last_error()); dare_server_shutdown(); }
+    g_tk_type = (uint8_t *)calloc(TK_RING, 1);
+    g_started = 1;
+    LOGT("replica %u/%u up on GPU %d (leader %u)\n", (unsigned)g_idx, (unsigned)g_n, cfg.device, (unsigned)g_leader_idx);
+
+    if (g_idx == g_leader_idx) leader_pump();
+    else follower_pump(cfg.log_size ? cfg.log_size : APUS_LOG_SIZE);
+    LOGT("SIGINT detected; shutdown\n");
+    dare_server_shutdown();
+    return NULL;
+}

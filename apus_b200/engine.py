@@ -53,7 +53,7 @@ EXPORTS = [
     "apus_replica_destroy", "apus_replica_export", "apus_replica_connect", "apus_replicas_launch",
     "apus_replica_wait", "apus_replica_last_launch_ms", "apus_replicas_stop", "apus_submit",
     "apus_submit_batch", "apus_submit_defer", "apus_submit_flush", "apus_committed_tickets",
-    "apus_wait_committed", "apus_closed_loop", "apus_log_offsets", "apus_log_read", "apus_get_stats",
+    "apus_progress", "apus_wait_committed", "apus_closed_loop", "apus_log_offsets", "apus_log_read", "apus_get_stats",
     "apus_latency_samples", "apus_set_head", "apus_remote_apply_offsets",
 ]
 
@@ -88,6 +88,7 @@ def load_library(path=LIB_PATH):
     L.apus_committed_tickets.restype = u64
     L.apus_wait_committed.argtypes = [vp, u64, i64]
     L.apus_closed_loop.argtypes = [vp, u32, u16, u16, u64, vp]
+    L.apus_progress.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.apus_log_offsets.argtypes = [vp, C.POINTER(LogOffsets)]
     L.apus_log_read.argtypes = [vp, u64, u64, vp]
     L.apus_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -185,6 +186,11 @@ class Replica:
 
     def committed(self):
         return int(lib().apus_committed_tickets(self.h))
+
+    def progress(self):
+        off, cnt = u64(), u64()
+        _ck(lib().apus_progress(self.h, C.byref(off), C.byref(cnt)), "apus_progress")
+        return int(off.value), int(cnt.value)
 
     def wait_committed(self, ticket, timeout_us=10_000_000):
         _ck(lib().apus_wait_committed(self.h, ticket, timeout_us), "apus_wait_committed")

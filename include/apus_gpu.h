@@ -166,6 +166,11 @@ int  apus_submit_flush(apus_replica_t *leader);
 
 /* ---- commit observation (what update_state / do_action hang off) ---------------- */
 uint64_t apus_committed_tickets(apus_replica_t *leader);
+/* No CUDA call, just the pinned words the kernels keep up to date.  Leader: *offset = commit
+ * offset, *count = tickets committed.  Follower: *offset = apply offset (everything before it
+ * is committed and held by this replica -- what apply_committed_entries walks,
+ * dare_server.c:1815-1974), *count = entries acked. */
+int  apus_progress(apus_replica_t *r, uint64_t *offset, uint64_t *count);
 /* spin until ticket is committed; APUS_RETRY on timeout */
 int  apus_wait_committed(apus_replica_t *leader, uint64_t ticket, int64_t timeout_us);
 
