@@ -24,6 +24,9 @@
 /* the one real definition of the reference's header-defined globals (message.h:20-22) */
 struct apus_tailhead_t tailhead;
 pthread_spinlock_t tailq_lock;
+/* dare_log.h:27 declares it extern and every includer of that header (proxy.c among them)
+ * references it; the reference defines it in dare_server.c */
+int prev_log_entry_head;
 
 static FILE *g_log;
 static apus_replica_t *g_rep;

@@ -61,3 +61,23 @@ def test_config_struct_matches_header(built):
     assert C.sizeof(built.PeerHandle) == 128
     assert C.sizeof(built.LogOffsets) == 64
     assert C.sizeof(built.Stats) == 144
+
+
+def test_engine_entry_resolves_reference_proxy(built):
+    """libapus_dare.so exports the engine-entry symbols and satisfies every undefined symbol of the
+    reference's unmodified proxy.c (oracle/_ref/libref_proxy.so), without a GPU."""
+    dare = os.path.join(ROOT, "apus_b200", "libapus_dare.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", dare], capture_output=True, text=True).stdout
+    for s in ("dare_server_init", "dare_server_shutdown", "is_leader", "get_node_id", "tailhead", "tailq_lock",
+              "prev_log_entry_head"):
+        assert re.search(rf"\b[TBDC] {s}\b", out), s
+    refproxy = os.path.join(ROOT, "oracle", "_ref", "libref_proxy.so")
+    if not os.path.exists(refproxy):
+        pytest.skip("oracle/_ref/libref_proxy.so absent")
+    code = ("import ctypes as C;"
+            f"C.CDLL({built.LIB_PATH!r}, mode=C.RTLD_GLOBAL);"
+            f"d=C.CDLL({dare!r}, mode=C.RTLD_GLOBAL);"
+            f"p=C.CDLL({refproxy!r}, mode=C.RTLD_GLOBAL | 2);"   # RTLD_NOW: resolve everything
+            "assert d.is_leader()==0; print('ok')")
+    r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr
