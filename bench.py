@@ -229,23 +229,15 @@ class Cell:
             self.devices = sorted(set(devs))
             self.placement = "all replicas on GPU 0" if not args.spread else f"replica r on GPU r % {nd}"
         else:
+            from apus_b200 import placement as P
             self.group = None
             mine = {}
-            for g in range(world):
-                for r in range(n):
-                    if (g + r) % world == rank:
-                        mine[(g, r)] = E.Replica(local, r, n, 0, 1, L, ring_mode, slots if r == 0 else 0,
-                                                 ring_bytes if r == 0 else 0, flags, args.leader_ctas)
-            blobs = {k: v.export() for k, v in mine.items()}
-            allb = [None] * world
-            dist.all_gather_object(allb, blobs)
-            merged = {}
-            for d in allb:
-                merged.update(d)
-            for (g, r), rep in mine.items():
-                for r2 in range(n):
-                    if r2 != r:
-                        rep.connect(r2, merged[(g, r2)])
+            for g, r in P.hosted(rank, world, n):
+                mine[(g, r)] = E.Replica(local, r, n, 0, 1, L, ring_mode, slots if r == 0 else 0,
+                                         ring_bytes if r == 0 else 0, flags, args.leader_ctas)
+            merged = P.exchange(dist, {k: v.export() for k, v in mine.items()}, world)
+            for g, r, p in P.connections(rank, world, n):
+                mine[(g, r)].connect(p, merged[(g, p)])
             self.leader = mine[(rank, 0)]
             self.local = list(mine.values())
             self.devices = [local]
