@@ -624,7 +624,7 @@ extern "C" int apus_get_stats(apus_replica_t *r, apus_stats_t *out)
     out->lat_samples = c.lat_count;
     out->auto_heads = c.auto_heads;
     out->entries_published = c.published;
-    for (int i = 0; i < 8; i++) out->phase_ns[i] = c.phase_ns[i];
+    for (int i = 0; i < 8; i++) { out->phase_ns[i] = c.phase_ns[i]; out->turn_ns[i] = c.turn_ns[i]; }
     return APUS_OK;
 }
 

@@ -61,6 +61,10 @@ __device__ __forceinline__ void ld_acquire_sys_2x64(const volatile void *p, uint
     // an acquire LOAD costs ~0.26 us here, a system fence ~1.5 us (profiles/r1_ubench_2gpu.txt)
     asm volatile("ld.acquire.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
+__device__ __forceinline__ void ld_relaxed_sys_2x64(const volatile void *p, uint64_t &a, uint64_t &b)
+{
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void st_relaxed_sys(volatile void *p, uint64_t v)
 {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -146,18 +150,26 @@ struct LeaderShared {
     // per fetched slot (filled while fetching: no strided re-reads of the 128 B slots)
     uint32_t es[MAXB];         // log stride of the entry (64 + len, or 64)
     uint32_t xb[MAXB];         // payload-ring bytes to stage for it (0 when inline)
+    uint32_t cum_es[MAXB];     // inclusive prefix sum of es over the fetched batch (state independent)
+    uint32_t cum_xb[MAXB];     // inclusive prefix sum of xb
     uint32_t rel[MAXB];        // entry start - sub-tile start (bytes)
     uint32_t xoff[MAXB];       // offset of the entry's image in the ext staging
+    uint64_t ap[32];           // apply offsets of the replicas, read ahead of the place turn
+    uint32_t static_cut;       // first k > 0 whose payload image restarted the payload ring (else n_fetch)
+    uint32_t first_ext_all;    // first entry with an external payload image (else 0xffffffff)
+    uint64_t idx_base;         // idx of an entry = idx_base + its 1-based position in the placement order
     uint8_t  ty[MAXB];
     uint8_t  flg[MAXB];        // bit0 EXT, bit1 WRAP
     // claim
     uint32_t n_fetch, finish;
-    uint64_t slot0, my_seq, t_dequeue, claim_next, st_head;
+    uint32_t avg_es, avg_xb;   // log / staged bytes per entry seen in this worker's last claim (sizes the next one)
+    uint64_t slot0, my_seq, t_dequeue, claim_next, st_head, t_place_acq;
     // placement state while this CTA holds the place turn (mirrors apus_seq_t.p_*)
     uint64_t st_end, st_tail, st_next_idx, st_hwm, st_placed, st_auto_heads;
     uint32_t st_prev_head, pad0;
     // current sub-tile
-    uint32_t kbase, m, gap, ghost, fresh, auto_head, ext_bytes, last, blocked, pad1;
+    uint32_t kbase, m, gap, ghost, fresh, auto_head, ext_bytes, last, blocked, hbytes;
+    uint32_t base_es, base_xb, fast, pad1;
     uint64_t ext_base, auto_head_val, a, b, idx0, cum_after, new_end, tail_after, hwm_after, auto_heads_after;
     uint8_t  *peer_entries[APUS_MAX_SERVERS];
     uint32_t *peer_index[APUS_MAX_SERVERS];
@@ -213,7 +225,7 @@ __device__ __forceinline__ uint32_t hdr_byte(uint32_t j, uint64_t idx, uint64_t 
 }
 
 // bytes 0..40 of an entry header into shared memory at any alignment, by `gl` lanes (sub = lane in group)
-__device__ __forceinline__ void group_write_header(uint8_t *e, int sub, int gl, uint64_t idx, uint64_t term, uint64_t req_id,
+__device__ __noinline__ void group_write_header(uint8_t *e, int sub, int gl, uint64_t idx, uint64_t term, uint64_t req_id,
                                                    uint32_t clt, uint32_t type, uint32_t sender, bool skip_sender)
 {
     if ((((uint32_t)(uintptr_t)e) & 7u) == 0) {
@@ -238,7 +250,7 @@ __device__ __forceinline__ void group_write_header(uint8_t *e, int sub, int gl, 
 }
 
 // copy nbytes from a 16 B-aligned shared source to an arbitrarily aligned shared destination
-__device__ __forceinline__ void group_copy_smem(uint8_t *dst, const uint8_t *src, uint32_t nbytes, int sub, int gl)
+__device__ __noinline__ void group_copy_smem(uint8_t *dst, const uint8_t *src, uint32_t nbytes, int sub, int gl)
 {
     const uint32_t nchunks = (nbytes + 15u) >> 4;
     const uint32_t dalign = (uint32_t)(uintptr_t)dst & 15u;
@@ -267,7 +279,7 @@ __device__ __forceinline__ void group_copy_smem(uint8_t *dst, const uint8_t *src
 }
 
 // global (16 B aligned) -> shared, nchunks 16 B chunks, by all producer threads, 4 loads in flight each
-__device__ __forceinline__ void cta_fetch_chunks(uint8_t *dst, const uint8_t *src, uint32_t nchunks, int tid)
+__device__ __noinline__ void cta_fetch_chunks(uint8_t *dst, const uint8_t *src, uint32_t nchunks, int tid)
 {
     uint32_t c = tid;
     for (; c + 3u * NT < nchunks; c += 4u * NT) {
@@ -294,7 +306,7 @@ __device__ __forceinline__ void note_desc(LeaderShared *S, uint32_t k, const uin
 }
 
 // fetch `cnt` slots starting at ring slot `s` into shared slot `k0` onward
-__device__ __forceinline__ void cta_fetch_slots(LeaderShared *S, uint8_t *slots, const apus_slot_t *ring, uint64_t s, uint32_t k0,
+__device__ __noinline__ void cta_fetch_slots(LeaderShared *S, uint8_t *slots, const apus_slot_t *ring, uint64_t s, uint32_t k0,
                                                 uint32_t cnt, int tid)
 {
     const uint8_t *src = reinterpret_cast<const uint8_t *>(ring + s);
@@ -433,12 +445,44 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
     }
 }
 
-// T2: place the next sub-tile of the fetched batch (entries kbase..nf) -- log_append_entry's offset
-// rules, free-space rule E2 and the pruning rule, all on the placement state this CTA holds.
-__device__ void leader_place(const apus_devctx_t *__restrict__ cx, LeaderShared *S, const apus_slot_t *sl, int lane)
+// T2a (outside the place turn): state-independent part of the placement -- inclusive prefix sums
+// of the log strides and of the staged payload bytes of the fetched batch; apply offsets read ahead
+__device__ __noinline__ void leader_prescan(const apus_devctx_t *__restrict__ cx, LeaderShared *S, int lane)
 {
-    const int N = cx->group_size, me = cx->idx;
     apus_ctrl_t *ctrl = reinterpret_cast<apus_ctrl_t *>(cx->region);
+    apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_HDR_OFF);
+    const uint32_t nf = S->n_fetch;
+    uint32_t carry = 0, xcarry = 0, scut = nf, fext = 0xffffffffu;
+    for (uint32_t r = 0; r < nf; r += 32) {
+        const uint32_t k = r + lane;
+        const bool in = k < nf;
+        uint32_t inc = in ? S->es[k] : 0u, xinc = in ? S->xb[k] : 0u;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, sft);
+            const uint32_t xo = __shfl_up_sync(0xffffffffu, xinc, sft);
+            if (lane >= sft) { inc += o; xinc += xo; }
+        }
+        if (in) { S->cum_es[k] = carry + inc; S->cum_xb[k] = xcarry + xinc; }
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+        xcarry += __shfl_sync(0xffffffffu, xinc, 31);
+        const uint32_t wm = __ballot_sync(0xffffffffu, in && k > 0 && (S->flg[k] & 2u));
+        const uint32_t em = __ballot_sync(0xffffffffu, in && (S->flg[k] & 1u));
+        if (wm && scut == nf) scut = r + (uint32_t)(__ffs(wm) - 1);
+        if (em && fext == 0xffffffffu) fext = r + (uint32_t)(__ffs(em) - 1);
+    }
+    if (lane == 0) { S->static_cut = scut; S->first_ext_all = fext; }
+    if (lane < cx->group_size)
+        S->ap[lane] = (lane == cx->idx) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[lane]);
+}
+
+// T2b (inside the place turn): place the next sub-tile of the fetched batch (entries kbase..nf) --
+// log_append_entry's offset rules, free-space rule E2 and the pruning rule, on the placement
+// state this CTA holds.  Kept short: everything state independent was done by leader_prescan.
+__device__ __noinline__ void leader_place(const apus_devctx_t *__restrict__ cx, LeaderShared *S, const apus_slot_t *sl, int lane,
+                                          const bool dry)
+{
+    const int N = cx->group_size;
     apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_HDR_OFF);
     const uint64_t L = cx->log_len;
     const bool autoprune = (cx->flags & APUS_FLAG_AUTOPRUNE) != 0;
@@ -455,10 +499,10 @@ __device__ void leader_place(const apus_devctx_t *__restrict__ cx, LeaderShared 
     if (autoprune && end != L && used >= (L >> 2) && !S->st_prev_head && L - pos0 >= APUS_HDR_BYTES) {
         uint64_t d = 0;                                   // distance apply -> end, per replica
         if (lane < N) {
-            const uint64_t ap = (lane == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[lane]);
-            d = ring_dist(ap, end, L);
-            if (d > used) d = used;                       // never behind the current head
+            d = ring_dist(S->ap[lane], end, L);
+            if (d > used) d = used;                       // never behind the current head (or stale read-ahead)
         }
+#pragma unroll
         for (int sft = 16; sft > 0; sft >>= 1) {
             const uint64_t o = __shfl_xor_sync(0xffffffffu, d, sft);
             d = o > d ? o : d;
@@ -480,35 +524,26 @@ __device__ void leader_place(const apus_devctx_t *__restrict__ cx, LeaderShared 
     const uint64_t reserve = autoprune ? APUS_HDR_BYTES : 0;
     const uint64_t lim_space = (L - used > 1 + reserve) ? (L - used - 1 - reserve) : 0;
     const uint64_t limit = lim < lim_space ? lim : lim_space;
+    const uint32_t base_es = kbase ? S->cum_es[kbase - 1] : 0u, base_xb = kbase ? S->cum_xb[kbase - 1] : 0u;
 
-    // rounds of 32 entries: inclusive scans of log strides and of staged payload bytes
-    uint32_t carry = hbytes, xcarry = 0, m = nf - kbase, first_ext = 0xffffffffu;
+    // how many entries from kbase fit: the prefix sums are monotone, one compare + ballot per 32 entries
+    uint32_t m = nf - kbase, first_ext = 0xffffffffu;
     for (uint32_t r = kbase; r < nf; r += 32) {
         const uint32_t k = r + lane;
         const bool in = k < nf;
-        const uint32_t es = in ? S->es[k] : 0u, xb = in ? S->xb[k] : 0u;
-        uint32_t inc = es, xinc = xb;
-        for (int sft = 1; sft < 32; sft <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, sft);
-            const uint32_t xo = __shfl_up_sync(0xffffffffu, xinc, sft);
-            if (lane >= sft) { inc += o; xinc += xo; }
-        }
-        const uint32_t run = carry + inc - es, xrun = xcarry + xinc - xb;     // exclusive
-        const bool bad = in && ((uint64_t)run + es > limit || xrun + xb > APUS_LEADER_EXT_BYTES ||
-                                (k > kbase && (S->flg[k] & 2u)));
+        const bool bad = in && ((uint64_t)hbytes + (S->cum_es[k] - base_es) > limit ||
+                                S->cum_xb[k] - base_xb > APUS_LEADER_EXT_BYTES || (k > kbase && (S->flg[k] & 2u)));
         const uint32_t badmask = __ballot_sync(0xffffffffu, bad);
-        const uint32_t good = badmask ? (uint32_t)(__ffs(badmask) - 1) : 32u;   // lanes below `good` are placed
-        if (in && (uint32_t)lane < good) { S->rel[k] = run; S->xoff[k] = xrun; }
+        const uint32_t good = badmask ? (uint32_t)(__ffs(badmask) - 1) : 32u;
         if (first_ext == 0xffffffffu) {
             const uint32_t extmask = __ballot_sync(0xffffffffu, in && (uint32_t)lane < good && (S->flg[k] & 1u));
             if (extmask) first_ext = r + (uint32_t)(__ffs(extmask) - 1);
         }
-        if (badmask) { m = r + good - kbase; xcarry = __shfl_sync(0xffffffffu, xrun, good); carry = __shfl_sync(0xffffffffu, run, good); break; }
-        carry = __shfl_sync(0xffffffffu, run + es, 31);
-        xcarry = __shfl_sync(0xffffffffu, xrun + xb, 31);
+        if (badmask) { m = r + good - kbase; break; }
     }
-    // carry = log bytes of the sub-tile (HEAD entry included), xcarry = staged payload bytes
     if (lane == 0) {
+        const uint32_t carry = hbytes + (m ? S->cum_es[kbase + m - 1] - base_es : 0u);      // log bytes of the sub-tile
+        const uint32_t xcarry = m ? S->cum_xb[kbase + m - 1] - base_xb : 0u;               // staged payload bytes
         S->gap = 0; S->ghost = 0; S->blocked = 0; S->last = 0;
         uint64_t a = pos0, b = pos0;
         if (m == 0 && !autoh) {
@@ -526,6 +561,7 @@ __device__ void leader_place(const apus_devctx_t *__restrict__ cx, LeaderShared 
             b = pos0 + carry;
         }
         S->a = a; S->b = b; S->m = m;
+        S->hbytes = hbytes; S->base_es = base_es; S->base_xb = base_xb;
         S->ext_bytes = (m && first_ext != 0xffffffffu) ? xcarry : 0u;
         S->ext_base = (first_ext != 0xffffffffu) ? (uint64_t)(sl[first_ext].type_off & APUS_SLOT_OFF_MASK) * 16ull : 0ull;
         S->auto_head = autoh; S->auto_head_val = new_head;
@@ -533,20 +569,20 @@ __device__ void leader_place(const apus_devctx_t *__restrict__ cx, LeaderShared 
         S->fresh = (a >= S->st_hwm) ? 1u : 0u;
         if (!S->blocked) {
             // commit the placement to the state this CTA carries
-            if (autoh) { st_relaxed_sys(&hdr->head, new_head); S->st_head = new_head; }
+            if (autoh && !dry) st_relaxed_sys(&hdr->head, new_head);
+            if (autoh) S->st_head = new_head;
             if (S->gap) {
                 S->st_end = 0; S->st_hwm = L;
             } else {
                 uint64_t ne = b; if (ne == L) ne = 0;                   // rule E1
                 S->new_end = ne;
                 S->st_end = ne;
-                S->st_tail = m ? a + S->rel[kbase + m - 1] : a;
+                S->st_tail = m ? a + hbytes + (S->cum_es[kbase + m - 1] - base_es) - S->es[kbase + m - 1] : a;
                 S->tail_after = S->st_tail;
                 S->st_next_idx += m + autoh;
                 S->st_placed += m + autoh;
                 S->cum_after = S->st_placed;
-                S->st_auto_heads += autoh;
-                S->auto_heads_after = S->st_auto_heads;
+                if (autoh && !dry) atomicAdd(reinterpret_cast<unsigned long long *>(&reinterpret_cast<apus_ctrl_t *>(cx->region)->auto_heads), 1ull);
                 S->st_prev_head = (autoh && m == 0) ? 1u : 0u;         // never two HEAD entries in a row (dare_log.h:477-480)
                 if (b > S->st_hwm) S->st_hwm = b;
                 S->last = (kbase + m == nf) ? 1u : 0u;
@@ -578,8 +614,10 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             seq->claim_ticket = 0; seq->claim_serving = 0;
             seq->claimed_slots = ctrl->consumed; seq->tile_seq = 0; seq->claims_closed = 0;
             seq->place_seq = 0; seq->pub_seq = 0; seq->workers_done = 0; seq->abort_flag = 0;
-            seq->p_end = hdr->end; seq->p_tail = hdr->tail; seq->p_next_idx = ctrl->next_idx; seq->p_hwm = ctrl->hwm;
-            seq->p_placed = ctrl->published; seq->p_prev_head = 0; seq->p_auto_heads = ctrl->auto_heads;
+            seq->rec_placed[0] = 0; seq->rec_placed[1] = ctrl->published;
+            seq->rec_end[0] = 0; seq->rec_end[1] = hdr->end;
+            seq->rec_tail[0] = 0; seq->rec_tail[1] = hdr->tail | (ctrl->hwm == cx->log_len ? APUS_REC_WRAPPED : 0ull);
+            seq->rec_head[0] = 0; seq->rec_head[1] = hdr->head;
             // entries published by an earlier launch but not yet committed come back as one record
             seq->pub_head = 0; seq->pub_tail = 0;
             if (ctrl->published != ctrl->committed) {
@@ -592,7 +630,8 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
         } else {
             while (ld_acquire_gpu(&seq->ready_epoch) != cx->epoch) { }
         }
-        S->finish = 0;
+        S->finish = 0; S->avg_es = 128; S->avg_xb = 0;
+        S->idx_base = ctrl->next_idx - 1 - ctrl->published;
         for (int i = 0; i < APUS_MAX_SERVERS; i++) {
             S->peer_entries[i] = (i < N && i != me && cx->peer[i]) ? cx->peer[i] + cx->entries_off : nullptr;
             S->peer_index[i] = (i < N && i != me && cx->peer[i]) ? reinterpret_cast<uint32_t *>(cx->peer[i] + APUS_INDEX_OFF) : nullptr;
@@ -608,18 +647,20 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
     // ---- producer warps 0..14 ------------------------------------------------------
     uint64_t last_progress = globaltimer_ns();
     const bool prof = (cx->flags & APUS_FLAG_STATS) != 0 && tid == 0 && wid == 0;
-    uint64_t ph[8], tprev = globaltimer_ns();
-    for (int i = 0; i < 8; i++) ph[i] = ctrl->phase_ns[i];
+    uint64_t ph[8], tn[8], tprev = globaltimer_ns();
+    for (int i = 0; i < 8; i++) { ph[i] = ctrl->phase_ns[i]; tn[i] = ctrl->turn_ns[i]; }
 #define PHASE(i) do { if (prof) { const uint64_t _t = globaltimer_ns(); ph[i] += _t - tprev; tprev = _t; } } while (0)
 
     for (;;) {
         // ---- T0: claim the next slots of the submission ring (ticket lock: one poller at a time) ----
         if (tid == 0) {
             uint32_t n = 0, fin = 0, spins = 0;
+            const uint64_t tw0 = prof ? globaltimer_ns() : 0;
             const uint64_t ticket = atomicAdd(reinterpret_cast<unsigned long long *>(&seq->claim_ticket), 1ull);
             while (ld_acquire_gpu(&seq->claim_serving) != ticket) {
                 if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
             }
+            if (prof) { tn[0] += globaltimer_ns() - tw0; tn[6]++; }
             if (ld_relaxed_sys(&seq->claims_closed) || ld_relaxed_sys(&seq->abort_flag)) fin = 1;
             uint64_t claimed = ld_relaxed_sys(&seq->claimed_slots);
             while (!fin) {
@@ -632,6 +673,14 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     // share a shallow queue between the workers instead of one big tile
                     uint64_t want = (avail + cx->n_workers - 1) / cx->n_workers;
                     if (want < 32) want = avail < 32 ? avail : 32;
+                    // a claim should fit ONE tile image / staging buffer (else it is placed in pieces
+                    // while holding the place turn, which serializes the workers)
+                    uint64_t aes = ld_relaxed_sys(&seq->avg_es), axb = ld_relaxed_sys(&seq->avg_xb);
+                    if (aes < 64) aes = 128;
+                    uint64_t fit = (APUS_LEADER_IMG_BYTES - 256u) / aes;
+                    if (axb) { const uint64_t xf = APUS_LEADER_EXT_BYTES / axb; if (xf < fit) fit = xf; }
+                    if (fit < 1) fit = 1;
+                    if (want > fit) want = fit;
                     n = want > MAXB ? MAXB : (uint32_t)want;
                     break;
                 }
@@ -658,7 +707,6 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
         if (tid == 0) st_release_gpu(&seq->claim_serving, S->claim_next);
         if (S->finish) break;
         const uint32_t nf = S->n_fetch;
-        const bool lowlat = nf <= 8;          // few requests in flight: favour latency over overlap
         PHASE(0);
 
         // ---- T1: fetch the slots (descriptor + inline payload), coalesced 16 B loads --------
@@ -669,34 +717,121 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             cta_fetch_slots(S, slots, cx->sub_slots, s0, 0, first, tid);
             if (first < nf) cta_fetch_slots(S, slots, cx->sub_slots, 0, first, nf - first, tid);
         }
-        // ---- wait for the place turn, take over the placement state ----
-        if (tid == 0) {
-            uint32_t spins = 0;
-            while (ld_acquire_gpu(&seq->place_seq) != S->my_seq) {
-                if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
-            }
-            S->st_end = seq->p_end; S->st_tail = seq->p_tail; S->st_next_idx = seq->p_next_idx; S->st_hwm = seq->p_hwm;
-            S->st_placed = seq->p_placed; S->st_prev_head = (uint32_t)seq->p_prev_head; S->st_auto_heads = seq->p_auto_heads;
-            S->st_head = ld_relaxed_sys(&hdr->head);
-            S->kbase = 0;
-        }
+        if (tid == 0) S->kbase = 0;
         bar_sync(1, NT);
         PHASE(1);
+        if (warp == 1) {
+            // entry-size statistics of this claim (sizes the next one)
+            uint32_t se = 0, sx = 0;
+            for (uint32_t k = lane; k < nf; k += 32) { se += S->es[k]; sx += S->xb[k]; }
+            for (int sft = 16; sft > 0; sft >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, sft); sx += __shfl_xor_sync(0xffffffffu, sx, sft); }
+            if (lane == 0) { st_relaxed_sys(&seq->avg_es, (se + nf - 1) / nf); st_relaxed_sys(&seq->avg_xb, (sx + nf - 1) / nf); }
+        }
         const apus_slot_t *sl = reinterpret_cast<const apus_slot_t *>(slots);
-        bool have_pub_turn = false, aborted = false;
+        bool have_pub_turn = false, have_place_turn = false, aborted = false;
         uint64_t gap_bytes = 0;      // bytes of a wrap gap replicated ahead of the next publish
 
         while (S->kbase < nf) {
             // ---- T2: placement of the next sub-tile (warp 0) ----
             if (warp == 0) {
-                leader_place(cx, S, sl, lane);
-                if (lane == 0 && S->last && !lowlat) {
-                    // all my slots are placed: hand the placement state to the next claim
-                    seq->p_end = S->st_end; seq->p_tail = S->st_tail; seq->p_next_idx = S->st_next_idx; seq->p_hwm = S->st_hwm;
-                    seq->p_placed = S->st_placed; seq->p_prev_head = S->st_prev_head; seq->p_auto_heads = S->st_auto_heads;
-                    st_release_gpu(&seq->place_seq, S->my_seq + 1);
+                bool placed_fast = false;
+                if (!have_place_turn) {
+                    leader_prescan(cx, S, lane);
+                    __syncwarp();
+                    // the place turn: wait until the three stamped pairs carry my claim number.  It is held for
+                    // the state-dependent offset arithmetic alone (not the fetch, not the prefix sums), and in
+                    // the common case -- everything fits contiguously, no pruning due -- for a dozen integer ops
+                    if (lane == 0) {
+                        uint32_t spins = 0;
+                        const uint64_t tw0 = prof ? globaltimer_ns() : 0;
+                        uint64_t s0, s1, s2, s3, placed, end, tf, headv;
+                        for (;;) {
+                            ld_relaxed_sys_2x64(seq->rec_placed, s0, placed);
+                            ld_relaxed_sys_2x64(seq->rec_end, s1, end);
+                            ld_relaxed_sys_2x64(seq->rec_tail, s2, tf);
+                            ld_relaxed_sys_2x64(seq->rec_head, s3, headv);
+                            if (s0 == S->my_seq && s1 == S->my_seq && s2 == S->my_seq && s3 == S->my_seq) break;
+                            if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
+                        }
+                        if (prof) { tn[1] += globaltimer_ns() - tw0; S->t_place_acq = globaltimer_ns(); }
+                        const uint64_t L = cx->log_len;
+                        const bool wrapped = (tf & APUS_REC_WRAPPED) != 0, prevh = (tf & APUS_REC_PREV_HEAD) != 0;
+                        const uint64_t tail = tf & ~(APUS_REC_WRAPPED | APUS_REC_PREV_HEAD);
+                        // ---- fast path ----
+                        // a host control plane may also move the head (apus_set_head): take the newer of the two
+                        {
+                            const uint64_t hh = ld_relaxed_sys(&hdr->head);
+                            if (end != L && ring_dist(hh, end, L) < ring_dist(headv, end, L)) headv = hh;
+                        }
+                        S->st_head = headv;
+                        const uint64_t pos0 = (end == L) ? 0 : end;
+                        const uint64_t used = (end == L) ? 0 : ring_dist(headv, end, L);
+                        const uint64_t total = S->cum_es[nf - 1];
+                        const bool autoprune = (cx->flags & APUS_FLAG_AUTOPRUNE) != 0;
+                        const uint64_t reserve = autoprune ? APUS_HDR_BYTES : 0;
+                        // is the pruning rule due?  (scalar version of the test in leader_place)
+                        bool prune_due = false;
+                        if (autoprune && end != L && used >= (L >> 2) && !prevh && L - pos0 >= APUS_HDR_BYTES) {
+                            uint64_t d = 0;
+                            for (int i = 0; i < cx->group_size; i++) {
+                                uint64_t di = ring_dist(S->ap[i], end, L);
+                                if (di > used) di = used;
+                                d = di > d ? di : d;
+                            }
+                            if (d == 0) d = ring_dist(tail, end, L);
+                            prune_due = (d <= used && used - d >= (L >> 3));
+                        }
+                        if (!prune_due && pos0 + total <= L &&
+                            total <= APUS_LEADER_IMG_BYTES - 16u - (pos0 & 15u) && used + total + reserve < L && S->cum_xb[nf - 1] <= APUS_LEADER_EXT_BYTES && S->static_cut == nf) {
+                            const uint64_t b = pos0 + total;
+                            const uint64_t ne = (b == L) ? 0 : b;
+                            const uint64_t nt = b - S->es[nf - 1];
+                            const bool nw = wrapped || b == L;
+                            // hand the turn on at once
+                            st_relaxed_sys_2x64(seq->rec_placed, S->my_seq + 1, placed + nf);
+                            st_relaxed_sys_2x64(seq->rec_end, S->my_seq + 1, ne);
+                            st_relaxed_sys_2x64(seq->rec_tail, S->my_seq + 1, nt | (nw ? APUS_REC_WRAPPED : 0ull));
+                            st_relaxed_sys_2x64(seq->rec_head, S->my_seq + 1, headv);
+                            if (prof) { tn[7] += globaltimer_ns() - S->t_place_acq; tn[3]++; }
+                            // ... and only then write down the tile for the other warps
+                            const uint64_t hwm = wrapped ? L : pos0;
+                            S->gap = 0; S->ghost = 0; S->blocked = 0; S->last = 1;
+                            S->a = pos0; S->b = b; S->m = nf;
+                            S->hbytes = 0; S->base_es = 0; S->base_xb = 0;
+                            S->ext_bytes = (S->first_ext_all != 0xffffffffu) ? S->cum_xb[nf - 1] : 0u;
+                            S->ext_base = (S->first_ext_all != 0xffffffffu)
+                                              ? (uint64_t)(sl[S->first_ext_all].type_off & APUS_SLOT_OFF_MASK) * 16ull : 0ull;
+                            S->auto_head = 0; S->auto_head_val = 0;
+                            S->idx0 = S->idx_base + placed + 1;
+                            S->fresh = (pos0 >= hwm && !wrapped) ? 1u : 0u;
+                            S->new_end = ne; S->tail_after = nt; S->cum_after = placed + nf;
+                            S->hwm_after = nw ? L : b;
+                            S->fast = 1;
+                        } else {
+                            S->st_end = end; S->st_tail = tail; S->st_placed = placed;
+                            S->st_next_idx = S->idx_base + placed + 1;
+                            S->st_hwm = wrapped ? L : pos0; S->st_prev_head = prevh ? 1u : 0u;
+                            S->fast = 0;
+                            if (prof) tn[4]++;
+                        }
+                    }
+                    __syncwarp();
+                    placed_fast = S->fast != 0;
+                }
+                if (!placed_fast) {
+                    leader_place(cx, S, sl, lane, false);
+                    if (lane == 0 && S->last) {
+                        // all my slots are placed: hand the placement state to the next claim
+                        st_relaxed_sys_2x64(seq->rec_placed, S->my_seq + 1, S->st_placed);
+                        st_relaxed_sys_2x64(seq->rec_end, S->my_seq + 1, S->st_end);
+                        st_relaxed_sys_2x64(seq->rec_tail, S->my_seq + 1, S->st_tail | (S->st_hwm == cx->log_len ? APUS_REC_WRAPPED : 0ull) |
+                                                                              (S->st_prev_head ? APUS_REC_PREV_HEAD : 0ull));
+                        st_relaxed_sys_2x64(seq->rec_head, S->my_seq + 1, S->st_head);
+                        if (prof) tn[7] += globaltimer_ns() - S->t_place_acq;
+                    }
                 }
             }
+            have_place_turn = true;
             bar_sync(1, NT);
             PHASE(2);
             if (S->blocked) {   // no space before head: poll again
@@ -707,7 +842,13 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         st_relaxed_sys(&seq->abort_flag, 1); S->finish = 1;
                     }
                 }
-                if (tid == 0) S->st_head = ld_relaxed_sys(&hdr->head);
+                if (tid == 0) {
+                    // a host control plane may have moved the head; the apply offsets move all the time
+                    const uint64_t hh = ld_relaxed_sys(&hdr->head);
+                    if (S->st_end != cx->log_len && ring_dist(hh, S->st_end, cx->log_len) < ring_dist(S->st_head, S->st_end, cx->log_len))
+                        S->st_head = hh;
+                }
+                if (tid < N) S->ap[tid] = (tid == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[tid]);
                 bar_sync(1, NT);
                 if (S->finish) { aborted = true; break; }
                 continue;
@@ -726,6 +867,11 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                 cta_fetch_chunks(img, entries + a16, nchunks, tid);
             }
             if (!gap && S->ext_bytes) cta_fetch_chunks(ext, cx->sub_pay + S->ext_base, S->ext_bytes >> 4, tid);
+            for (uint32_t j = tid; j < m; j += NT) {
+                const uint32_t k = kbase + j;
+                S->rel[k] = S->hbytes + (S->cum_es[k] - S->base_es) - S->es[k];
+                S->xoff[k] = (S->cum_xb[k] - S->base_xb) - S->xb[k];
+            }
             bar_sync(1, NT);
             PHASE(3);
 
@@ -800,6 +946,11 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     for (int f = 0; f < N; f++)
                         if (S->peer_index[f]) S->peer_index[f][at] = w;
                 }
+                // data before tail (invariant I1): EVERY thread waits until its own stores are performed
+                // system-wide, then the barrier, then the tail.  (A single fence behind the barrier is
+                // equivalent in the PTX model, but it lets the other warps' stores drain into the next
+                // tile, where they stall the warp that holds the place turn.)
+                __threadfence_system();
             }
             bar_sync(1, NT);
             PHASE(5);
@@ -813,12 +964,13 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             }
             if (warp == 0) {
                 const bool pubs = lane < N && lane != me && cx->peer[lane];
-                if (pubs || lane == 0) __threadfence_system();          // my CTA's data stores, system wide
                 if (lane == 0 && !have_pub_turn) {
                     uint32_t spins = 0;
+                    const uint64_t tw0 = prof ? globaltimer_ns() : 0;
                     while (ld_acquire_gpu(&seq->pub_seq) != S->my_seq) {
                         if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
                     }
+                    if (prof) tn[2] += globaltimer_ns() - tw0;
                 }
                 __syncwarp();
                 if (pubs) {
@@ -829,7 +981,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     const uint64_t consumed = S->slot0 + kbase + m;
                     hdr->end = S->new_end; hdr->tail = S->tail_after; hdr->old_end = S->new_end;
                     ctrl->next_idx = S->idx0 + m + autoh; ctrl->consumed = consumed;
-                    ctrl->hwm = S->hwm_after; ctrl->auto_heads = S->auto_heads_after;
+                    ctrl->hwm = S->hwm_after;
                     ctrl->bytes_replicated += (b - a + gap_bytes) * (uint64_t)(N - 1);   // a gap skipped before it counts too
                     ctrl->batches += 1;
                     const uint64_t h = ld_relaxed_sys(&seq->pub_head);
@@ -842,12 +994,6 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     st_relaxed_sys(&ctrl->published, S->cum_after);
                     st_release_gpu(&seq->pub_head, h + 1);
                     st_relaxed_sys(&hw->consumed, consumed);
-                    if (S->last && lowlat) {
-                        // deferred hand-over of the placement state (kept off the latency path)
-                        seq->p_end = S->st_end; seq->p_tail = S->st_tail; seq->p_next_idx = S->st_next_idx; seq->p_hwm = S->st_hwm;
-                        seq->p_placed = S->st_placed; seq->p_prev_head = S->st_prev_head; seq->p_auto_heads = S->st_auto_heads;
-                        st_release_gpu(&seq->place_seq, S->my_seq + 1);
-                    }
                     if (S->last) st_release_gpu(&seq->pub_seq, S->my_seq + 1);
                     S->kbase = kbase + m;
                 }
@@ -858,12 +1004,12 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             bar_sync(1, NT);
             if (prof) {
                 PHASE(6); ph[7]++;
-                for (int i = 0; i < 8; i++) ctrl->phase_ns[i] = ph[i];
+                for (int i = 0; i < 8; i++) { ctrl->phase_ns[i] = ph[i]; ctrl->turn_ns[i] = tn[i]; }
             }
         }
         if (aborted) break;
     }
-    if (prof) for (int i = 0; i < 8; i++) ctrl->phase_ns[i] = ph[i];
+    if (prof) for (int i = 0; i < 8; i++) { ctrl->phase_ns[i] = ph[i]; ctrl->turn_ns[i] = tn[i]; }
     if (tid == 0) { __threadfence(); atomicAdd(reinterpret_cast<unsigned long long *>(&seq->workers_done), 1ull); }
 }
 

@@ -102,7 +102,8 @@ typedef struct apus_ctrl {
     uint64_t pad2[14];
     /* --- leader profiling (APUS_F_DEVICE_STATS): ns spent per phase of the tile loop --- */
     uint64_t phase_ns[8];        /* [0] wait for requests, [1..6] T1..T6, [7] tiles */
-    uint64_t pad3[8];
+    uint64_t turn_ns[8];         /* worker 0: [0] claim-lock wait, [1] place-turn wait, [2] publish-turn wait (ns),
+                                    [3] fast placements, [4] slow placements, [7] place-turn hold (ns) */
 } apus_ctrl_t;
 
 /* Sequencer shared by the leader's worker CTAs (device memory, gpu-scope atomics).
@@ -124,10 +125,20 @@ typedef struct apus_seq {
     uint64_t abort_flag;
     uint64_t ready_epoch;        /* == devctx.epoch once worker 0 has reset the block */
     uint64_t pad_h[13];
-    /* placement state, owned by the worker holding the place turn */
-    uint64_t p_end, p_tail, p_next_idx, p_hwm, p_placed, p_prev_head, p_auto_heads;
-    uint64_t pad_i[9];
+    /* placement state handed from claim to claim: three 16 B {stamp, value} pairs, each written
+     * with ONE 16 B store and read with one 16 B load.  stamp == the claim sequence number whose
+     * turn it is: the hand-over needs no fence (a system/gpu fence costs 0.2-1.5 us and the turn is
+     * the only serialized part of the leader) */
+    uint64_t rec_placed[2];      /* {stamp, entries placed so far} */
+    uint64_t rec_end[2];         /* {stamp, end offset after the last placed entry (len = empty log)} */
+    uint64_t rec_tail[2];        /* {stamp, tail offset | APUS_REC_PREV_HEAD | APUS_REC_WRAPPED} */
+    uint64_t rec_head[2];        /* {stamp, head offset} (only the turn holder moves the head) */
+    uint64_t avg_es, avg_xb;     /* log / staged bytes per entry of the latest claim (sizes the next claims;
+                                    kept across launches) */
+    uint64_t pad_i[6];
 } apus_seq_t;
+#define APUS_REC_PREV_HEAD (1ull << 62)   /* the last placed entry is a HEAD entry of the pruning rule */
+#define APUS_REC_WRAPPED   (1ull << 63)   /* the ring has wrapped at least once (no fresh bytes left) */
 
 typedef struct apus_pubrec {
     uint64_t cum;                /* entries published up to and including this tile */

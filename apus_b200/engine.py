@@ -43,7 +43,7 @@ class LogOffsets(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(k, u64) for k in ("tickets_submitted", "tickets_consumed", "tickets_committed",
                                    "entries_acked", "bytes_replicated", "batches", "kernel_launches",
-                                   "lat_samples", "auto_heads", "entries_published")] + [("phase_ns", u64 * 8)]
+                                   "lat_samples", "auto_heads", "entries_published")] + [("phase_ns", u64 * 8), ("turn_ns", u64 * 8)]
 
 
 _lib = None
@@ -216,8 +216,9 @@ class Replica:
     def stats(self):
         s = Stats()
         _ck(lib().apus_get_stats(self.h, C.byref(s)), "apus_get_stats")
-        d = {k: int(getattr(s, k)) for k, _ in Stats._fields_ if k != "phase_ns"}
+        d = {k: int(getattr(s, k)) for k, _ in Stats._fields_ if k not in ("phase_ns", "turn_ns")}
         d["phase_ns"] = [int(x) for x in s.phase_ns]
+        d["turn_ns"] = [int(x) for x in s.turn_ns]
         return d
 
     def latency_ns(self, max_samples=65536):

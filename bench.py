@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--e2e-ring", default="mapped", choices=["mapped", "device"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-stats", action="store_true", help="value run without device-side profiling counters")
     ap.add_argument("--leader-ctas", type=int, default=0, help="leader worker CTAs (0 = engine default)")
     ap.add_argument("--spread", action="store_true",
                     help="single process: place replica r on GPU r %% visible GPUs (NVLink path)")
@@ -316,6 +317,7 @@ def run_ours(args):
     if ring_bytes // 16 > 0xFFFFFF:
         raise SystemExit("steps*batch*payload too large for the device submission ring (256 MiB)")
     flags = E.F_DEVICE_STATS | E.F_AUTOPRUNE
+    vflags = E.F_AUTOPRUNE if args.no_stats else flags
 
     def barrier():
         torch.cuda.synchronize()
@@ -352,7 +354,7 @@ def run_ours(args):
     payloads = np.random.default_rng(0xA5A50000 + payload).integers(0, 256, size=batch * max(payload, 1), dtype=np.uint8)
 
     # =========================== value: inputs resident in HBM ===========================
-    cell = Cell(A, E, args, A.RING_DEVICE, slots, ring_bytes, flags, dist, rank, world, local)
+    cell = Cell(A, E, args, A.RING_DEVICE, slots, ring_bytes, vflags, dist, rank, world, local)
     cell.submit(E.CONFIG, 0, 0, E.cid_image(n)) if n > 1 else None
     cell.submit(CONNECT, conn, 1, b"")
     barrier()
@@ -391,6 +393,7 @@ def run_ours(args):
     lat_dev = cell.leader.latency_ns()
     auto_heads = st["auto_heads"]
     log(f"leader phases (ns, cumulative): {st['phase_ns']}")
+    log(f"worker-0 turns [claim-wait ns, place-wait ns, publish-wait ns, fast placements, slow placements, -, -, place-hold ns]: {st['turn_ns'][:8]}")
     batches = st["batches"]
     off = cell.leader.offsets()
     cell.close()

@@ -116,6 +116,8 @@ typedef struct apus_stats {
     uint64_t auto_heads;          /* leader: HEAD entries appended by the device-side pruning rule */
     uint64_t entries_published;   /* leader: entries appended (tickets + auto HEAD entries) */
     uint64_t phase_ns[8];         /* leader profiling: ns waiting for requests, in T1..T6, and tile count */
+    uint64_t turn_ns[8];          /* worker 0: [0..2] ns waiting for the claim lock / place turn / publish turn,
+                                     [3] fast placements, [4] slow placements, [7] ns holding the place turn */
 } apus_stats_t;
 
 /* ---- library ------------------------------------------------------------------- */

@@ -60,7 +60,7 @@ def test_config_struct_matches_header(built):
     assert C.sizeof(built.Config) == 48
     assert C.sizeof(built.PeerHandle) == 128
     assert C.sizeof(built.LogOffsets) == 64
-    assert C.sizeof(built.Stats) == 144
+    assert C.sizeof(built.Stats) == 208
 
 
 def test_engine_entry_resolves_reference_proxy(built):

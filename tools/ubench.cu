@@ -35,6 +35,8 @@ __global__ void k_single(volatile uint64_t *target, uint8_t *buf, int mode, int 
         else if (mode == 9) { uint64_t v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(target + (acc & 1)) : "memory"); acc += v; }
         else if (mode == 10) { st16(buf + ((i & 63) * 512) + threadIdx.x * 16, make_uint4(i, i, i, i)); asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
         else if (mode == 11) { st16(buf + ((i & 63) * 512) + threadIdx.x * 16, make_uint4(i, i, i, i)); if (threadIdx.x == 0) asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(target + 8), "l"((uint64_t)1) : "memory"); }
+        else if (mode == 13) { acc += gt(); }
+        else if (mode == 14) { acc += clock64(); }
         else if (mode == 12) { st16(buf + ((i & 63) * 512) + threadIdx.x * 16, make_uint4(i, i, i, i)); }
     }
     uint64_t t1 = gt();
@@ -64,6 +66,38 @@ __global__ void k_ping(volatile uint64_t *my_flag, volatile uint64_t *peer_flag,
     }
     uint64_t t1 = gt();
     if (threadIdx.x == 0) out_ns[0] = t1 - t0;
+}
+
+// interference: CTA 0 measures dependent-load latency while CTAs 1..n hammer fences / stores
+__global__ void k_interfere(volatile uint64_t *target, uint8_t *buf, int mode, int iters, uint64_t *out_ns, volatile int *stop)
+{
+    if (blockIdx.x == 0) {
+        uint64_t acc = 0;
+        uint64_t t0 = gt();
+        for (int i = 0; i < iters; i++) acc += ldr(target + (acc & 1));
+        uint64_t t1 = gt();
+        if (threadIdx.x == 0) { out_ns[0] = t1 - t0 + (acc == 0xdeadbeef); *stop = 1; }
+    } else {
+        int i = 0;
+        while (!*stop) {
+            i++;
+            if (mode == 1) __threadfence_system();
+            else if (mode == 2) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            else if (mode == 3) { st16(buf + blockIdx.x * 65536 + ((i & 63) * 512) + threadIdx.x * 16, make_uint4(i, i, i, i)); }
+            else if (mode == 4) { st16(buf + blockIdx.x * 65536 + ((i & 63) * 512) + threadIdx.x * 16, make_uint4(i, i, i, i)); if ((i & 15) == 0) __threadfence_system(); }
+            else if (mode == 5) { uint64_t v; asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(target + 16) : "memory"); if (v == 12345) break; }
+        }
+    }
+}
+
+static void run_interfere(volatile uint64_t *target, uint8_t *buf, const char *name, int mode, int nblk)
+{
+    uint64_t *ns; int *stop;
+    CK(cudaMallocManaged(&ns, 8)); CK(cudaMallocManaged(&stop, 4));
+    *stop = 0;
+    k_interfere<<<nblk, 32>>>(target, buf, mode, 20000, ns, stop); CK(cudaDeviceSynchronize());
+    printf("poll local L2 while %d other CTAs %s: %.1f ns\n", nblk - 1, name, (double)ns[0] / 20000);
+    cudaFree(ns); cudaFree(stop);
 }
 
 static double run_single(volatile uint64_t *target, uint8_t *buf, int mode, int iters, int threads)
@@ -100,7 +134,16 @@ int main()
     printf("ld.acquire.sys local (dependent): "); printf("%.1f ns\n", run_single(dflag, dbuf, 9, 20000, 32));
     printf("warp 512 B local stores + fence.acq_rel.gpu: "); printf("%.1f ns\n", run_single(dflag, dbuf, 10, 20000, 32));
     printf("warp 512 B local stores + red.release.sys: "); printf("%.1f ns\n", run_single(dflag, dbuf, 11, 20000, 32));
+    printf("read %%globaltimer: "); printf("%.1f ns\n", run_single(dflag, dbuf, 13, 20000, 32));
+    printf("read clock64: "); printf("%.1f ns\n", run_single(dflag, dbuf, 14, 20000, 32));
     printf("warp 512 B local stores only (issue rate): "); printf("%.1f ns\n", run_single(dflag, dbuf, 12, 20000, 32));
+    run_interfere(dflag, dbuf, "do nothing", 0, 1);
+    run_interfere(dflag, dbuf, "loop fence.sc.sys", 1, 2);
+    run_interfere(dflag, dbuf, "loop fence.sc.sys", 1, 8);
+    run_interfere(dflag, dbuf, "loop fence.acq_rel.gpu", 2, 8);
+    run_interfere(dflag, dbuf, "stream 512 B stores", 3, 8);
+    run_interfere(dflag, dbuf, "stream stores + fence.sys every 16", 4, 8);
+    run_interfere(dflag, dbuf, "spin ld.acquire.gpu on a neighbour line", 5, 8);
     // same-GPU ping-pong between two CTAs
     for (int cfg = 0; cfg < 5; cfg++) {
         int data = cfg == 0 ? 0 : (cfg == 1 ? 128 : (cfg == 2 ? 32768 : 128)), fence = cfg == 0 ? 0 : (cfg <= 2 ? 1 : (cfg == 3 ? 2 : 3));
