@@ -275,6 +275,7 @@ static void fill_ctx(apus_replica *r, uint64_t target)
     c->n_workers = r->cfg.leader_ctas ? r->cfg.leader_ctas : 4;
     if (c->n_workers > 32) c->n_workers = 32;
     c->epoch = (uint32_t)(r->launches + 1);
+    c->doorbell_relay = (r->cfg.ring_mode == APUS_RING_HOST_MAPPED && c->n_workers >= 2) ? 1u : 0u;
     c->region = r->region;
     for (int i = 0; i < APUS_MAX_SERVER_COUNT; i++)
         c->peer[i] = (i == r->cfg.server_idx) ? NULL : (uint8_t *)r->peer_ptr[i];

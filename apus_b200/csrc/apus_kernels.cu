@@ -163,7 +163,7 @@ struct LeaderShared {
     // claim
     uint32_t n_fetch, finish;
     uint32_t avg_es, avg_xb;   // log / staged bytes per entry seen in this worker's last claim (sizes the next one)
-    uint64_t slot0, my_seq, t_dequeue, claim_next, st_head, t_place_acq;
+    uint64_t slot0, my_seq, t_dequeue, claim_next, st_head, t_place_acq, pub_h;
     // placement state while this CTA holds the place turn (mirrors apus_seq_t.p_*)
     uint64_t st_end, st_tail, st_next_idx, st_hwm, st_placed, st_auto_heads;
     uint32_t st_prev_head, pad0;
@@ -346,22 +346,38 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
     uint64_t committed = ctrl->committed;
     uint64_t committed_tickets = ctrl->committed_tickets;
     uint64_t lat_count = ctrl->lat_count;
-    uint64_t tail = ld_relaxed_sys(&seq->pub_tail);
+    uint64_t bytes_rep = ctrl->bytes_replicated, batches = ctrl->batches;
+    uint64_t tail = 0;                       // next record to commit
+    uint64_t seen = 0;                       // records [tail, seen) are valid and not committed yet
+    uint64_t published = ctrl->published;    // entries published = cum of the newest valid record
     uint64_t last_progress = globaltimer_ns();
     uint32_t spins = 0;
+    bool S_rec_ok = false;
     volatile uint64_t *peer_commit = nullptr;
     if (lane < N && lane != me && cx->peer[lane])
         peer_commit = &reinterpret_cast<apus_loghdr_t *>(cx->peer[lane] + APUS_HDR_OFF)->commit;
 
     for (;;) {
-        // lane i holds what replica i has acked (entries, monotone); the leader's own
-        // vote is everything it has published (dare_ibv_rc.c:1736 "i == idx")
-        uint64_t v = 0;
-        if (lane < N) v = (lane == me) ? ld_relaxed_sys(&ctrl->published) : ld_relaxed_sys(&ctrl->ack[lane]);
-        else if (lane == 31) v = ld_acquire_gpu(&seq->pub_head);   // polled alongside the acks: off the critical path
-        const uint64_t published_now = __shfl_sync(0xffffffffu, v, me);
-        const uint64_t head = __shfl_sync(0xffffffffu, v, 31);
-        if (lane == 31) v = 0;
+        // every lane looks at one 16 B pair of the next four publish records (lane>>3 = record, lane&7 = pair)
+        // while lanes 0..N-1 also poll the acks
+        uint64_t st = 0, rv = 0, v = 0;
+        {
+            const uint64_t rn = seen + (uint64_t)(lane >> 3);
+            ld_relaxed_sys_2x64(&ring[rn & PUBMASK].w[2 * (lane & 7)], st, rv);
+            const uint32_t okm = __ballot_sync(0xffffffffu, st == rn + 1);
+            // records are valid only in order: count the leading records whose eight pairs all match
+            uint32_t nvalid = 0;
+            while (nvalid < 4 && ((okm >> (8 * nvalid)) & 0xffu) == 0xffu) nvalid++;
+            if (nvalid) {
+                published = __shfl_sync(0xffffffffu, rv, 8 * (nvalid - 1) + PR_CUM);
+                seen += nvalid;
+            }
+            S_rec_ok = nvalid != 0;
+        }
+        if (lane < N && lane != me) v = ld_relaxed_sys(&ctrl->ack[lane]);
+        // lane i holds what replica i has acked (entries, monotone); the leader's own vote is
+        // everything it has published (dare_ibv_rc.c:1736 "i == idx")
+        if (lane == me) v = published;
         // rank: how many replicas hold at least what I hold
         int cnt = 0;
         for (int j = 0; j < N; j++) {
@@ -375,54 +391,70 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
             cand = o > cand ? o : cand;
         }
         const uint64_t Q = cand;
-        if (Q > committed) {
-            // (no acquire fence on the followers' side of things: the commit rule consumes
-            //  nothing but the ack words themselves)
-            // map the entry count to the log offset recorded at publish time
-            uint64_t off = 0, tickets = committed_tickets;
+        if (Q > committed && tail != seen) {
+            // map the entry count to the log offset recorded at publish time; the commit is a
+            // prefix and an entry boundary (invariant I3).  Four records per step.
+            uint64_t off = 0, tickets = committed_tickets, r_tail = 0, r_hwm = 0, r_next = 0;
             bool any = false;
-            while (tail != head) {
-                const apus_pubrec_t *r = &ring[tail & PUBMASK];
-                const uint64_t cum = ld_relaxed_sys(&r->cum);
-                if (cum > Q) break;
-                off = ld_relaxed_sys(&r->end);
-                tickets = ld_relaxed_sys(&r->tickets);
-                if ((cx->flags & APUS_FLAG_STATS) && cx->lat_ns && lane == 0) {
-                    const uint64_t d = globaltimer_ns() - ld_relaxed_sys(&r->t0);
-                    cx->lat_ns[lat_count & (APUS_LAT_RING - 1)] = d > 0xffffffffull ? 0xffffffffu : (uint32_t)d;
+            while (tail != seen) {
+                const uint64_t rn = tail + (uint64_t)(lane >> 3);
+                uint64_t st2 = 0, val = 0;
+                if (rn < seen) ld_relaxed_sys_2x64(&ring[rn & PUBMASK].w[2 * (lane & 7)], st2, val);
+                // how many of these (up to four, in order) are covered by the quorum count
+                const uint32_t cm = __ballot_sync(0xffffffffu, (lane & 7) == PR_CUM && rn < seen && val <= Q);
+                uint32_t nc = 0;
+                while (nc < 4 && ((cm >> (8 * nc)) & 1u)) nc++;
+                if (nc == 0) break;
+                const int base = 8 * (int)(nc - 1);
+                committed = __shfl_sync(0xffffffffu, val, base + PR_CUM);
+                off = __shfl_sync(0xffffffffu, val, base + PR_END);
+                tickets = __shfl_sync(0xffffffffu, val, base + PR_TICKETS);
+                r_tail = __shfl_sync(0xffffffffu, val, base + PR_TAIL);
+                r_hwm = __shfl_sync(0xffffffffu, val, base + PR_HWM);
+                r_next = __shfl_sync(0xffffffffu, val, base + PR_NEXTIDX);
+                for (uint32_t q = 0; q < nc; q++) {
+                    bytes_rep += __shfl_sync(0xffffffffu, val, 8 * q + PR_BYTES);
+                    const uint64_t t0 = __shfl_sync(0xffffffffu, val, 8 * q + PR_T0);
+                    if ((cx->flags & APUS_FLAG_STATS) && cx->lat_ns && lane == 0) {
+                        const uint64_t d = globaltimer_ns() - t0;
+                        cx->lat_ns[(lat_count + q) & (APUS_LAT_RING - 1)] = d > 0xffffffffull ? 0xffffffffu : (uint32_t)d;
+                    }
                 }
-                lat_count++;
-                committed = cum;
-                tail++;
+                lat_count += nc; batches += nc;
+                tail += nc;
                 any = true;
+                if (nc < 4) break;
             }
             if (any) {
-                // commit is a prefix and an entry boundary (invariant I3)
                 if (peer_commit) st_relaxed_sys(peer_commit, off);          // dare_ibv_rc.c:1810
                 if (lane == 0) {
-                    hdr->commit = off;
-                    st_relaxed_sys(&hdr->apply, off);                       // leader applies = update_state
-                    ctrl->committed = committed;
-                    ctrl->committed_tickets = tickets;
-                    ctrl->lat_count = lat_count;
                     st_relaxed_sys(&hw->commit_off, off);
                     st_relaxed_sys(&hw->committed_tickets, tickets);        // releases proxy.c:160 spinners
-                    st_release_gpu(&seq->pub_tail, tail);
+                    st_relaxed_sys(&hw->consumed, tickets);                 // submission-ring space
+                    st_relaxed_sys(&seq->pub_tail, tail);                   // publish-ring space
+                    // the leader's bookkeeping, in publish order (single writer)
+                    hdr->commit = off;
+                    st_relaxed_sys(&hdr->apply, off);                       // leader applies = update_state
+                    hdr->end = off; hdr->tail = r_tail; hdr->old_end = off;
+                    ctrl->committed = committed; ctrl->committed_tickets = tickets; ctrl->lat_count = lat_count;
+                    ctrl->published = committed; ctrl->consumed = tickets; ctrl->next_idx = r_next; ctrl->hwm = r_hwm;
+                    ctrl->bytes_replicated = bytes_rep; ctrl->batches = batches;
                 }
                 committed_tickets = tickets;
                 last_progress = globaltimer_ns();
                 __syncwarp();
             }
         }
+        const bool rec_ok = S_rec_ok;
         // exit: every worker finished and nothing is in flight
         int ex = 0;
         if (lane == 0) {
-            if (ld_acquire_gpu(&seq->workers_done) == cx->n_workers && committed == ld_relaxed_sys(&ctrl->published)) ex = 1;
-            else if ((++spins & 0x3ffu) == 0) {
+            if (!rec_ok && tail == seen && committed == published && ld_acquire_gpu(&seq->workers_done) == cx->n_workers) {
+                // one more look at the ring after the workers are known to be done
+                ex = 3;
+            } else if ((++spins & 0x3ffu) == 0) {
                 if (ld_relaxed_sys(&seq->abort_flag)) ex = 2;
-                else if (ld_relaxed_sys_u32(&hw->stop) && committed == published_now &&
-                         ld_acquire_gpu(&seq->workers_done) == cx->n_workers) ex = 2;
-                else if (globaltimer_ns() - last_progress > WATCHDOG_NS && committed != published_now &&
+                else if (globaltimer_ns() - last_progress > WATCHDOG_NS && (tail != seen || committed != published) &&
                          (cx->target != ~0ull || ld_relaxed_sys_u32(&hw->stop))) {
                     st_relaxed_sys(&hw->error, APUS_KERR_WATCHDOG_COMMIT);
                     st_relaxed_sys(&seq->abort_flag, 1);
@@ -431,6 +463,13 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
             }
         }
         ex = __shfl_sync(0xffffffffu, ex, 0);
+        if (ex == 3) {
+            // workers are done (acquire above): any record they wrote is visible now; re-check once
+            uint64_t st3 = 0, v3 = 0;
+            if (lane >= 16 && lane < 24) ld_relaxed_sys_2x64(&ring[seen & PUBMASK].w[2 * (lane - 16)], st3, v3);
+            const bool more = __ballot_sync(0xffffffffu, lane >= 16 && lane < 24 && st3 == seen + 1) == 0x00ff0000u;
+            ex = more ? 0 : 1;
+        }
         if (ex) {
             // clean end of a bounded launch: tell every follower how many entries exist, so
             // that it can leave once it has acked and applied all of them
@@ -611,20 +650,21 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
     // ---- sequencer reset handshake: worker 0 prepares the shared words of this launch ----
     if (tid == 0) {
         if (wid == 0) {
-            seq->claim_ticket = 0; seq->claim_serving = 0;
-            seq->claimed_slots = ctrl->consumed; seq->tile_seq = 0; seq->claims_closed = 0;
-            seq->place_seq = 0; seq->pub_seq = 0; seq->workers_done = 0; seq->abort_flag = 0;
-            seq->rec_placed[0] = 0; seq->rec_placed[1] = ctrl->published;
-            seq->rec_end[0] = 0; seq->rec_end[1] = hdr->end;
-            seq->rec_tail[0] = 0; seq->rec_tail[1] = hdr->tail | (ctrl->hwm == cx->log_len ? APUS_REC_WRAPPED : 0ull);
-            seq->rec_head[0] = 0; seq->rec_head[1] = hdr->head;
+            seq->claimed_slots = ctrl->consumed;
+            seq->doorbell = ctrl->consumed;
+            seq->place_seq = 0; seq->workers_done = 0; seq->abort_flag = 0;
+            for (uint32_t i = 0; i < APUS_PUBRING_RECORDS; i++)
+                for (int q = 0; q < 8; q++) pubring[i].w[2 * q] = 0;          // no valid record
+            // the turns are stamped with slot numbers: the first claim of this launch starts at ctrl->consumed
+            seq->rec_placed[0] = ctrl->consumed; seq->rec_placed[1] = ctrl->published;
+            seq->rec_end[0] = ctrl->consumed; seq->rec_end[1] = hdr->end;
+            seq->rec_tail[0] = ctrl->consumed; seq->rec_tail[1] = hdr->tail | (ctrl->hwm == cx->log_len ? APUS_REC_WRAPPED : 0ull);
+            seq->rec_head[0] = ctrl->consumed; seq->rec_head[1] = hdr->head;
             // entries published by an earlier launch but not yet committed come back as one record
             seq->pub_head = 0; seq->pub_tail = 0;
-            if (ctrl->published != ctrl->committed) {
-                pubring[0].cum = ctrl->published; pubring[0].end = hdr->end;
-                pubring[0].tickets = ctrl->consumed; pubring[0].t0 = globaltimer_ns();
-                seq->pub_head = 1;
-            }
+            seq->pub_turn[0] = ctrl->consumed; seq->pub_turn[1] = 0;
+            // (the commit warp keeps ctrl/hdr in step with what is COMMITTED; a clean launch ends with
+            //  everything committed, so there is nothing published-but-uncommitted to carry over)
             __threadfence();
             st_release_gpu(&seq->ready_epoch, cx->epoch);
         } else {
@@ -641,6 +681,18 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
 
     if (warp == N_PRODUCER_WARPS) {   // warp 15: the commit warp lives in worker 0
         if (wid == 0) leader_commit_warp(cx);
+        else if (wid == 1 && cx->doorbell_relay && lane == 0) {
+            // doorbell relay: the only poller of the host-mapped doorbell (one PCIe read in flight instead
+            // of one per idle worker -- those reads also slow every system fence down); workers poll the mirror
+            uint64_t last = ld_relaxed_sys(&seq->doorbell);
+            uint32_t spins = 0;
+            for (;;) {
+                const uint64_t t = ld_acquire_sys(cx->sub_tail);
+                if (t != last) { st_relaxed_sys(&seq->doorbell, t); last = t; }
+                if ((++spins & 0x3fu) == 0 &&
+                    (ld_relaxed_sys(&seq->abort_flag) || ld_relaxed_sys(&seq->workers_done) >= cx->n_workers)) break;
+            }
+        }
         return;
     }
 
@@ -652,22 +704,21 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
 #define PHASE(i) do { if (prof) { const uint64_t _t = globaltimer_ns(); ph[i] += _t - tprev; tprev = _t; } } while (0)
 
     for (;;) {
-        // ---- T0: claim the next slots of the submission ring (ticket lock: one poller at a time) ----
+        // ---- T0: claim the next slots of the submission ring: lock-free, one compare-and-swap on the
+        //      claimed-slots counter.  The claimed range [slot0, slot0+n) is also the worker's place in
+        //      the order: the place and publish turns are stamped with slot numbers ----
         if (tid == 0) {
             uint32_t n = 0, fin = 0, spins = 0;
             const uint64_t tw0 = prof ? globaltimer_ns() : 0;
-            const uint64_t ticket = atomicAdd(reinterpret_cast<unsigned long long *>(&seq->claim_ticket), 1ull);
-            while (ld_acquire_gpu(&seq->claim_serving) != ticket) {
-                if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
-            }
-            if (prof) { tn[0] += globaltimer_ns() - tw0; tn[6]++; }
-            if (ld_relaxed_sys(&seq->claims_closed) || ld_relaxed_sys(&seq->abort_flag)) fin = 1;
-            uint64_t claimed = ld_relaxed_sys(&seq->claimed_slots);
-            while (!fin) {
+            uint64_t claimed = 0;
+            for (;;) {
+                if (ld_relaxed_sys(&seq->abort_flag)) { fin = 1; break; }
+                claimed = ld_relaxed_sys(&seq->claimed_slots);
                 if (claimed >= cx->target) { fin = 1; break; }
-                const uint64_t t = ld_acquire_sys(cx->sub_tail);   // slots + payload were written before it
+                // slots + payload were written before the doorbell (read directly, or through the relay's mirror)
+                const uint64_t t = cx->doorbell_relay ? ld_relaxed_sys(&seq->doorbell) : ld_acquire_sys(cx->sub_tail);
                 uint64_t avail = t - claimed;
-                if (avail) {
+                if (t > claimed) {
                     const uint64_t room = cx->target - claimed;
                     if (avail > room) avail = room;
                     // share a shallow queue between the workers instead of one big tile
@@ -681,30 +732,28 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     if (axb) { const uint64_t xf = APUS_LEADER_EXT_BYTES / axb; if (xf < fit) fit = xf; }
                     if (fit < 1) fit = 1;
                     if (want > fit) want = fit;
-                    n = want > MAXB ? MAXB : (uint32_t)want;
-                    break;
+                    const uint32_t nn = want > MAXB ? MAXB : (uint32_t)want;
+                    if (atomicCAS(reinterpret_cast<unsigned long long *>(&seq->claimed_slots), (unsigned long long)claimed,
+                                  (unsigned long long)(claimed + nn)) == (unsigned long long)claimed) {
+                        n = nn;
+                        break;
+                    }
+                    continue;      // somebody else took these slots: look again
                 }
                 if ((++spins & 0xffu) == 0) {
-                    if (ld_relaxed_sys_u32(&hw->stop) || ld_relaxed_sys(&seq->abort_flag)) { fin = 1; break; }
+                    if (ld_relaxed_sys_u32(&hw->stop)) { fin = 1; break; }
                     if (cx->target != ~0ull && globaltimer_ns() - last_progress > WATCHDOG_NS) {
                         st_relaxed_sys(&hw->error, APUS_KERR_WATCHDOG_LEADER);
                         st_relaxed_sys(&seq->abort_flag, 1); fin = 1; break;
                     }
                 }
             }
-            if (fin) st_relaxed_sys(&seq->claims_closed, 1);
-            if (n) {
-                S->slot0 = claimed; S->my_seq = ld_relaxed_sys(&seq->tile_seq);
-                st_relaxed_sys(&seq->claimed_slots, claimed + n);
-                st_relaxed_sys(&seq->tile_seq, S->my_seq + 1);
-            }
+            if (prof) { tn[0] += globaltimer_ns() - tw0; tn[6]++; }
+            if (n) { S->slot0 = claimed; S->my_seq = claimed; }
             S->n_fetch = n; S->finish = fin;
             S->t_dequeue = globaltimer_ns();
-            S->claim_next = ticket + 1;
         }
         bar_sync(1, NT);
-        // the other warps start fetching while thread 0 hands the claim lock on
-        if (tid == 0) st_release_gpu(&seq->claim_serving, S->claim_next);
         if (S->finish) break;
         const uint32_t nf = S->n_fetch;
         PHASE(0);
@@ -736,7 +785,16 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             if (warp == 0) {
                 bool placed_fast = false;
                 if (!have_place_turn) {
-                    leader_prescan(cx, S, lane);
+                    if (nf == 1) {
+                        // one request in flight (closed-loop latency path): nothing to scan
+                        if (lane == 0) {
+                            S->cum_es[0] = S->es[0]; S->cum_xb[0] = S->xb[0];
+                            S->static_cut = 1; S->first_ext_all = (S->flg[0] & 1u) ? 0u : 0xffffffffu;
+                        }
+                        if (lane < N) S->ap[lane] = (lane == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[lane]);
+                    } else {
+                        leader_prescan(cx, S, lane);
+                    }
                     __syncwarp();
                     // the place turn: wait until the three stamped pairs carry my claim number.  It is held for
                     // the state-dependent offset arithmetic alone (not the fetch, not the prefix sums), and in
@@ -788,10 +846,10 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                             const uint64_t nt = b - S->es[nf - 1];
                             const bool nw = wrapped || b == L;
                             // hand the turn on at once
-                            st_relaxed_sys_2x64(seq->rec_placed, S->my_seq + 1, placed + nf);
-                            st_relaxed_sys_2x64(seq->rec_end, S->my_seq + 1, ne);
-                            st_relaxed_sys_2x64(seq->rec_tail, S->my_seq + 1, nt | (nw ? APUS_REC_WRAPPED : 0ull));
-                            st_relaxed_sys_2x64(seq->rec_head, S->my_seq + 1, headv);
+                            st_relaxed_sys_2x64(seq->rec_placed, S->my_seq + S->n_fetch, placed + nf);
+                            st_relaxed_sys_2x64(seq->rec_end, S->my_seq + S->n_fetch, ne);
+                            st_relaxed_sys_2x64(seq->rec_tail, S->my_seq + S->n_fetch, nt | (nw ? APUS_REC_WRAPPED : 0ull));
+                            st_relaxed_sys_2x64(seq->rec_head, S->my_seq + S->n_fetch, headv);
                             if (prof) { tn[7] += globaltimer_ns() - S->t_place_acq; tn[3]++; }
                             // ... and only then write down the tile for the other warps
                             const uint64_t hwm = wrapped ? L : pos0;
@@ -822,11 +880,11 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     leader_place(cx, S, sl, lane, false);
                     if (lane == 0 && S->last) {
                         // all my slots are placed: hand the placement state to the next claim
-                        st_relaxed_sys_2x64(seq->rec_placed, S->my_seq + 1, S->st_placed);
-                        st_relaxed_sys_2x64(seq->rec_end, S->my_seq + 1, S->st_end);
-                        st_relaxed_sys_2x64(seq->rec_tail, S->my_seq + 1, S->st_tail | (S->st_hwm == cx->log_len ? APUS_REC_WRAPPED : 0ull) |
+                        st_relaxed_sys_2x64(seq->rec_placed, S->my_seq + S->n_fetch, S->st_placed);
+                        st_relaxed_sys_2x64(seq->rec_end, S->my_seq + S->n_fetch, S->st_end);
+                        st_relaxed_sys_2x64(seq->rec_tail, S->my_seq + S->n_fetch, S->st_tail | (S->st_hwm == cx->log_len ? APUS_REC_WRAPPED : 0ull) |
                                                                               (S->st_prev_head ? APUS_REC_PREV_HEAD : 0ull));
-                        st_relaxed_sys_2x64(seq->rec_head, S->my_seq + 1, S->st_head);
+                        st_relaxed_sys_2x64(seq->rec_head, S->my_seq + S->n_fetch, S->st_head);
                         if (prof) tn[7] += globaltimer_ns() - S->t_place_acq;
                     }
                 }
@@ -946,11 +1004,6 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     for (int f = 0; f < N; f++)
                         if (S->peer_index[f]) S->peer_index[f][at] = w;
                 }
-                // data before tail (invariant I1): EVERY thread waits until its own stores are performed
-                // system-wide, then the barrier, then the tail.  (A single fence behind the barrier is
-                // equivalent in the PTX model, but it lets the other warps' stores drain into the next
-                // tile, where they stall the warp that holds the place turn.)
-                __threadfence_system();
             }
             bar_sync(1, NT);
             PHASE(5);
@@ -964,37 +1017,48 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             }
             if (warp == 0) {
                 const bool pubs = lane < N && lane != me && cx->peer[lane];
-                if (lane == 0 && !have_pub_turn) {
+                // data before tail (invariant I1): all data stores of the tile -> bar.sync (above) -> one system
+                // fence per publishing lane (cumulative over the barrier) -> the tail.  One fence costs 1.5 us;
+                // fencing in every warp serializes 15 of them.
+                if (pubs || lane == 0) __threadfence_system();
+                // the publish turn: {slot number, record number} in one 16 B word.  Held for the N-1 tail stores
+                // and the eight 16 B stores of the publish record -- no fence inside the turn
+                if (lane == 0) {
+                    if (!have_pub_turn) {
+                        uint32_t spins = 0;
+                        const uint64_t tw0 = prof ? globaltimer_ns() : 0;
+                        uint64_t sq, h;
+                        for (;;) {
+                            ld_relaxed_sys_2x64(seq->pub_turn, sq, h);
+                            if (sq == S->my_seq) break;
+                            if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
+                        }
+                        if (prof) tn[2] += globaltimer_ns() - tw0;
+                        S->pub_h = h;
+                    }
+                    // room in the publish ring (the commit warp drains it)
                     uint32_t spins = 0;
-                    const uint64_t tw0 = prof ? globaltimer_ns() : 0;
-                    while (ld_acquire_gpu(&seq->pub_seq) != S->my_seq) {
+                    while (S->pub_h - ld_relaxed_sys(&seq->pub_tail) >= APUS_PUBRING_RECORDS - 2) {
                         if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
                     }
-                    if (prof) tn[2] += globaltimer_ns() - tw0;
                 }
                 __syncwarp();
                 if (pubs) {
                     apus_ctrl_t *pc = reinterpret_cast<apus_ctrl_t *>(cx->peer[lane]);
                     st_relaxed_sys_2x64(&pc->pub_end, S->new_end, S->cum_after);
                 }
+                if (lane >= 16 && lane < 24) {
+                    const int q = lane - 16;
+                    const uint64_t h = S->pub_h;
+                    const uint64_t val = q == PR_CUM ? S->cum_after : q == PR_END ? S->new_end : q == PR_TICKETS ? S->slot0 + kbase + m
+                                       : q == PR_T0 ? S->t_dequeue : q == PR_TAIL ? S->tail_after : q == PR_HWM ? S->hwm_after
+                                       : q == PR_NEXTIDX ? S->idx0 + m + autoh : (b - a + gap_bytes) * (uint64_t)(N - 1);
+                    st_relaxed_sys_2x64(&pubring[h & PUBMASK].w[2 * q], h + 1, val);
+                }
+                __syncwarp();
                 if (lane == 0) {
-                    const uint64_t consumed = S->slot0 + kbase + m;
-                    hdr->end = S->new_end; hdr->tail = S->tail_after; hdr->old_end = S->new_end;
-                    ctrl->next_idx = S->idx0 + m + autoh; ctrl->consumed = consumed;
-                    ctrl->hwm = S->hwm_after;
-                    ctrl->bytes_replicated += (b - a + gap_bytes) * (uint64_t)(N - 1);   // a gap skipped before it counts too
-                    ctrl->batches += 1;
-                    const uint64_t h = ld_relaxed_sys(&seq->pub_head);
-                    uint32_t spins = 0;
-                    while (h - ld_acquire_gpu(&seq->pub_tail) >= APUS_PUBRING_RECORDS - 2) {   // commit warp drains
-                        if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
-                    }
-                    apus_pubrec_t *r = &pubring[h & PUBMASK];
-                    r->cum = S->cum_after; r->end = S->new_end; r->tickets = consumed; r->t0 = S->t_dequeue;
-                    st_relaxed_sys(&ctrl->published, S->cum_after);
-                    st_release_gpu(&seq->pub_head, h + 1);
-                    st_relaxed_sys(&hw->consumed, consumed);
-                    if (S->last) st_release_gpu(&seq->pub_seq, S->my_seq + 1);
+                    S->pub_h += 1;
+                    if (S->last) st_relaxed_sys_2x64(seq->pub_turn, S->my_seq + S->n_fetch, S->pub_h);
                     S->kbase = kbase + m;
                 }
             }

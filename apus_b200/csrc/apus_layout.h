@@ -45,7 +45,7 @@
 #define APUS_LOGHDR_BYTES     (320u * 1024u)
 #define APUS_SEQ_OFF          4096u
 #define APUS_PUBRING_OFF      8192u
-#define APUS_PUBRING_RECORDS  1024u                   /* 32 B each; power of two */
+#define APUS_PUBRING_RECORDS  256u                    /* 128 B each; power of two */
 #define APUS_HDR_OFF          65536u
 #define APUS_INDEX_OFF        (APUS_HDR_OFF + APUS_LOGHDR_BYTES)
 #define APUS_IDX_HEAD_FLAG    0x80000000u             /* index word: the entry is a HEAD entry */
@@ -107,18 +107,14 @@ typedef struct apus_ctrl {
 } apus_ctrl_t;
 
 /* Sequencer shared by the leader's worker CTAs (device memory, gpu-scope atomics).
- * A worker CLAIMS the next slots of the submission ring (ticket lock: one poller at a
- * time), builds its tile in parallel with the others, but PLACES it in the log and
- * PUBLISHES its tail strictly in claim order -- log order == submission order. */
+ * A worker CLAIMS the next slots of the submission ring (one compare-and-swap), builds its
+ * tile in parallel with the others, but PLACES it in the log and PUBLISHES its tail strictly
+ * in slot order -- log order == submission order.  The turns are stamped with slot numbers. */
 typedef struct apus_seq {
-    uint64_t claim_ticket;   uint64_t pad_a[15];
-    uint64_t claim_serving;  uint64_t pad_b[15];
-    uint64_t claimed_slots;      /* slots handed to workers so far (>= ctrl.consumed) */
-    uint64_t tile_seq;           /* claims with work handed out */
-    uint64_t claims_closed;      /* target reached or stop requested: no more claims */
-    uint64_t pad_c[13];
+    uint64_t claimed_slots;      /* slots handed to workers so far (>= ctrl.consumed); compare-and-swap */
+    uint64_t pad_c[15];
     uint64_t place_seq;      uint64_t pad_d[15];   /* next claim allowed to place */
-    uint64_t pub_seq;        uint64_t pad_e[15];   /* next claim allowed to publish */
+    uint64_t pub_turn[2];    uint64_t pad_e[14];   /* {next claim allowed to publish, next record number}: one 16 B word */
     uint64_t pub_head;       uint64_t pad_f[15];   /* publish ring: next record written */
     uint64_t pub_tail;       uint64_t pad_g[15];   /* ... next record the commit warp reads */
     uint64_t workers_done;
@@ -135,16 +131,26 @@ typedef struct apus_seq {
     uint64_t rec_head[2];        /* {stamp, head offset} (only the turn holder moves the head) */
     uint64_t avg_es, avg_xb;     /* log / staged bytes per entry of the latest claim (sizes the next claims;
                                     kept across launches) */
-    uint64_t pad_i[6];
+    uint64_t doorbell;           /* device-memory mirror of a host-mapped doorbell, kept by ONE relay warp so that
+                                    idle workers do not all poll over PCIe */
+    uint64_t pad_i[5];
 } apus_seq_t;
 #define APUS_REC_PREV_HEAD (1ull << 62)   /* the last placed entry is a HEAD entry of the pruning rule */
 #define APUS_REC_WRAPPED   (1ull << 63)   /* the ring has wrapped at least once (no fresh bytes left) */
 
+/* One record per published tile, consumed in order by the commit warp.  Eight 16 B {stamp, value}
+ * pairs, each written with one 16 B store (stamp = record number + 1): a record is valid when all
+ * eight stamps match, no fence needed.  The commit warp also does the leader's bookkeeping from it. */
+#define PR_CUM     0   /* entries published up to and including this tile */
+#define PR_END     1   /* `end` after this tile */
+#define PR_TICKETS 2   /* tickets consumed up to and including this tile */
+#define PR_T0      3   /* dequeue timestamp (ns) */
+#define PR_TAIL    4   /* offset of the last entry */
+#define PR_HWM     5   /* high-water mark of bytes ever written */
+#define PR_NEXTIDX 6   /* idx of the next entry */
+#define PR_BYTES   7   /* bytes replicated by this tile, summed over followers */
 typedef struct apus_pubrec {
-    uint64_t cum;                /* entries published up to and including this tile */
-    uint64_t end;                /* `end` after this tile */
-    uint64_t tickets;            /* tickets consumed up to and including this tile */
-    uint64_t t0;                 /* dequeue timestamp (ns) */
+    uint64_t w[16];
 } apus_pubrec_t;
 
 /* submission slot, 128 B: the fields of tailq_entry_t (message.h:11-17).  Requests
@@ -201,6 +207,8 @@ typedef struct apus_devctx {
     uint32_t pad_i;
     uint64_t target;                      /* cumulative ticket / entry target of this launch */
     uint32_t n_workers;                   /* leader CTAs of this launch */
+    uint32_t doorbell_relay;              /* 1: workers poll seq.doorbell, a relay warp polls the host word */
+    uint32_t pad_r;
     uint32_t epoch;                       /* launch counter (sequencer reset handshake) */
     uint8_t *region;                      /* own region */
     uint8_t *peer[APUS_MAX_SERVERS];      /* peers' regions as mapped here (NULL = absent) */
