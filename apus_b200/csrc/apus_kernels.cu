@@ -155,6 +155,7 @@ struct LeaderShared {
     uint32_t rel[MAXB];        // entry start - sub-tile start (bytes)
     uint32_t xoff[MAXB];       // offset of the entry's image in the ext staging
     uint64_t ap[32];           // apply offsets of the replicas, read ahead of the place turn
+    uint32_t ap_valid;         // ap[] was read for this claim
     uint32_t static_cut;       // first k > 0 whose payload image restarted the payload ring (else n_fetch)
     uint32_t first_ext_all;    // first entry with an external payload image (else 0xffffffff)
     uint64_t idx_base;         // idx of an entry = idx_base + its 1-based position in the placement order
@@ -163,7 +164,7 @@ struct LeaderShared {
     // claim
     uint32_t n_fetch, finish;
     uint32_t avg_es, avg_xb;   // log / staged bytes per entry seen in this worker's last claim (sizes the next one)
-    uint64_t slot0, my_seq, t_dequeue, claim_next, st_head, t_place_acq, pub_h;
+    uint64_t slot0, my_seq, t_dequeue, claim_next, st_head, t_place_acq, pub_h, pub_tail_seen;
     // placement state while this CTA holds the place turn (mirrors apus_seq_t.p_*)
     uint64_t st_end, st_tail, st_next_idx, st_hwm, st_placed, st_auto_heads;
     uint32_t st_prev_head, pad0;
@@ -670,7 +671,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
         } else {
             while (ld_acquire_gpu(&seq->ready_epoch) != cx->epoch) { }
         }
-        S->finish = 0; S->avg_es = 128; S->avg_xb = 0;
+        S->finish = 0; S->avg_es = 128; S->avg_xb = 0; S->pub_tail_seen = 0; S->ap_valid = 0;
         S->idx_base = ctrl->next_idx - 1 - ctrl->published;
         for (int i = 0; i < APUS_MAX_SERVERS; i++) {
             S->peer_entries[i] = (i < N && i != me && cx->peer[i]) ? cx->peer[i] + cx->entries_off : nullptr;
@@ -791,9 +792,10 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                             S->cum_es[0] = S->es[0]; S->cum_xb[0] = S->xb[0];
                             S->static_cut = 1; S->first_ext_all = (S->flg[0] & 1u) ? 0u : 0xffffffffu;
                         }
-                        if (lane < N) S->ap[lane] = (lane == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[lane]);
+                        S->ap_valid = 0;          // apply offsets are read only if the pruning rule could be due
                     } else {
                         leader_prescan(cx, S, lane);
+                        if (lane == 0) S->ap_valid = 1;
                     }
                     __syncwarp();
                     // the place turn: wait until the three stamped pairs carry my claim number.  It is held for
@@ -803,6 +805,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         uint32_t spins = 0;
                         const uint64_t tw0 = prof ? globaltimer_ns() : 0;
                         uint64_t s0, s1, s2, s3, placed, end, tf, headv;
+                        const uint64_t hh = ld_relaxed_sys(&hdr->head);     // in flight together with the record
                         for (;;) {
                             ld_relaxed_sys_2x64(seq->rec_placed, s0, placed);
                             ld_relaxed_sys_2x64(seq->rec_end, s1, end);
@@ -817,10 +820,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         const uint64_t tail = tf & ~(APUS_REC_WRAPPED | APUS_REC_PREV_HEAD);
                         // ---- fast path ----
                         // a host control plane may also move the head (apus_set_head): take the newer of the two
-                        {
-                            const uint64_t hh = ld_relaxed_sys(&hdr->head);
-                            if (end != L && ring_dist(hh, end, L) < ring_dist(headv, end, L)) headv = hh;
-                        }
+                        if (end != L && ring_dist(hh, end, L) < ring_dist(headv, end, L)) headv = hh;
                         S->st_head = headv;
                         const uint64_t pos0 = (end == L) ? 0 : end;
                         const uint64_t used = (end == L) ? 0 : ring_dist(headv, end, L);
@@ -830,6 +830,11 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         // is the pruning rule due?  (scalar version of the test in leader_place)
                         bool prune_due = false;
                         if (autoprune && end != L && used >= (L >> 2) && !prevh && L - pos0 >= APUS_HDR_BYTES) {
+                            if (!S->ap_valid) {
+                                for (int i = 0; i < cx->group_size; i++)
+                                    S->ap[i] = (i == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[i]);
+                                S->ap_valid = 1;
+                            }
                             uint64_t d = 0;
                             for (int i = 0; i < cx->group_size; i++) {
                                 uint64_t di = ring_dist(S->ap[i], end, L);
@@ -877,6 +882,12 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     placed_fast = S->fast != 0;
                 }
                 if (!placed_fast) {
+                    if (!S->ap_valid) {
+                        if (lane < N) S->ap[lane] = (lane == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[lane]);
+                        __syncwarp();
+                        if (lane == 0) S->ap_valid = 1;
+                        __syncwarp();
+                    }
                     leader_place(cx, S, sl, lane, false);
                     if (lane == 0 && S->last) {
                         // all my slots are placed: hand the placement state to the next claim
@@ -1020,7 +1031,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                 // data before tail (invariant I1): all data stores of the tile -> bar.sync (above) -> one system
                 // fence per publishing lane (cumulative over the barrier) -> the tail.  One fence costs 1.5 us;
                 // fencing in every warp serializes 15 of them.
-                if (pubs || lane == 0) __threadfence_system();
+                if (pubs) __threadfence_system();
                 // the publish turn: {slot number, record number} in one 16 B word.  Held for the N-1 tail stores
                 // and the eight 16 B stores of the publish record -- no fence inside the turn
                 if (lane == 0) {
@@ -1036,9 +1047,11 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         if (prof) tn[2] += globaltimer_ns() - tw0;
                         S->pub_h = h;
                     }
-                    // room in the publish ring (the commit warp drains it)
+                    // room in the publish ring (the commit warp drains it); the tail is re-read only when the
+                    // last value seen would not leave room
                     uint32_t spins = 0;
-                    while (S->pub_h - ld_relaxed_sys(&seq->pub_tail) >= APUS_PUBRING_RECORDS - 2) {
+                    while (S->pub_h - S->pub_tail_seen >= APUS_PUBRING_RECORDS - 2) {
+                        S->pub_tail_seen = ld_relaxed_sys(&seq->pub_tail);
                         if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
                     }
                 }
