@@ -164,14 +164,14 @@ struct LeaderShared {
     // claim
     uint32_t n_fetch, finish;
     uint32_t avg_es, avg_xb;   // log / staged bytes per entry seen in this worker's last claim (sizes the next one)
-    uint64_t slot0, my_seq, t_dequeue, claim_next, st_head, t_place_acq, pub_h, pub_tail_seen;
+    uint64_t slot0, my_seq, t_dequeue, st_head, t_place_acq, pub_h, pub_tail_seen;
     // placement state while this CTA holds the place turn (mirrors apus_seq_t.p_*)
-    uint64_t st_end, st_tail, st_next_idx, st_hwm, st_placed, st_auto_heads;
+    uint64_t st_end, st_tail, st_next_idx, st_hwm, st_placed;
     uint32_t st_prev_head, pad0;
     // current sub-tile
     uint32_t kbase, m, gap, ghost, fresh, auto_head, ext_bytes, last, blocked, hbytes;
     uint32_t base_es, base_xb, fast, pad1;
-    uint64_t ext_base, auto_head_val, a, b, idx0, cum_after, new_end, tail_after, hwm_after, auto_heads_after;
+    uint64_t ext_base, auto_head_val, a, b, idx0, cum_after, new_end, tail_after, hwm_after;
     uint8_t  *peer_entries[APUS_MAX_SERVERS];
     uint32_t *peer_index[APUS_MAX_SERVERS];
 };

@@ -82,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -121,8 +121,8 @@ class ClockSampler:
 
 def ncu_traffic(n, payload, batch):
     """dram__bytes_read.sum + dram__bytes_write.sum of the replica kernel per launch, from the committed
-    `ncu --set full` capture (profiles/r1_ncu_v3.json); only valid for the configuration it was taken on."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_v3.json")
+    `ncu --set full` capture (profiles/r1_ncu_v5.json); only valid for the configuration it was taken on."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_v5.json")
     try:
         d = json.load(open(p))
         if n == 5 and payload == 64 and batch == 65536:
@@ -486,7 +486,7 @@ def run_ours(args):
         "roofline": {"bound": bound, "achieved": round(ach, 3), "peak": peak, "unit": "GB/s",
                      "frac": round(ach / peak, 6),
                      "traffic": (ncu_traffic(n, payload, batch) if world == 1 and not args.spread else None),
-                     "traffic_note": "bytes per launch (dram read+write), profiles/r1_ncu_v3.json; algorithmic bytes per launch = "
+                     "traffic_note": "bytes per launch (dram read+write), profiles/r1_ncu_v5.json; algorithmic bytes per launch = "
                                      f"{alg_bytes_per_op * batch}",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_op": alg_bytes_per_op,
