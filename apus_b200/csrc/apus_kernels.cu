@@ -519,8 +519,7 @@ __device__ __noinline__ void leader_prescan(const apus_devctx_t *__restrict__ cx
 // T2b (inside the place turn): place the next sub-tile of the fetched batch (entries kbase..nf) --
 // log_append_entry's offset rules, free-space rule E2 and the pruning rule, on the placement
 // state this CTA holds.  Kept short: everything state independent was done by leader_prescan.
-__device__ __noinline__ void leader_place(const apus_devctx_t *__restrict__ cx, LeaderShared *S, const apus_slot_t *sl, int lane,
-                                          const bool dry)
+__device__ __noinline__ void leader_place(const apus_devctx_t *__restrict__ cx, LeaderShared *S, const apus_slot_t *sl, int lane)
 {
     const int N = cx->group_size;
     apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_HDR_OFF);
@@ -609,7 +608,7 @@ __device__ __noinline__ void leader_place(const apus_devctx_t *__restrict__ cx, 
         S->fresh = (a >= S->st_hwm) ? 1u : 0u;
         if (!S->blocked) {
             // commit the placement to the state this CTA carries
-            if (autoh && !dry) st_relaxed_sys(&hdr->head, new_head);
+            if (autoh) st_relaxed_sys(&hdr->head, new_head);
             if (autoh) S->st_head = new_head;
             if (S->gap) {
                 S->st_end = 0; S->st_hwm = L;
@@ -622,7 +621,7 @@ __device__ __noinline__ void leader_place(const apus_devctx_t *__restrict__ cx, 
                 S->st_next_idx += m + autoh;
                 S->st_placed += m + autoh;
                 S->cum_after = S->st_placed;
-                if (autoh && !dry) atomicAdd(reinterpret_cast<unsigned long long *>(&reinterpret_cast<apus_ctrl_t *>(cx->region)->auto_heads), 1ull);
+                if (autoh) atomicAdd(reinterpret_cast<unsigned long long *>(&reinterpret_cast<apus_ctrl_t *>(cx->region)->auto_heads), 1ull);
                 S->st_prev_head = (autoh && m == 0) ? 1u : 0u;         // never two HEAD entries in a row (dare_log.h:477-480)
                 if (b > S->st_hwm) S->st_hwm = b;
                 S->last = (kbase + m == nf) ? 1u : 0u;
@@ -888,7 +887,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         if (lane == 0) S->ap_valid = 1;
                         __syncwarp();
                     }
-                    leader_place(cx, S, sl, lane, false);
+                    leader_place(cx, S, sl, lane);
                     if (lane == 0 && S->last) {
                         // all my slots are placed: hand the placement state to the next claim
                         st_relaxed_sys_2x64(seq->rec_placed, S->my_seq + S->n_fetch, S->st_placed);

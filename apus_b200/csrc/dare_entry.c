@@ -10,6 +10,7 @@
  */
 #define _GNU_SOURCE
 #include <errno.h>
+#include <execinfo.h>
 #include <signal.h>
 #include <stdlib.h>
 #include <string.h>
@@ -83,6 +84,36 @@ static int rendezvous(const char *dir, const apus_peer_handle_t *mine, apus_peer
         }
     }
     return 0;
+}
+
+/* apus_segv_trace=1: print a backtrace on SIGSEGV/SIGBUS/SIGABRT before dying (the host application may
+ * install its own handler later; this one covers the engine's start-up inside an LD_PRELOADed process) */
+static void segv_trace(int sig)
+{
+    void *bt[64];
+    int n = backtrace(bt, 64);
+    static const char msg[] = "apus: fatal signal in an engine-hosting process, backtrace:\n";
+    if (write(2, msg, sizeof msg - 1) < 0) { }
+    backtrace_symbols_fd(bt, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+/* The engine's own environment variables are read ONCE, when the library is loaded (before the application's
+ * main()): the DARE thread must not call getenv() -- the hosting application may rewrite environ concurrently
+ * (redis-server's setproctitle does: clearenv + setenv at the top of main), and getenv() racing with that
+ * crashes.  The reference reads its variables in proxy.c:33-58 on the main thread for the same reason. */
+static int g_env_gpu = -1, g_env_leader = 0;
+static unsigned long long g_env_log_size;
+static char g_env_rdv[256];
+__attribute__((constructor)) static void engine_env_init(void)
+{
+    const char *s;
+    if ((s = getenv("apus_gpu"))) g_env_gpu = atoi(s);
+    if ((s = getenv("apus_leader"))) g_env_leader = atoi(s);
+    if ((s = getenv("apus_log_size"))) g_env_log_size = strtoull(s, NULL, 0);
+    if ((s = getenv("apus_rendezvous"))) snprintf(g_env_rdv, sizeof g_env_rdv, "%s", s);
+    else snprintf(g_env_rdv, sizeof g_env_rdv, "/tmp/apus-rdv-%u", (unsigned)getuid());
+    if (getenv("apus_segv_trace")) { signal(SIGSEGV, segv_trace); signal(SIGBUS, segv_trace); signal(SIGABRT, segv_trace); }
 }
 
 static int csm_like(uint8_t type) { return !(type == APUS_NOOP || type == APUS_CONFIG || type == APUS_HEAD); }
@@ -189,8 +220,11 @@ void *dare_server_init(void *arg)
     signal(SIGINT, int_handler);                       /* dare_server.c:186-187 */
 
     g_idx = g_in.server_idx; g_n = g_in.group_size;
-    const char *s;
-    g_leader_idx = (s = getenv("apus_leader")) ? (uint8_t)atoi(s) : 0;
+    /* this thread is created from the interposer's init hook, microseconds before the application's main();
+     * let main()'s first instructions (redis: setproctitle rewriting environ) pass before the CUDA runtime
+     * starts reading the environment on this thread */
+    usleep(10000);
+    g_leader_idx = (uint8_t)g_env_leader;
     if (g_in.srv_type != SRV_TYPE_START) { LOGT("server_type=join is not supported by the GPU engine yet\n"); return NULL; }
     if (g_n < 1 || g_n > APUS_MAX_SERVER_COUNT || g_idx >= g_n) { LOGT("bad group_size/server_idx\n"); return NULL; }
 
@@ -199,19 +233,17 @@ void *dare_server_init(void *arg)
     cfg.struct_size = sizeof cfg;
     int ndev = apus_device_count();
     if (ndev < 1) { LOGT("no CUDA device: the engine has no CPU fallback\n"); return NULL; }
-    cfg.device = (s = getenv("apus_gpu")) ? atoi(s) : (int)(g_idx % (unsigned)ndev);
+    cfg.device = g_env_gpu >= 0 ? g_env_gpu : (int)(g_idx % (unsigned)ndev);
     cfg.server_idx = g_idx; cfg.group_size = g_n; cfg.leader_idx = g_leader_idx;
     cfg.ring_mode = APUS_RING_HOST_MAPPED;
     cfg.flags = APUS_F_EXPLICIT | APUS_F_DEVICE_STATS | APUS_F_AUTOPRUNE;
     cfg.term = 1;                                      /* term of a clean first election */
-    cfg.log_size = (s = getenv("apus_log_size")) ? strtoull(s, NULL, 0) : 0;
+    cfg.log_size = g_env_log_size;
     cfg.leader_ctas = 2;
     if (apus_replica_create(&cfg, &g_rep) != APUS_OK) { LOGT("apus_replica_create: %s\n", apus_last_error()); return NULL; }
 
     apus_peer_handle_t mine, all[APUS_MAX_SERVER_COUNT];
-    char dir[256];
-    if ((s = getenv("apus_rendezvous"))) snprintf(dir, sizeof dir, "%s", s);
-    else snprintf(dir, sizeof dir, "/tmp/apus-rdv-%u", (unsigned)getuid());
+    const char *dir = g_env_rdv;
     if (apus_replica_export(g_rep, &mine) != APUS_OK || rendezvous(dir, &mine, all)) {
         LOGT("peer rendezvous failed in %s\n", dir); dare_server_shutdown();
     }

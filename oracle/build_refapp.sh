@@ -1,0 +1,45 @@
+#!/bin/bash
+# oracle/build_refapp.sh -- TEST INFRASTRUCTURE ONLY (drop-in test of SURVEY.md s8f row N2).
+#
+# Builds, from the tarballs and sources where they lie under $REF (nothing is copied into the repository):
+#   oracle/_ref/redis-server, redis-benchmark, redis-cli   apps/redis/redis-2.8.17.tar.gz   (apps/redis/mk)
+#   libconfig 1.4.9, BerkeleyDB 5.1.29 (static)             utils/dep-lib/*.tar.gz           (utils/mk)
+#   oracle/_ref/interpose.so = the reference's UNMODIFIED src/spec_hooks.cpp, src/proxy/proxy.c,
+#       src/db/db-interface.c, src/config-comp/config-proxy.c, linked per INTEGRATION.md section 2:
+#       libapus_dare.so + libapus_gpu.so in place of libdare.a -lev -libverbs (target/makefile:19).
+# Scratch goes to oracle/_ref/build and is removed at the end; oracle/_ref is git-ignored and travels to the GPU box.
+set -e
+REF=${REF:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+OUT=$HERE/_ref
+ENGINE=$(cd "$HERE/../apus_b200" && pwd)
+J=${J:-8}
+if [ ! -f "$REF/apps/redis/redis-2.8.17.tar.gz" ]; then
+  echo "reference tree absent: keeping prebuilt oracle/_ref application binaries (if any)"; exit 0
+fi
+if [ -x "$OUT/redis-server" ] && [ -f "$OUT/interpose.so" ] && [ "$OUT/interpose.so" -nt "$REF/src/proxy/proxy.c" ] \
+   && [ -z "$FORCE" ]; then
+  echo "oracle/_ref application binaries up to date"; exit 0
+fi
+B=$OUT/build
+rm -rf "$B"; mkdir -p "$B"; cd "$B"
+tar xzf "$REF/apps/redis/redis-2.8.17.tar.gz"
+make -C redis-2.8.17 -j$J MALLOC=libc > redis.log 2>&1
+cp redis-2.8.17/src/redis-server redis-2.8.17/src/redis-benchmark redis-2.8.17/src/redis-cli "$OUT/"
+tar xzf "$REF/utils/dep-lib/libconfig-1.4.9.tar.gz"
+(cd libconfig-1.4.9 && ./configure --disable-shared --disable-cxx --with-pic > ../libconfig.log 2>&1 \
+   && make -j$J >> ../libconfig.log 2>&1)
+tar xzf "$REF/utils/dep-lib/db-5.1.29.tar.gz"
+(cd db-5.1.29/build_unix && ../dist/configure --disable-shared --with-pic --disable-cxx --disable-java --disable-tcl \
+   --disable-replication > ../../bdb.log 2>&1 && make -j$J libdb.a >> ../../bdb.log 2>&1)
+INC="-I$HERE/ref_stubs -I$REF/src/include -I$REF/src -I$B/libconfig-1.4.9/lib -I$B/db-5.1.29/build_unix"
+CF="-fPIC -rdynamic -O0 -g -w -fcommon -DDEBUG=0"          # the flags of target/src/*/subdir.mk (+ -fcommon)
+gcc $CF -std=gnu99 $INC -c "$REF/src/proxy/proxy.c" -o proxy.o
+gcc $CF -std=gnu99 $INC -c "$REF/src/db/db-interface.c" -o db-interface.o
+gcc $CF -std=gnu99 $INC -c "$REF/src/config-comp/config-proxy.c" -o config-proxy.o
+g++ -fPIC -rdynamic -O0 -g -w -I"$REF/src" -c "$REF/src/spec_hooks.cpp" -o spec_hooks.o
+g++ -shared -Wl,-soname,interpose.so -o "$OUT/interpose.so" spec_hooks.o proxy.o db-interface.o config-proxy.o \
+    libconfig-1.4.9/lib/.libs/libconfig.a db-5.1.29/build_unix/libdb.a \
+    -L"$ENGINE" -lapus_dare -lapus_gpu -Wl,-rpath,'$ORIGIN/../../apus_b200' -lpthread -ldl -lm
+cd "$OUT"; rm -rf "$B"
+echo "built oracle/_ref/{redis-server,redis-benchmark,redis-cli,interpose.so}"

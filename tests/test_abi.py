@@ -81,3 +81,41 @@ def test_engine_entry_resolves_reference_proxy(built):
             "assert d.is_leader()==0; print('ok')")
     r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+def test_reference_interposer_links_on_engine_and_refuses_without_gpu(built, tmp_path):
+    """oracle/_ref/interpose.so = the reference's unmodified spec_hooks.cpp + proxy.c + db-interface.c +
+    config-proxy.c (vendored libconfig, BerkeleyDB) linked on libapus_dare.so/libapus_gpu.so
+    (oracle/build_refapp.sh): every symbol resolves, and an unmodified redis-server
+    started the way benchmarks/run.sh:26 starts it reaches dare_server_init, which -- on a box without a GPU --
+    refuses loudly instead of falling back to a CPU path (the app then simply runs unreplicated)."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    inter, server = os.path.join(ref, "interpose.so"), os.path.join(ref, "redis-server")
+    if not (os.path.exists(inter) and os.path.exists(server)):
+        pytest.skip("oracle/_ref application binaries absent (oracle/build_refapp.sh needs /root/reference)")
+    out = subprocess.run(["ldd", "-r", inter], capture_output=True, text=True)
+    assert "undefined symbol" not in out.stdout + out.stderr, out.stdout + out.stderr
+    assert "libapus_dare.so" in out.stdout and "libapus_gpu.so" in out.stdout
+    assert "libibverbs" not in out.stdout and "libev." not in out.stdout
+    if built.lib().apus_device_count() > 0:
+        return                                        # with a GPU the full run is tests/test_gpu_redis_dropin.py
+    cfg = tmp_path / "node.cfg"
+    cfg.write_text('db_name = "node_test";\nreq_log = 0;\nip_address = "127.0.0.1";\nport = 18870;\n')
+    env = dict(os.environ, server_type="start", server_idx="0", group_size="1", config_path=str(cfg),
+               dare_log_file=str(tmp_path / "dare.log"), LD_PRELOAD=inter)
+    p = subprocess.Popen([server, "--port", "18870", "--save", "", "--bind", "127.0.0.1"], cwd=tmp_path, env=env,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    try:
+        import time
+        log = ""
+        for _ in range(100):
+            time.sleep(0.1)
+            if (tmp_path / "dare.log").exists():
+                log = (tmp_path / "dare.log").read_text()
+                if "no CPU fallback" in log:
+                    break
+        assert "no CUDA device: the engine has no CPU fallback" in log, log
+        assert p.poll() is None                       # the application itself keeps running
+    finally:
+        p.kill()
+        p.wait(timeout=10)

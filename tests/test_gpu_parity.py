@@ -132,6 +132,35 @@ def test_default_log_size_64MiB(eng, orc):
     run_and_compare(eng, orc, 3, 0 or O.LOG_SIZE, S.uniform_stream(3000, 4096, conns=2))
 
 
+def test_full_size_parity_run_2pow18_x_64B(eng, orc):
+    """The parity run of SURVEY.md s8d at full size: 2^18 requests of 64 B behind the CONFIG prologue,
+    32 MiB of the reference's 64 MiB ring at 5 replicas, every byte of every replica against the oracle."""
+    n, L = 5, O.LOG_SIZE
+    nreq = 1 << 18
+    rng = np.random.default_rng(0xA5A50040)
+    payloads = rng.integers(0, 256, size=nreq * 64, dtype=np.uint8)
+    orc.set_rules(O.RULES_ENGINE)
+    c = O.Cluster(orc, n, leader=0, term=1, length=L)
+    c.prologue()
+    c.submit(S.CONNECT, 0, 1, O.cmd_image(b""))
+    pb = payloads.tobytes()
+    for i in range(nreq):
+        assert c.submit(S.SEND, 0, 2 + i, O.cmd_image(pb[64 * i:64 * i + 64]))
+        if i % 4096 == 4095:
+            c.round()
+    c.round(); c.round()
+    with eng.Group(n, devices=devices_for(eng, n), log_size=L, ring_mode=eng.RING_DEVICE, ring_slots=1 << 19,
+                   ring_bytes=1 << 20) as g:
+        g.prologue()
+        g.submit(S.CONNECT, 0, 1, b"")
+        g.submit_uniform(nreq, 64, 0, 2, payloads)
+        g.run(timeout_ms=120_000)
+        EU.compare_group_to_oracle(g, c, exact=True)
+        assert g.leader.committed() == nreq + 2
+        assert g.leader.stats()["bytes_replicated"] == c.bytes_replicated() == (n - 1) * (128 * nreq + 128)
+    c.close()
+
+
 def test_exact_fit_wrap_rule_E1(eng, orc):
     """An entry that ends exactly at len: the engine stores end = 0 (divergence E1; the
     reference's end == len would read as "log empty", SURVEY.md H11 iv)."""
@@ -207,6 +236,12 @@ def test_wrap_laps_with_pruning(eng, orc, n, L, seed, mode):
         EU.compare_group_to_oracle(g, c, exact=True)
         assert g.leader.committed() == total
         assert c.offsets(0)["head"] != 0
+        # every follower adopted the head carried by the last committed HEAD entry
+        # (poll_config_entries, dare_server.c:2163-2186)
+        lh = g.leader.offsets()["head"]
+        assert lh == c.offsets(0)["head"]
+        for r in g.replicas[1:]:
+            assert r.offsets()["head"] == lh
     c.close()
 
 
