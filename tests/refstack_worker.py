@@ -134,7 +134,15 @@ def main():
                       pct_us={str(q): allat[min(len(allat) - 1, int(len(allat) * q / 100))] / 1e3
                               for q in (10, 25, 50, 75, 90, 95, 99, 99.9)} if allat else {},
                       max_us=allat[-1] / 1e3 if allat else 0.0)
-        o = offsets()
+        # quiescence: the prune timer may still append one HEAD entry (never two in a row, dare_log.h:472-478)
+        quiet = max(0.25, 5 * float(os.environ.get("REFSTACK_PRUNE", "0.05"))) if float(os.environ.get("REFSTACK_PRUNE", "0.05")) < 10 else 0.25
+        last, since = None, time.time()
+        while time.time() - since < quiet:
+            o = offsets()
+            cur = (o["end"], o["commit"], o["apply"])
+            if cur != last or not (o["end"] == o["commit"] == o["apply"]):
+                last, since = cur, time.time()
+            time.sleep(0.005)
         with open(done_file + ".tmp", "w") as f:
             json.dump({"end": o["end"], "term": o["term"]}, f)
         os.rename(done_file + ".tmp", done_file)
