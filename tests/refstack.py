@@ -47,13 +47,16 @@ def expected_stream(leader, nconn, nreq, plen):
     return out
 
 
-def run(n, nconn, nreq, plen, threads=1, prune=None, timeout=120, keep=None):
+def run(n, nconn, nreq, plen, threads=1, prune=None, timeout=120, keep=None, steps=1, images=True):
     """Returns dict(leader, term, results[i], images[i] (np.uint8 arrays of entries[0..end)), logs[i])."""
     d = keep or tempfile.mkdtemp(prefix="apus-refstack-")
     os.makedirs(d, exist_ok=True)
     env = dict(os.environ)
     if prune is not None:
         env["REFSTACK_PRUNE"] = str(prune)
+    env["REFSTACK_STEPS"] = str(steps)
+    if not images:
+        env["REFSTACK_NO_IMAGE"] = "1"
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "refstack_worker.py"), str(i), str(n), str(nconn),
                                str(nreq), str(plen), d, str(threads)], env=env, stdout=subprocess.PIPE,
                               stderr=subprocess.STDOUT) for i in range(n)]
@@ -73,7 +76,8 @@ def run(n, nconn, nreq, plen, threads=1, prune=None, timeout=120, keep=None):
         if not os.path.exists(path):
             raise RuntimeError(f"reference replica {i} produced no result:\n{outs[i][-1500:]}\n{logs[i][-1500:]}")
         res.append(json.load(open(path)))
-        imgs.append(np.fromfile(os.path.join(d, f"image{i}.bin"), dtype=np.uint8))
+        ip = os.path.join(d, f"image{i}.bin")
+        imgs.append(np.fromfile(ip, dtype=np.uint8) if os.path.exists(ip) else None)
     leaders = [r["idx"] for r in res if r["leader"]]
     if len(leaders) != 1:
         raise RuntimeError(f"expected one leader, got {leaders}:\n" + "\n".join(l[-800:] for l in logs))

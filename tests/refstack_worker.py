@@ -124,16 +124,20 @@ def main():
         secs = C.c_double(0.0)
         st.refstack_drive.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_double)]
-        rc = st.refstack_drive(proxy, nthreads, nconn, nreq, plen, lat, C.byref(secs))   # spec_hooks.cpp:116-174
-        assert rc == 0
-        dt = secs.value
-        allat = sorted(int(x) for x in lat[:nreq])
-        result.update(seconds=dt, requests=nreq, threads=nthreads, ops_per_s=(nreq + 2 * nconn) / dt if dt > 0 else 0.0,
-                      p50_us=allat[len(allat) // 2] / 1e3 if allat else 0.0,
-                      p99_us=allat[int(len(allat) * 0.99)] / 1e3 if allat else 0.0,
-                      pct_us={str(q): allat[min(len(allat) - 1, int(len(allat) * q / 100))] / 1e3
-                              for q in (10, 25, 50, 75, 90, 95, 99, 99.9)} if allat else {},
-                      max_us=allat[-1] / 1e3 if allat else 0.0)
+        steps = []
+        for _ in range(int(os.environ.get("REFSTACK_STEPS", "1"))):       # bench.py: warm-up + timed steps, same group
+            rc = st.refstack_drive(proxy, nthreads, nconn, nreq, plen, lat, C.byref(secs))   # spec_hooks.cpp:116-174
+            assert rc == 0
+            dt = secs.value
+            allat = sorted(int(x) for x in lat[:nreq])
+            steps.append(dict(seconds=dt, requests=nreq, threads=nthreads, ops_per_s=(nreq + 2 * nconn) / dt if dt > 0 else 0.0,
+                              p50_us=allat[len(allat) // 2] / 1e3 if allat else 0.0,
+                              p99_us=allat[int(len(allat) * 0.99)] / 1e3 if allat else 0.0,
+                              pct_us={str(q): allat[min(len(allat) - 1, int(len(allat) * q / 100))] / 1e3
+                                      for q in (10, 25, 50, 75, 90, 95, 99, 99.9)} if allat else {},
+                              max_us=allat[-1] / 1e3 if allat else 0.0))
+        result.update(steps[-1])
+        result["steps"] = steps
         # quiescence: the prune timer may still append one HEAD entry (never two in a row, dare_log.h:472-478)
         quiet = max(0.25, 5 * float(os.environ.get("REFSTACK_PRUNE", "0.05"))) if float(os.environ.get("REFSTACK_PRUNE", "0.05")) < 10 else 0.25
         last, since = None, time.time()
@@ -161,7 +165,7 @@ def main():
     time.sleep(0.2)
     o = offsets() or {}
     result["offsets"] = o
-    if o:
+    if o and not os.environ.get("REFSTACK_NO_IMAGE"):
         end = o["end"] if o["end"] != o["len"] else 0
         img = C.create_string_buffer(max(end, 1))
         if end:

@@ -43,7 +43,7 @@ def check_replay(rr, nconn, nreq, plen):
             assert sorted(r["replay"]["sha"]) == sorted(want)
 
 
-@pytest.mark.parametrize("n,nconn,nreq,plen", [(3, 2, 300, 64), (5, 3, 200, 128), (3, 1, 120, -3000)])
+@pytest.mark.parametrize("n,nconn,nreq,plen", [(3, 2, 300, 64), (5, 3, 200, 128), (3, 1, 120, -3000), (7, 4, 400, 64)])
 def test_reference_log_equals_oracle_log(orc, n, nconn, nreq, plen):
     """log_pruning_period is set out of reach, so the log holds exactly CONFIG + the stream."""
     rr = R.run(n, nconn, nreq, plen, prune=1000.0)
