@@ -372,3 +372,36 @@ def test_sustained_autoprune_many_laps(eng, n, L, payload):
         # followers adopted a head carried by a committed HEAD entry
         for i in range(1, n):
             assert g.replicas[i].offsets()["head"] != 0
+
+
+# ---- golden vectors produced by the RUNNING reference (tests/golden/gen_refstack_golden.py) -----------------------
+REFGOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refstack_golden.json")
+
+
+def _refgold():
+    with open(REFGOLD) as f:
+        return json.load(f)["scenarios"]
+
+
+@pytest.mark.parametrize("gold", _refgold(), ids=lambda g: g["name"])
+def test_engine_reproduces_reference_run(eng, gold):
+    """The logs the reference's own replicas held after its unmodified election / replication / commit code ran the
+    scenario (leader index and term as its election produced them; SHA-256, followers under the H5 reply mask):
+    the CUDA engine, led by the same replica in the same term, must leave the same bytes."""
+    import refstack as R
+    n, lead, end = gold["n"], gold["leader"], gold["end"]
+    with eng.Group(n, devices=devices_for(eng, n), leader=lead, term=gold["term"], log_size=O.LOG_SIZE) as g:
+        g.prologue()
+        g.submit_stream(R.expected_stream(lead, gold["nconn"], gold["nreq"], gold["plen"]))
+        g.run()
+        ents = O.walk_entries(g.leader.image(0, end), 0, end, O.LOG_SIZE)
+        assert len(ents) == gold["entries"] == g.leader.committed()
+        for i in range(n):
+            o = g.replicas[i].offsets()
+            assert {k: o[k] for k in ("head", "apply", "commit", "end")} == gold["offsets"][i], (i, o)
+            img = g.replicas[i].image(0, end)
+            if i != lead:
+                for off, _ in ents:
+                    assert img[off + 28 + i] == 1            # I7: the follower's own ack byte
+                img = O.mask_replies(img, ents)
+            assert hashlib.sha256(img.tobytes()).hexdigest() == gold["sha256"][i], f"replica {i}"
