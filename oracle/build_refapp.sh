@@ -24,7 +24,7 @@ if [ ! -f "$REF/apps/redis/redis-2.8.17.tar.gz" ]; then
 fi
 if [ -x "$OUT/redis-server" ] && [ -f "$OUT/interpose.so" ] && [ "$OUT/interpose.so" -nt "$REF/src/proxy/proxy.c" ] \
    && [ -f "$OUT/libref_stack.so" ] && [ "$OUT/libref_stack.so" -nt "$HERE/verbs_shim/verbs_shim.c" ] \
-   && [ "$OUT/libref_stack.so" -nt "$HERE/ref_stack_access.c" ] && [ -z "$FORCE" ]; then
+   && [ "$OUT/libref_stack.so" -nt "$HERE/ref_stack_access.c" ] && [ -f "$OUT/interpose_ref.so" ] && [ -z "$FORCE" ]; then
   echo "oracle/_ref application binaries up to date"; exit 0
 fi
 B=$OUT/build
@@ -62,5 +62,9 @@ gcc -fPIC -O2 -g -std=gnu99 -Wall -I"$HERE/verbs_shim" -c "$HERE/verbs_shim/verb
 gcc -fPIC -O0 -g -std=gnu99 -w -fcommon $DINC -c "$HERE/ref_stack_access.c" -o stack/ref_stack_access.o
 gcc -shared -o "$OUT/libref_stack.so" stack/*.o db-interface.o config-proxy.o \
     libev-4.15/.libs/libev.a libconfig-1.4.9/lib/.libs/libconfig.a db-5.1.29/build_unix/libdb.a -lpthread -lm
+# the reference's interposer on the reference's OWN stack (shim NIC): the CPU-side counterpart of interpose.so, used to
+# run the same redis drop-in scenario against the reference itself (tests/test_refstack_redis.py)
+g++ -shared -Wl,-soname,interpose.so -o "$OUT/interpose_ref.so" spec_hooks.o stack/*.o db-interface.o config-proxy.o \
+    libev-4.15/.libs/libev.a libconfig-1.4.9/lib/.libs/libconfig.a db-5.1.29/build_unix/libdb.a -lpthread -ldl -lm
 cd "$OUT"; rm -rf "$B"
-echo "built oracle/_ref/{redis-server,redis-benchmark,redis-cli,interpose.so,libref_stack.so}"
+echo "built oracle/_ref/{redis-server,redis-benchmark,redis-cli,interpose.so,interpose_ref.so,libref_stack.so}"

@@ -1,0 +1,20 @@
+"""The redis drop-in scenario of tests/test_gpu_redis_dropin.py against the REFERENCE ITSELF: unmodified redis-servers
+under the reference's unmodified interposer linked on the reference's own src/dare stack (oracle/_ref/interpose_ref.so,
+verbs shim NIC).  It shows what the scenario's pass criteria mean on the original system -- whoever the election makes
+leader takes redis-benchmark's SETs and an ordered RPUSH/INCR stream, the followers converge to the same
+DEBUG DIGEST -- and gives the reference-side number for BASELINE config 3.  CPU only."""
+import os
+
+import pytest
+
+import redis_group as RG
+
+pytestmark = [pytest.mark.timeout(300)]
+
+
+@pytest.mark.parametrize("n", [3])
+def test_redis_replicated_through_reference_stack(n):
+    for f in (RG.SERVER, RG.BENCH, RG.CLI, RG.INTERPOSE_REF):
+        if not os.path.exists(f):
+            pytest.skip(f"{f} absent (built only where /root/reference exists: oracle/build_refapp.sh)")
+    print(RG.run_redis_group(n, 0, 3000, 300, stack="refstack", base_port=18860, startup_timeout=60))

@@ -2,7 +2,7 @@
 import os, sys, traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import test_gpu_redis_dropin as T
+import redis_group as T
 import apus_b200
 ndev = apus_b200.lib().apus_device_count()
 for name, kw in (("simultaneous", {}), ("staggered 5s", dict(stagger=5.0)), ("followers first", dict(stagger=5.0, order=[2, 1, 0]))):
