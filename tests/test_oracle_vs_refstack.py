@@ -143,3 +143,27 @@ def test_reference_reply_bytes_invariant_I7():
             else:
                 assert rep[i] == 1 and rep[lead] == 0
             assert img[off + 27] == lead          # sender stamped before replication (dare_server.c:1803)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_reference_log_equals_oracle_log_random_shapes(orc, seed):
+    """Group size, connection count, request count and payload regime drawn from a seeded generator."""
+    rng = np.random.default_rng(0xA5A5 + seed)
+    n = int(rng.choice([3, 5]))
+    nconn = int(rng.integers(1, 7))
+    nreq = int(rng.integers(50, 500))
+    plen = int(rng.choice([1, 17, 64, 255, 1024, -200, -1500, -9000]))
+    rr = R.run(n, nconn, nreq, plen, prune=1000.0)
+    c = oracle_for(orc, rr, n, nconn, nreq, plen)
+    lead = rr["leader"]
+    end = c.offsets(lead)["end"]
+    ents = O.walk_entries(c.image(lead, 0, end), 0, end, O.LOG_SIZE)
+    assert len(ents) == 1 + 2 * nconn + nreq
+    for i in range(n):
+        assert rr["results"][i]["offsets"]["end"] == end, (n, nconn, nreq, plen)
+        img, want = rr["images"][i], c.image(i, 0, end)
+        if i != lead:
+            img, want = O.mask_replies(img, ents), O.mask_replies(want, ents)
+        assert np.array_equal(img, want), (i, lead, n, nconn, nreq, plen)
+    check_replay(rr, nconn, nreq, plen)
+    c.close()
