@@ -24,7 +24,7 @@ if [ ! -f "$REF/apps/redis/redis-2.8.17.tar.gz" ]; then
 fi
 if [ -x "$OUT/redis-server" ] && [ -f "$OUT/interpose.so" ] && [ "$OUT/interpose.so" -nt "$REF/src/proxy/proxy.c" ] \
    && [ -f "$OUT/libref_stack.so" ] && [ "$OUT/libref_stack.so" -nt "$HERE/verbs_shim/verbs_shim.c" ] \
-   && [ "$OUT/libref_stack.so" -nt "$HERE/ref_stack_access.c" ] && [ -f "$OUT/interpose_ref.so" ] && [ -z "$FORCE" ]; then
+   && [ "$OUT/libref_stack.so" -nt "$HERE/ref_stack_access.c" ] && [ -f "$OUT/interpose_ref.so" ] && [ -f "$OUT/libref_stack_O2.so" ] && [ -z "$FORCE" ]; then
   echo "oracle/_ref application binaries up to date"; exit 0
 fi
 B=$OUT/build
@@ -49,22 +49,32 @@ g++ -fPIC -rdynamic -O0 -g -w -I"$REF/src" -c "$REF/src/spec_hooks.cpp" -o spec_
 g++ -shared -Wl,-soname,interpose.so -o "$OUT/interpose.so" spec_hooks.o proxy.o db-interface.o config-proxy.o \
     libconfig-1.4.9/lib/.libs/libconfig.a db-5.1.29/build_unix/libdb.a \
     -L"$ENGINE" -lapus_dare -lapus_gpu -Wl,-rpath,'$ORIGIN/../../apus_b200' -lpthread -ldl -lm
-# the complete reference stack on the verbs shim; flags of target/src/dare/subdir.mk (+ -fcommon, -g)
+# the complete reference stack on the verbs shim; flags of target/src/dare/subdir.mk (+ -fcommon, -g): -O0 as the
+# reference builds, and a second time with -O2 ("build twice") -> libref_stack_O2.so
 DINC="-I$REF/src/include/dare -I$REF/utils/rbtree/include -I$HERE/verbs_shim -I$B/libev-4.15"
-mkdir -p stack
-for f in "$REF"/src/dare/*.c "$REF"/utils/rbtree/src/*.c; do
-  gcc -fPIC -rdynamic -std=gnu99 -O0 -g -w -fcommon $DINC -c "$f" -o "stack/$(basename "$f" .c).o"
-done
 SINC="-I$B/libev-4.15 -I$HERE/verbs_shim -I$REF/src/include -I$REF/src -I$B/libconfig-1.4.9/lib -I$B/db-5.1.29/build_unix"
-gcc $CF -std=gnu99 $SINC -c "$REF/src/proxy/proxy.c" -o stack/proxy.o
-gcc $CF -std=gnu99 $SINC -c "$REF/src/config-comp/config-dare.c" -o stack/config-dare.o
-gcc -fPIC -O2 -g -std=gnu99 -Wall -I"$HERE/verbs_shim" -c "$HERE/verbs_shim/verbs_shim.c" -o stack/verbs_shim.o
-gcc -fPIC -O0 -g -std=gnu99 -w -fcommon $DINC -c "$HERE/ref_stack_access.c" -o stack/ref_stack_access.o
-gcc -shared -o "$OUT/libref_stack.so" stack/*.o db-interface.o config-proxy.o \
+for OPT in O0 O2; do
+  S=stack; [ $OPT = O2 ] && S=stack_O2
+  mkdir -p $S
+  for f in "$REF"/src/dare/*.c "$REF"/utils/rbtree/src/*.c; do
+    gcc -fPIC -rdynamic -std=gnu99 -$OPT -g -w -fcommon $DINC -c "$f" -o "$S/$(basename "$f" .c).o"
+  done
+  # proxy.c stays at -O0 in both: its commit wait `while (cur_rec > proxy->highest_rec);` (proxy.c:160) reads a plain
+  # field another thread updates; at -O2 the load is hoisted and the application thread never wakes up
+  gcc -fPIC -rdynamic -O0 -g -w -fcommon -DDEBUG=0 -std=gnu99 $SINC -c "$REF/src/proxy/proxy.c" -o $S/proxy.o
+  gcc -fPIC -rdynamic -$OPT -g -w -fcommon -DDEBUG=0 -std=gnu99 $SINC -c "$REF/src/config-comp/config-dare.c" -o $S/config-dare.o
+  gcc -fPIC -rdynamic -$OPT -g -w -fcommon -DDEBUG=0 -std=gnu99 $INC -c "$REF/src/db/db-interface.c" -o $S/db-interface.o
+  gcc -fPIC -rdynamic -$OPT -g -w -fcommon -DDEBUG=0 -std=gnu99 $INC -c "$REF/src/config-comp/config-proxy.c" -o $S/config-proxy.o
+  gcc -fPIC -O2 -g -std=gnu99 -Wall -I"$HERE/verbs_shim" -c "$HERE/verbs_shim/verbs_shim.c" -o $S/verbs_shim.o
+  gcc -fPIC -$OPT -g -std=gnu99 -w -fcommon $DINC -c "$HERE/ref_stack_access.c" -o $S/ref_stack_access.o
+done
+gcc -shared -o "$OUT/libref_stack.so" stack/*.o \
+    libev-4.15/.libs/libev.a libconfig-1.4.9/lib/.libs/libconfig.a db-5.1.29/build_unix/libdb.a -lpthread -lm
+gcc -shared -o "$OUT/libref_stack_O2.so" stack_O2/*.o \
     libev-4.15/.libs/libev.a libconfig-1.4.9/lib/.libs/libconfig.a db-5.1.29/build_unix/libdb.a -lpthread -lm
 # the reference's interposer on the reference's OWN stack (shim NIC): the CPU-side counterpart of interpose.so, used to
 # run the same redis drop-in scenario against the reference itself (tests/test_refstack_redis.py)
-g++ -shared -Wl,-soname,interpose.so -o "$OUT/interpose_ref.so" spec_hooks.o stack/*.o db-interface.o config-proxy.o \
+g++ -shared -Wl,-soname,interpose.so -o "$OUT/interpose_ref.so" spec_hooks.o stack/*.o \
     libev-4.15/.libs/libev.a libconfig-1.4.9/lib/.libs/libconfig.a db-5.1.29/build_unix/libdb.a -lpthread -ldl -lm
 cd "$OUT"; rm -rf "$B"
-echo "built oracle/_ref/{redis-server,redis-benchmark,redis-cli,interpose.so,interpose_ref.so,libref_stack.so}"
+echo "built oracle/_ref/{redis-server,redis-benchmark,redis-cli,interpose.so,interpose_ref.so,libref_stack.so,libref_stack_O2.so}"

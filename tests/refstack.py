@@ -47,7 +47,7 @@ def expected_stream(leader, nconn, nreq, plen):
     return out
 
 
-def run(n, nconn, nreq, plen, threads=1, prune=None, timeout=120, keep=None, steps=1, images=True):
+def run(n, nconn, nreq, plen, threads=1, prune=None, timeout=120, keep=None, steps=1, images=True, lib=None):
     """Returns dict(leader, term, results[i], images[i] (np.uint8 arrays of entries[0..end)), logs[i])."""
     d = keep or tempfile.mkdtemp(prefix="apus-refstack-")
     os.makedirs(d, exist_ok=True)
@@ -55,6 +55,8 @@ def run(n, nconn, nreq, plen, threads=1, prune=None, timeout=120, keep=None, ste
     if prune is not None:
         env["REFSTACK_PRUNE"] = str(prune)
     env["REFSTACK_STEPS"] = str(steps)
+    if lib:
+        env["REFSTACK_LIB"] = lib                    # e.g. "libref_stack_O2.so": the same sources built with -O2
     if not images:
         env["REFSTACK_NO_IMAGE"] = "1"
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "refstack_worker.py"), str(i), str(n), str(nconn),

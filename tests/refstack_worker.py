@@ -22,7 +22,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-STACK = os.path.join(ROOT, "oracle", "_ref", "libref_stack.so")
+STACK = os.path.join(ROOT, "oracle", "_ref", os.environ.get("REFSTACK_LIB", "libref_stack.so"))
 
 CFG = """db_name = "node_test{idx}";
 req_log = 0;
