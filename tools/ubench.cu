@@ -68,6 +68,49 @@ __global__ void k_ping(volatile uint64_t *my_flag, volatile uint64_t *peer_flag,
     if (threadIdx.x == 0) out_ns[0] = t1 - t0;
 }
 
+
+// self-certifying replication experiment (round-2 design): the writer stores a 128 B entry with
+// eight relaxed 16 B stores and then a certificate word {seq, checksum} with a relaxed 8 B store -- NO fence between
+// them.  The reader polls the certificate, loads the entry, recomputes the checksum and retries until it matches
+// (a torn read = data still in flight), then acks.  Reports the round trip and how many torn reads were seen.
+__device__ __forceinline__ uint32_t mix4(uint4 v) { return (v.x * 0x9E3779B1u) ^ (v.y * 0x85EBCA77u) ^ (v.z * 0xC2B2AE3Du) ^ (v.w * 0x27D4EB2Fu); }
+__device__ __forceinline__ uint4 ld16(const uint8_t *p) { uint4 v; asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); return v; }
+__global__ void k_selfcert(volatile uint64_t *my_flag, volatile uint64_t *peer_cert, uint8_t *peer_ring, volatile uint64_t *my_cert, uint8_t *my_ring,
+                           volatile uint64_t *peer_flag, int iters, int writer, uint64_t *out)
+{
+    const int lane = threadIdx.x & 31;
+    uint64_t t0 = gt(), torn = 0;
+    for (int i = 1; i <= iters; i++) {
+        uint8_t *slot_w = peer_ring + (size_t)(i & 255) * 128, *slot_r = my_ring + (size_t)(i & 255) * 128;
+        if (writer) {
+            uint4 v = make_uint4(i * 7 + lane, i ^ (lane << 8), i + 0x1234567, lane * 0x01010101u + i);
+            uint32_t h = lane < 8 ? mix4(v) : 0;
+            if (lane < 8) st16(slot_w + lane * 16, v);
+            for (int s = 4; s > 0; s >>= 1) h ^= __shfl_xor_sync(0xffffffffu, h, s);
+            if (lane == 0) {
+                str(peer_cert, ((uint64_t)h << 32) | (uint32_t)i);           // relaxed, no fence
+                while (ldr(my_flag) < (uint64_t)i) ;
+            }
+            __syncwarp();
+        } else {
+            uint64_t c;
+            do { c = ldr(my_cert); } while ((uint32_t)c != (uint32_t)i);
+            for (;;) {
+                uint4 v = lane < 8 ? ld16(slot_r + lane * 16) : make_uint4(0, 0, 0, 0);
+                uint32_t h = lane < 8 ? mix4(v) : 0;
+                for (int s = 4; s > 0; s >>= 1) h ^= __shfl_xor_sync(0xffffffffu, h, s);
+                h = __shfl_sync(0xffffffffu, h, 0);
+                if (h == (uint32_t)(c >> 32)) break;
+                torn++;
+            }
+            if (lane == 0) str(peer_flag, i);
+            __syncwarp();
+        }
+    }
+    uint64_t t1 = gt();
+    if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = torn; }
+}
+
 // interference: CTA 0 measures dependent-load latency while CTAs 1..n hammer fences / stores
 __global__ void k_interfere(volatile uint64_t *target, uint8_t *buf, int mode, int iters, uint64_t *out_ns, volatile int *stop)
 {
@@ -157,6 +200,17 @@ int main()
         printf("same-GPU ping-pong, %d B data, fence=%d: %.1f ns round trip\n", data, fence, (double)ns[0] / iters);
         cudaFree(ns);
     }
+    {   // self-certifying writes, two CTAs of one GPU
+        uint8_t *ring; uint64_t *w; CK(cudaMalloc(&ring, 256 * 128)); CK(cudaMalloc(&w, 4096)); CK(cudaMemset(w, 0, 4096)); CK(cudaMemset(ring, 0, 256 * 128));
+        uint64_t *o; CK(cudaMallocManaged(&o, 64)); memset(o, 0, 64);
+        cudaStream_t s1, s2; CK(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        int iters = 20000;
+        // w[0] = writer's ack flag, w[64] = certificate word (reader side)
+        k_selfcert<<<1, 32, 0, s1>>>(w, w + 64, ring, nullptr, nullptr, nullptr, iters, 1, o);
+        k_selfcert<<<1, 32, 0, s2>>>(nullptr, nullptr, nullptr, w + 64, ring, w, iters, 0, o + 2);
+        CK(cudaDeviceSynchronize());
+        printf("same-GPU self-certifying 128 B entry (no fence): %.1f ns round trip, %llu torn reads in %d\n", (double)o[0] / iters, (unsigned long long)o[3], iters);
+    }
     if (ndev >= 2) {
         int can = 0; CK(cudaDeviceCanAccessPeer(&can, 0, 1));
         printf("peer access 0->1: %d\n", can);
@@ -183,6 +237,17 @@ int main()
                 CK(cudaSetDevice(0)); CK(cudaDeviceSynchronize()); CK(cudaSetDevice(1)); CK(cudaDeviceSynchronize());
                 printf("NVLink ping-pong GPU0<->GPU1, %d B data, fence=%d: %.1f ns round trip\n", data, fence, (double)ns[0] / iters);
                 cudaFree(ns);
+            }
+            {   // self-certifying writes over NVLink: writer on GPU 0, entry ring + certificate in GPU 1's memory, ack flag in GPU 0's
+                uint8_t *ring1; uint64_t *w1, *w0; uint64_t *o; CK(cudaMallocManaged(&o, 64)); memset(o, 0, 64);
+                CK(cudaSetDevice(1)); CK(cudaMalloc(&ring1, 256 * 128)); CK(cudaMalloc(&w1, 4096)); CK(cudaMemset(w1, 0, 4096)); CK(cudaMemset(ring1, 0, 256 * 128)); CK(cudaDeviceSynchronize());
+                CK(cudaSetDevice(0)); CK(cudaMalloc(&w0, 4096)); CK(cudaMemset(w0, 0, 4096)); CK(cudaDeviceSynchronize());
+                int iters = 10000;
+                CK(cudaSetDevice(1)); k_selfcert<<<1, 32>>>(nullptr, nullptr, nullptr, w1, ring1, w0, iters, 0, o + 2);
+                CK(cudaSetDevice(0)); k_selfcert<<<1, 32>>>(w0, w1, ring1, nullptr, nullptr, nullptr, iters, 1, o);
+                CK(cudaSetDevice(0)); CK(cudaDeviceSynchronize()); CK(cudaSetDevice(1)); CK(cudaDeviceSynchronize());
+                printf("NVLink self-certifying 128 B entry (no fence) GPU0->GPU1, ack back: %.1f ns round trip, %llu torn reads in %d\n",
+                       (double)o[0] / iters, (unsigned long long)o[3], iters);
             }
         }
     }
