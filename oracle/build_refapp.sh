@@ -24,7 +24,7 @@ if [ ! -f "$REF/apps/redis/redis-2.8.17.tar.gz" ]; then
 fi
 if [ -x "$OUT/redis-server" ] && [ -f "$OUT/interpose.so" ] && [ "$OUT/interpose.so" -nt "$REF/src/proxy/proxy.c" ] \
    && [ -f "$OUT/libref_stack.so" ] && [ "$OUT/libref_stack.so" -nt "$HERE/verbs_shim/verbs_shim.c" ] \
-   && [ "$OUT/libref_stack.so" -nt "$HERE/ref_stack_access.c" ] && [ -f "$OUT/interpose_ref.so" ] && [ -f "$OUT/libref_stack_O2.so" ] && [ -z "$FORCE" ]; then
+   && [ "$OUT/libref_stack.so" -nt "$HERE/ref_stack_access.c" ] && [ "$OUT/libref_stack.so" -nt "$HERE/ref_stack_proxy_access.c" ] && [ -f "$OUT/interpose_ref.so" ] && [ -f "$OUT/libref_stack_O2.so" ] && [ -z "$FORCE" ]; then
   echo "oracle/_ref application binaries up to date"; exit 0
 fi
 B=$OUT/build
@@ -67,6 +67,7 @@ for OPT in O0 O2; do
   gcc -fPIC -rdynamic -$OPT -g -w -fcommon -DDEBUG=0 -std=gnu99 $INC -c "$REF/src/config-comp/config-proxy.c" -o $S/config-proxy.o
   gcc -fPIC -O2 -g -std=gnu99 -Wall -I"$HERE/verbs_shim" -c "$HERE/verbs_shim/verbs_shim.c" -o $S/verbs_shim.o
   gcc -fPIC -$OPT -g -std=gnu99 -w -fcommon $DINC -c "$HERE/ref_stack_access.c" -o $S/ref_stack_access.o
+  gcc -fPIC -$OPT -g -std=gnu99 -w -fcommon $SINC -c "$HERE/ref_stack_proxy_access.c" -o $S/ref_stack_proxy_access.o
 done
 gcc -shared -o "$OUT/libref_stack.so" stack/*.o \
     libev-4.15/.libs/libev.a libconfig-1.4.9/lib/.libs/libconfig.a db-5.1.29/build_unix/libdb.a -lpthread -lm

@@ -36,6 +36,7 @@ int refstack_log_read(uint64_t off, uint64_t n, void *dst)
 }
 
 int refstack_is_leader(void) { return refstack_ready() && is_leader(); }
+
 int refstack_group_size(void) { return refstack_ready() ? (int)SRV->config.cid.size[0] : 0; }
 
 /* ---- application-side driver: what src/spec_hooks.cpp does around an application's socket calls ------------------

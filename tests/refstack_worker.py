@@ -172,6 +172,13 @@ def main():
             st.refstack_log_read(0, end, img)
         with open(os.path.join(outdir, f"image{idx}.bin"), "wb") as f:
             f.write(img.raw[:end])
+    st.refstack_highest_rec.restype = C.c_uint64
+    st.refstack_highest_rec.argtypes = [C.c_void_p]
+    st.refstack_cur_rec.restype = C.c_uint64
+    st.refstack_cur_rec.argtypes = [C.c_void_p]
+    st.refstack_records_len.restype = C.c_uint32
+    result["proxy"] = {"highest_rec": int(st.refstack_highest_rec(proxy)), "cur_rec": int(st.refstack_cur_rec(proxy)),
+                       "records_len": int(st.refstack_records_len())}
     with lock:
         result["replay"] = {"conns": len(received), "bytes": sum(v[0] for v in received.values()),
                             "sha": sorted(v[1].hexdigest() for v in received.values())}

@@ -72,6 +72,13 @@ def test_reference_log_equals_oracle_log(orc, n, nconn, nreq, plen):
                                  f"first at {int(dd[0])}: reference {img[dd[0]]} oracle {want[dd[0]]}")
     if n > 1:
         check_replay(rr, nconn, nreq, plen)
+    # what proxy.c / db-interface.c counted (the callbacks the engine entry must reproduce):
+    # store_cmd once per entry on every replica -- 4 B records for CONNECT/CLOSE, 24 B for SEND whatever its payload;
+    # update_state once per committed request on the leader
+    for r in rr["results"]:
+        assert r["proxy"]["records_len"] == 8 * nconn + 24 * nreq, r["proxy"]
+        if r["leader"]:
+            assert r["proxy"]["highest_rec"] == r["proxy"]["cur_rec"] == 2 * nconn + nreq
     c.close()
 
 
