@@ -196,7 +196,7 @@ def refstack_leg(n, payload, nreq, steps, timeout=600):
     application threads through proxy_on_accept/read/close.  Returns (per-step dicts, cores, threads) or None when
     the stack cannot run here (library absent, or the box forbids process_vm_writev)."""
     import refstack as R
-    if not R.available():
+    if not R.available() or n < 2:        # a group of one never holds an election in the reference (it waits for joins)
         return None
     cores = host_cores()
     threads = max(1, min(REFSTACK_CONNS, cores - n))
