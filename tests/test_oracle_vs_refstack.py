@@ -174,3 +174,51 @@ def test_reference_log_equals_oracle_log_random_shapes(orc, seed):
         assert np.array_equal(img, want), (i, lead, n, nconn, nreq, plen)
     check_replay(rr, nconn, nreq, plen)
     c.close()
+
+
+def test_reference_log_with_concurrent_application_threads(orc):
+    """Four application threads (memcached-style) race into proxy.c's admission lock, so the global order is whatever
+    the lock produced.  The order is read back from the reference's log, the oracle replays exactly that order and
+    must produce the same bytes; per connection the requests are all there, in order, with consecutive req_ids
+    (proxy.c:121-133), and followers replay each connection's stream in order."""
+    n, nconn, nreq, plen, threads = 3, 8, 800, 96, 4
+    rr = R.run(n, nconn, nreq, plen, threads=threads, prune=1000.0)
+    lead = rr["leader"]
+    img = rr["images"][lead]
+    end = rr["results"][lead]["offsets"]["end"]
+    ents = O.walk_entries(img, 0, end, O.LOG_SIZE)
+    assert len(ents) == 1 + 2 * nconn + nreq
+    orc.set_rules(O.RULES_REFERENCE)
+    c = O.Cluster(orc, n, leader=lead, term=rr["term"], length=O.LOG_SIZE)
+    c.prologue()
+    seen = {}
+    for off, stride in ents[1:]:
+        typ = int(img[off + 26])
+        clt = int(img[off + 24]) | (int(img[off + 25]) << 8)
+        rid = int(np.frombuffer(img[off + 16: off + 24].tobytes(), dtype="<u8")[0])
+        ln = int(img[off + 48]) | (int(img[off + 49]) << 8)
+        payload = img[off + 50: off + 50 + ln].tobytes()
+        assert (clt >> 8) == lead
+        assert rid == seen.get(clt, 0) + 1, "req_ids of one connection are consecutive, in log order"
+        seen[clt] = rid
+        if typ == S.SEND:
+            assert ln == plen and payload[1] == (payload[0] + 1) & 0xFF
+        assert c.submit(typ, clt, rid, O.cmd_image(payload))
+    c.round(); c.round()
+    assert len(seen) == nconn and sum(seen.values()) == 2 * nconn + nreq
+    for i in range(n):
+        got, want = rr["images"][i], c.image(i, 0, end)
+        if i != lead:
+            got, want = O.mask_replies(got, ents), O.mask_replies(want, ents)
+        assert np.array_equal(got, want), i
+    # followers: every connection's byte stream arrived in order
+    want_sha = {}
+    for off, stride in ents[1:]:
+        if int(img[off + 26]) == S.SEND:
+            clt = int(img[off + 24]) | (int(img[off + 25]) << 8)
+            ln = int(img[off + 48]) | (int(img[off + 49]) << 8)
+            want_sha.setdefault(clt, hashlib.sha256()).update(img[off + 50: off + 50 + ln].tobytes())
+    for r in rr["results"]:
+        if not r["leader"]:
+            assert sorted(r["replay"]["sha"]) == sorted(h.hexdigest() for h in want_sha.values())
+    c.close()
