@@ -10,6 +10,9 @@
  * bytes, and there is no CPU fallback.
  */
 #include <cuda_runtime.h>
+#include <emmintrin.h>
+#include <pthread.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -89,7 +92,10 @@ struct apus_replica {
     uint64_t    *sub_tail_dev;    /* device doorbell (device mode) */
     uint64_t    *sub_tail_stage;  /* pinned staging word for the device doorbell */
     uint32_t ring_slots, ring_bytes;
-    uint64_t submitted, flushed;
+    uint64_t submitted, flushed;  /* tickets handed out / tickets whose slots the device can read */
+    uint64_t belled;              /* doorbell value the kernel has been given */
+    uint8_t *stage;               /* pinned bounce buffer for log reads */
+    size_t   stage_bytes;
     uint64_t pay_head;            /* payload bytes handed out (monotone; position = % ring_bytes) */
     uint64_t pay_flushed;         /* payload bytes already made visible to the kernel */
     uint64_t *pay_end;            /* [ticket & mask] = pay_head after that ticket's image */
@@ -116,26 +122,19 @@ extern "C" int apus_device_count(void)
 
 static inline int is_leader(const apus_replica *r) { return r->cfg.server_idx == r->cfg.leader_idx; }
 
-extern "C" int apus_replica_create(const apus_config_t *cfg, apus_replica_t **out)
+static int ensure_host_ring(apus_replica *r)
 {
-    if (!cfg || !out) return fail("null argument");
-    if (cfg->struct_size != sizeof(apus_config_t)) return fail("apus_config_t size mismatch (ABI)");
-    if (cfg->group_size < 1 || cfg->group_size > APUS_MAX_SERVER_COUNT) return fail("group_size out of range");
-    if (cfg->server_idx >= cfg->group_size || cfg->leader_idx >= cfg->group_size) return fail("bad server/leader idx");
-    int ndev = apus_device_count();
-    if (ndev <= 0) return fail("no CUDA device: the engine has no CPU fallback");
-    if (cfg->device < 0 || cfg->device >= ndev) return fail("device %d out of range (%d present)", cfg->device, ndev);
-    uint64_t log_len = cfg->log_size ? cfg->log_size : APUS_LOG_SIZE;
-    if (log_len % 4096 || log_len < 8192) return fail("log_size must be a multiple of 4096 (>= 8192)");
+    /* device ring: the pinned staging copy of the ring is only needed when the HOST submits (lazily allocated:
+     * a ring filled by apus_submit_synth never touches host memory) */
+    if (r->ring_desc_host) return APUS_OK;
+    CK(cudaHostAlloc(&r->ring_desc_host, sizeof(apus_slot_t) * r->ring_slots, cudaHostAllocMapped | cudaHostAllocPortable));
+    CK(cudaHostAlloc(&r->ring_pay_host, r->ring_bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+    return APUS_OK;
+}
 
-    DeviceGuard g(cfg->device);
-    if (!g.ok) return fail("cudaSetDevice(%d) failed", cfg->device);
-    apus_replica *r = (apus_replica *)calloc(1, sizeof(*r));
-    if (!r) return fail("out of memory");
-    r->cfg = *cfg;
-    if (!(r->cfg.flags & APUS_F_EXPLICIT)) r->cfg.flags |= APUS_F_DEVICE_STATS;
+static int replica_init(apus_replica *r, const apus_config_t *cfg, uint64_t log_len)
+{
     r->log_len = log_len;
-    if (log_len > (1ull << 31)) return fail("log_size above 2 GiB is not supported (32-bit offset index)");
     uint32_t cap = 1024;
     while ((uint64_t)cap * 64ull < log_len) cap <<= 1;
     r->idx_cap = cap;
@@ -157,6 +156,8 @@ extern "C" int apus_replica_create(const apus_config_t *cfg, apus_replica_t **ou
     CK(cudaHostAlloc(&r->hw, sizeof(apus_hostwords_t), cudaHostAllocMapped | cudaHostAllocPortable));
     memset((void *)r->hw, 0, sizeof(apus_hostwords_t));
     CK(cudaHostGetDevicePointer(&r->hw_dev, r->hw, 0));
+    r->stage_bytes = 1u << 20;
+    CK(cudaHostAlloc(&r->stage, r->stage_bytes, cudaHostAllocPortable));
     CK(cudaMalloc(&r->d_ctx, sizeof(apus_devctx_t)));
     CK(cudaMalloc(&r->d_roles, sizeof(apus_role_t) * 64));
     CK(cudaMalloc(&r->d_lat, sizeof(uint32_t) * APUS_LAT_RING));
@@ -167,28 +168,62 @@ extern "C" int apus_replica_create(const apus_config_t *cfg, apus_replica_t **ou
     CK(cudaEventCreate(&r->ev_stop));
 
     if (is_leader(r)) {
-        uint32_t slots = cfg->ring_slots ? cfg->ring_slots : (1u << 16);
-        uint32_t bytes = cfg->ring_bytes ? cfg->ring_bytes : (16u << 20);
-        if (slots & (slots - 1)) return fail("ring_slots must be a power of two");
-        if (bytes % 4096 || bytes < (1u << 17)) return fail("ring_bytes must be a multiple of 4096, >= 128 KiB");
-        if (bytes / 16 > 0x00ffffffu) return fail("ring_bytes too large for the 24-bit descriptor offset");
-        r->ring_slots = slots; r->ring_bytes = bytes;
-        r->pay_end = (uint64_t *)calloc(slots, sizeof(uint64_t));
+        r->pay_end = (uint64_t *)calloc(r->ring_slots, sizeof(uint64_t));
         if (!r->pay_end) return fail("out of memory");
-        CK(cudaHostAlloc(&r->ring_desc_host, sizeof(apus_slot_t) * slots, cudaHostAllocMapped | cudaHostAllocPortable));
-        CK(cudaHostAlloc(&r->ring_pay_host, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
         if (cfg->ring_mode == APUS_RING_HOST_MAPPED) {
+            if (ensure_host_ring(r) != APUS_OK) return APUS_ERROR;
+            memset(r->ring_desc_host, 0, sizeof(apus_slot_t) * r->ring_slots);     /* no stamp matches ticket 0 */
             CK(cudaHostGetDevicePointer(&r->ring_desc_dev, r->ring_desc_host, 0));
             CK(cudaHostGetDevicePointer(&r->ring_pay_dev, r->ring_pay_host, 0));
         } else {
-            CK(cudaMalloc(&r->ring_desc_dev, sizeof(apus_slot_t) * slots));
-            CK(cudaMalloc(&r->ring_pay_dev, bytes));
+            CK(cudaMalloc(&r->ring_desc_dev, sizeof(apus_slot_t) * r->ring_slots));
+            CK(cudaMalloc(&r->ring_pay_dev, r->ring_bytes));
             CK(cudaMalloc(&r->sub_tail_dev, 128));
             CK(cudaMemset(r->sub_tail_dev, 0, 128));
             CK(cudaHostAlloc(&r->sub_tail_stage, 64, cudaHostAllocPortable));
         }
     }
     r->peer_ptr[cfg->server_idx] = r->region;
+    return APUS_OK;
+}
+
+extern "C" int apus_replica_create(const apus_config_t *cfg, apus_replica_t **out)
+{
+    if (!cfg || !out) return fail("null argument");
+    if (cfg->struct_size != sizeof(apus_config_t) && cfg->struct_size != APUS_CONFIG_SIZE_V1)
+        return fail("apus_config_t size mismatch (ABI)");
+    if (cfg->group_size < 1 || cfg->group_size > APUS_MAX_SERVER_COUNT) return fail("group_size out of range");
+    if (cfg->server_idx >= cfg->group_size || cfg->leader_idx >= cfg->group_size) return fail("bad server/leader idx");
+    int ndev = apus_device_count();
+    if (ndev <= 0) return fail("no CUDA device: the engine has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("device %d out of range (%d present)", cfg->device, ndev);
+    /* every parameter is validated BEFORE anything is allocated */
+    uint64_t log_len = cfg->log_size ? cfg->log_size : APUS_LOG_SIZE;
+    if (log_len % 4096 || log_len < 8192) return fail("log_size must be a multiple of 4096 (>= 8192)");
+    if (log_len > (1ull << 31)) return fail("log_size above 2 GiB is not supported (32-bit offset index)");
+    uint32_t slots = cfg->ring_slots ? cfg->ring_slots : (1u << 16);
+    uint32_t bytes = cfg->ring_bytes ? cfg->ring_bytes : (16u << 20);
+    if (slots & (slots - 1)) return fail("ring_slots must be a power of two");
+    if (bytes % 4096 || bytes < (1u << 17)) return fail("ring_bytes must be a multiple of 4096, >= 128 KiB");
+    if (bytes / 16 > 0x00ffffffu) return fail("ring_bytes too large for the 24-bit descriptor offset");
+
+    DeviceGuard g(cfg->device);
+    if (!g.ok) return fail("cudaSetDevice(%d) failed", cfg->device);
+    apus_replica *r = (apus_replica *)calloc(1, sizeof(*r));
+    if (!r) return fail("out of memory");
+    memset(&r->cfg, 0, sizeof r->cfg);
+    memcpy(&r->cfg, cfg, cfg->struct_size);
+    r->cfg.struct_size = sizeof(apus_config_t);
+    if (!(r->cfg.flags & APUS_F_EXPLICIT)) r->cfg.flags |= APUS_F_DEVICE_STATS;
+    if (cfg->server_idx == cfg->leader_idx) { r->ring_slots = slots; r->ring_bytes = bytes; }
+    if (replica_init(r, cfg, log_len) != APUS_OK) {
+        /* one cleanup path: whatever was allocated so far goes away with the partial object (g_err is kept) */
+        char keep[sizeof g_err];
+        memcpy(keep, g_err, sizeof keep);
+        apus_replica_destroy(r);
+        memcpy(g_err, keep, sizeof keep);
+        return APUS_ERROR;
+    }
     *out = r;
     return APUS_OK;
 }
@@ -197,23 +232,31 @@ extern "C" void apus_replica_destroy(apus_replica_t *r)
 {
     if (!r) return;
     DeviceGuard g(r->cfg.device);
-    if (r->in_flight) {
+    if (r->in_flight && r->hw) {
         r->hw->stop = 1;
         cudaEventSynchronize(r->launch_owner ? r->launch_owner->ev_stop : r->ev_stop);
     }
     for (int i = 0; i < APUS_MAX_SERVER_COUNT; i++)
         if (r->peer_is_ipc[i] && r->peer_ptr[i]) cudaIpcCloseMemHandle(r->peer_ptr[i]);
     if (r->cfg.ring_mode != APUS_RING_HOST_MAPPED) {
-        cudaFree(r->ring_desc_dev); cudaFree(r->ring_pay_dev); cudaFree(r->sub_tail_dev);
+        if (r->ring_desc_dev) cudaFree(r->ring_desc_dev);
+        if (r->ring_pay_dev) cudaFree(r->ring_pay_dev);
+        if (r->sub_tail_dev) cudaFree(r->sub_tail_dev);
         if (r->sub_tail_stage) cudaFreeHost(r->sub_tail_stage);
     }
     if (r->ring_desc_host) cudaFreeHost(r->ring_desc_host);
     if (r->ring_pay_host) cudaFreeHost(r->ring_pay_host);
-    cudaFree(r->d_lat); cudaFree(r->d_roles); cudaFree(r->d_ctx);
-    cudaEventDestroy(r->ev_start); cudaEventDestroy(r->ev_stop);
-    cudaStreamDestroy(r->stream); cudaStreamDestroy(r->copy_stream);
-    cudaFreeHost((void *)r->hw);
-    cudaFree(r->region);
+    if (r->stage) cudaFreeHost(r->stage);
+    if (r->d_lat) cudaFree(r->d_lat);
+    if (r->d_roles) cudaFree(r->d_roles);
+    if (r->d_ctx) cudaFree(r->d_ctx);
+    if (r->ev_start) cudaEventDestroy(r->ev_start);
+    if (r->ev_stop) cudaEventDestroy(r->ev_stop);
+    if (r->stream) cudaStreamDestroy(r->stream);
+    if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
+    if (r->hw) cudaFreeHost((void *)r->hw);
+    if (r->region) cudaFree(r->region);
+    cudaGetLastError();
     free(r->pay_end);
     free(r);
 }
@@ -276,6 +319,9 @@ static void fill_ctx(apus_replica *r, uint64_t target)
     if (c->n_workers > 32) c->n_workers = 32;
     c->epoch = (uint32_t)(r->launches + 1);
     c->doorbell_relay = (r->cfg.ring_mode == APUS_RING_HOST_MAPPED && c->n_workers >= 2) ? 1u : 0u;
+    c->slot_poll = (r->cfg.ring_mode == APUS_RING_HOST_MAPPED) ? 1u : 0u;
+    c->hb_period_ns = (uint64_t)r->cfg.hb_period_us * 1000ull;
+    c->hb_timeout_ns = (target == ~0ull) ? (uint64_t)r->cfg.hb_timeout_us * 1000ull : 0;   /* bounded launches end on their own */
     c->region = r->region;
     for (int i = 0; i < APUS_MAX_SERVER_COUNT; i++)
         c->peer[i] = (i == r->cfg.server_idx) ? NULL : (uint8_t *)r->peer_ptr[i];
@@ -303,7 +349,7 @@ extern "C" int apus_replicas_launch(apus_replica_t **rs, int n, uint64_t target)
     for (int i = 0; i < n; i++) {
         apus_replica *r = rs[i];
         fill_ctx(r, target);
-        r->hw->stop = 0; r->hw->error = 0;
+        r->hw->stop = 0; r->hw->error = 0; r->hw->leader_suspect = 0;
         CK(cudaMemcpyAsync(r->d_ctx, &r->h_ctx, sizeof(apus_devctx_t), cudaMemcpyHostToDevice, owner->stream));
         if (is_leader(r)) {
             for (uint32_t w = 0; w < r->h_ctx.n_workers; w++) {
@@ -385,20 +431,29 @@ static inline uint32_t image_bytes(uint8_t type, uint16_t len)
     return 2u + len;
 }
 
-/* Requests whose data image fits APUS_SLOT_INLINE travel inside their 128 B slot;
- * larger images go to the payload byte ring.  Payload space is tracked with monotone
- * byte counters: pay_head (bytes handed out, skip gaps included) and, per ticket, the
- * counter value after its image. */
-static int ring_put(apus_replica *r, uint8_t type, uint16_t conn, uint64_t req_id, const void *cmd, uint16_t len)
+/* payload byte k of the synthetic request `req_id` (apus_submit_synth); the same function runs in the fill kernel */
+__host__ __device__ static inline uint32_t synth_word(uint32_t seed, uint64_t req_id, uint32_t w)
 {
-    const uint64_t consumed = r->hw->consumed;
+    uint32_t x = seed ^ ((uint32_t)req_id * 0x9E3779B1u) ^ ((uint32_t)(req_id >> 32) * 0x7F4A7C15u) ^ (w * 0x85EBCA77u);
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ static inline uint8_t synth_byte(uint32_t seed, uint64_t req_id, uint32_t k)
+{
+    return (uint8_t)(synth_word(seed, req_id, k >> 2) >> (8u * (k & 3u)));
+}
+extern "C" uint8_t apus_synth_byte(uint32_t seed, uint64_t req_id, uint32_t k) { return synth_byte(seed, req_id, k); }
+
+/* Where the data image of a request goes: inline in its slot (<= APUS_SLOT_INLINE bytes) or into the payload byte
+ * ring.  Payload space is tracked with monotone byte counters: pay_head (bytes handed out, skip gaps included) and,
+ * per ticket, the counter value after its image.  Returns the type_off word; *ppos = ring position of an external
+ * image.  APUS_RETRY when the payload ring has no room. */
+static inline int place_image(apus_replica *r, uint8_t type, uint32_t nb, uint64_t consumed, uint64_t *head_io,
+                              uint32_t *type_off_out, uint64_t *ppos)
+{
     const uint32_t mask = r->ring_slots - 1;
-    if (r->submitted - consumed >= r->ring_slots) return APUS_RETRY;
-    const uint32_t nb = image_bytes(type, len);
-    apus_slot_t *d = &r->ring_desc_host[r->submitted & mask];
     uint32_t type_off = ((uint32_t)type & APUS_SLOT_TYPE_MASK) << APUS_SLOT_TYPE_SHIFT;
-    uint64_t head = r->pay_head;
-    uint8_t *dst = d->inl;
+    uint64_t head = *head_io;
     if (nb > APUS_SLOT_INLINE) {
         const uint32_t need = (nb + 15u) & ~15u;
         const uint64_t R = r->ring_bytes;
@@ -408,11 +463,22 @@ static int ring_put(apus_replica *r, uint8_t type, uint16_t conn, uint64_t req_i
         if ((head - tail) + skip + need > R) return APUS_RETRY;
         head += skip;
         pos = head % R;
-        dst = r->ring_pay_host + pos;
+        *ppos = pos;
         type_off |= APUS_SLOT_EXT | (uint32_t)(pos / 16);
         if (skip || (pos == 0 && head != 0)) type_off |= APUS_SLOT_WRAP;
         head += need;
     }
+    *head_io = head;
+    *type_off_out = type_off;
+    return APUS_OK;
+}
+
+/* write one slot: image first, descriptor, then the two stamps -- each 64 B half is complete once its stamp is there */
+static inline void write_slot(apus_slot_t *d, uint8_t *paydst, uint64_t ticket, uint8_t type, uint32_t type_off,
+                              uint16_t conn, uint64_t req_id, const void *cmd, uint16_t len, uint32_t nb)
+{
+    uint8_t img[APUS_SLOT_INLINE];
+    uint8_t *dst = paydst ? paydst : img;
     if (nb) {
         if (type == APUS_CONFIG || type == APUS_HEAD) {
             memcpy(dst, cmd, nb);
@@ -421,22 +487,58 @@ static int ring_put(apus_replica *r, uint8_t type, uint16_t conn, uint64_t req_i
             if (len) memcpy(dst + 2, cmd, len);
         }
     }
+    if (!paydst && nb) {
+        memcpy(d->inl0, img, nb < 32 ? nb : 32);
+        if (nb > 32) memcpy(d->inl1, img + 32, nb - 32);
+    }
     d->req_id = req_id;
     d->type_off = type_off;
     d->len = len;
     d->clt_id = conn;
+    __atomic_store_n(&d->stamp1, ticket, __ATOMIC_RELEASE);
+    __atomic_store_n(&d->stamp0, ticket, __ATOMIC_RELEASE);
+}
+
+static int ring_put(apus_replica *r, uint8_t type, uint16_t conn, uint64_t req_id, const void *cmd, uint16_t len)
+{
+    const uint64_t consumed = r->hw->consumed;
+    const uint32_t mask = r->ring_slots - 1;
+    if (r->submitted - consumed >= r->ring_slots) return APUS_RETRY;
+    if (!r->ring_desc_host && ensure_host_ring(r) != APUS_OK) return APUS_ERROR;
+    const uint32_t nb = image_bytes(type, len);
+    uint64_t head = r->pay_head, pos = 0;
+    uint32_t type_off = 0;
+    int rc = place_image(r, type, nb, consumed, &head, &type_off, &pos);
+    if (rc != APUS_OK) return rc;
+    write_slot(&r->ring_desc_host[r->submitted & mask], (type_off & APUS_SLOT_EXT) ? r->ring_pay_host + pos : NULL,
+               r->submitted + 1, type, type_off, conn, req_id, cmd, len, nb);
     r->pay_end[r->submitted & mask] = head;
     r->pay_head = head;
     r->submitted++;
     return APUS_OK;
 }
 
-static int ring_flush(apus_replica *r)
+/* give the kernel the doorbell value `upto` (slots up to it are readable by the device) */
+static int ring_bell(apus_replica *r, uint64_t upto)
+{
+    if (upto <= r->belled) return APUS_OK;
+    if (r->cfg.ring_mode == APUS_RING_HOST_MAPPED) {
+        __sync_synchronize();                        /* descriptors + payload before the doorbell */
+        r->hw->sub_tail = upto;
+    } else {
+        *r->sub_tail_stage = upto;
+        CK(cudaMemcpyAsync(r->sub_tail_dev, r->sub_tail_stage, 8, cudaMemcpyHostToDevice, r->copy_stream));
+        CK(cudaStreamSynchronize(r->copy_stream));
+    }
+    r->belled = upto;
+    return APUS_OK;
+}
+
+/* make the slots [flushed, submitted) readable by the device (device ring: copy them over) */
+static int ring_push(apus_replica *r)
 {
     if (r->flushed == r->submitted) return APUS_OK;
     if (r->cfg.ring_mode == APUS_RING_HOST_MAPPED) {
-        __sync_synchronize();                        /* descriptors + payload before the doorbell */
-        r->hw->sub_tail = r->submitted;
         r->flushed = r->submitted;
         r->pay_flushed = r->pay_head;
         return APUS_OK;
@@ -463,12 +565,18 @@ static int ring_flush(apus_replica *r)
         CK(cudaMemcpyAsync(r->ring_pay_dev + p0, r->ring_pay_host + p0, run, cudaMemcpyHostToDevice, r->copy_stream));
         pf += run;
     }
-    *r->sub_tail_stage = r->submitted;
-    CK(cudaMemcpyAsync(r->sub_tail_dev, r->sub_tail_stage, 8, cudaMemcpyHostToDevice, r->copy_stream));
     CK(cudaStreamSynchronize(r->copy_stream));
     r->flushed = r->submitted;
     r->pay_flushed = r->pay_head;
     return APUS_OK;
+}
+
+static int ring_flush(apus_replica *r)
+{
+    int rc = ring_push(r);
+    if (rc != APUS_OK) return rc;
+    DeviceGuard g(r->cfg.device);
+    return ring_bell(r, r->submitted);
 }
 
 extern "C" int apus_submit(apus_replica_t *r, uint8_t type, uint16_t connection_id, uint64_t req_id,
@@ -507,6 +615,208 @@ extern "C" int apus_submit_batch(apus_replica_t *r, uint32_t n, const uint8_t *t
     return APUS_OK;
 }
 
+/* ---- bulk submission of one request shape, filled by several host threads ------------------------ */
+struct fill_job {
+    apus_replica *r;
+    uint32_t n;
+    uint8_t type; uint16_t conn; uint64_t first_req; uint16_t len;
+    const uint8_t *payloads; size_t stride;
+    uint64_t first_slot;          /* r->submitted when the job was cut */
+    const uint32_t *type_off;     /* per request (external images) or NULL: all inline */
+    const uint64_t *pos;
+    uint32_t type_off_inline;
+};
+static void fill_range(const fill_job *j, uint32_t k0, uint32_t k1)
+{
+    apus_replica *r = j->r;
+    const uint32_t mask = r->ring_slots - 1;
+    const uint32_t nb = image_bytes(j->type, j->len);
+    for (uint32_t k = k0; k < k1; k++) {
+        const uint64_t s = j->first_slot + k;
+        const uint32_t to = j->type_off ? j->type_off[k] : j->type_off_inline;
+        write_slot(&r->ring_desc_host[s & mask], (to & APUS_SLOT_EXT) ? r->ring_pay_host + j->pos[k] : NULL, s + 1, j->type, to,
+                   j->conn, j->first_req + k, j->payloads ? j->payloads + (size_t)k * j->stride : NULL, j->len, nb);
+    }
+}
+
+#define POOL_MAX 16
+static struct {
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    pthread_t th[POOL_MAX];
+    int nthreads, started;
+    const fill_job *job;
+    volatile uint64_t gen;                 /* job generation */
+    volatile uint32_t next, done_parts, parts, chunk;
+} g_pool = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER };
+
+static void pool_work(const fill_job *j)
+{
+    for (;;) {
+        const uint32_t p = __atomic_fetch_add(&g_pool.next, 1, __ATOMIC_ACQ_REL);
+        if (p >= g_pool.parts) break;
+        const uint32_t k0 = p * g_pool.chunk, k1 = (k0 + g_pool.chunk < j->n) ? k0 + g_pool.chunk : j->n;
+        fill_range(j, k0, k1);
+        __atomic_fetch_add(&g_pool.done_parts, 1, __ATOMIC_ACQ_REL);
+    }
+}
+static void *pool_main(void *)
+{
+    uint64_t seen = 0;
+    for (;;) {
+        /* spin briefly for the next job (bulk submits come back to back), then sleep */
+        uint64_t g = seen;
+        for (int i = 0; i < 200000 && (g = __atomic_load_n(&g_pool.gen, __ATOMIC_ACQUIRE)) == seen; i++) _mm_pause();
+        if (g == seen) {
+            pthread_mutex_lock(&g_pool.mu);
+            while ((g = g_pool.gen) == seen) pthread_cond_wait(&g_pool.cv, &g_pool.mu);
+            pthread_mutex_unlock(&g_pool.mu);
+        }
+        seen = g;
+        pool_work(g_pool.job);
+    }
+    return NULL;
+}
+static pthread_mutex_t g_pool_run = PTHREAD_MUTEX_INITIALIZER;     /* one bulk job at a time per process */
+static void pool_run(const fill_job *j)
+{
+    pthread_mutex_lock(&g_pool_run);
+    pthread_mutex_lock(&g_pool.mu);
+    if (!g_pool.started) {
+        int want = 4;
+        const char *e = getenv("apus_submit_threads");
+        if (e) want = atoi(e);
+        long cores = sysconf(_SC_NPROCESSORS_ONLN);
+        if (want > cores - 1) want = (int)cores - 1;
+        if (want > POOL_MAX) want = POOL_MAX;
+        if (want < 1) want = 1;
+        g_pool.nthreads = want - 1;                         /* the caller is a worker too */
+        for (int i = 0; i < g_pool.nthreads; i++)
+            if (pthread_create(&g_pool.th[i], NULL, pool_main, NULL)) { g_pool.nthreads = i; break; }
+        g_pool.started = 1;
+    }
+    g_pool.job = j;
+    g_pool.chunk = 4096;
+    g_pool.parts = (j->n + g_pool.chunk - 1) / g_pool.chunk;
+    g_pool.next = 0; g_pool.done_parts = 0;
+    __atomic_fetch_add(&g_pool.gen, 1, __ATOMIC_RELEASE);
+    pthread_cond_broadcast(&g_pool.cv);
+    pthread_mutex_unlock(&g_pool.mu);
+    pool_work(j);
+    while (__atomic_load_n(&g_pool.done_parts, __ATOMIC_ACQUIRE) < g_pool.parts) _mm_pause();
+    pthread_mutex_unlock(&g_pool_run);
+}
+
+extern "C" int apus_submit_uniform(apus_replica_t *r, uint32_t n, uint8_t type, uint16_t connection_id,
+                                   uint64_t first_req_id, uint16_t len, const void *payloads, size_t stride,
+                                   uint64_t *first_ticket)
+{
+    if (!r) return fail("null argument");
+    if (!is_leader(r)) return fail("submit on a follower");
+    if (len && !payloads) return fail("null payload");
+    if (n == 0) return APUS_OK;
+    const uint64_t consumed = r->hw->consumed;
+    if (r->submitted + n - consumed > r->ring_slots) { snprintf(g_err, sizeof g_err, "submission ring full"); return APUS_RETRY; }
+    if (!r->ring_desc_host && ensure_host_ring(r) != APUS_OK) return APUS_ERROR;
+    const uint32_t mask = r->ring_slots - 1;
+    const uint32_t nb = image_bytes(type, len);
+    fill_job j;
+    memset(&j, 0, sizeof j);
+    j.r = r; j.n = n; j.type = type; j.conn = connection_id; j.first_req = first_req_id; j.len = len;
+    j.payloads = (const uint8_t *)payloads; j.stride = stride; j.first_slot = r->submitted;
+    uint32_t *tos = NULL; uint64_t *poss = NULL;
+    uint64_t head = r->pay_head;
+    if (nb > APUS_SLOT_INLINE) {
+        /* external images: positions are handed out serially (cheap), the copies run in parallel */
+        tos = (uint32_t *)malloc(sizeof(uint32_t) * n); poss = (uint64_t *)malloc(sizeof(uint64_t) * n);
+        if (!tos || !poss) { free(tos); free(poss); return fail("out of memory"); }
+        for (uint32_t k = 0; k < n; k++) {
+            int rc = place_image(r, type, nb, consumed, &head, &tos[k], &poss[k]);
+            if (rc != APUS_OK) { free(tos); free(poss); snprintf(g_err, sizeof g_err, "payload ring full"); return rc; }
+            r->pay_end[(r->submitted + k) & mask] = head;
+        }
+        j.type_off = tos; j.pos = poss;
+    } else {
+        j.type_off_inline = ((uint32_t)type & APUS_SLOT_TYPE_MASK) << APUS_SLOT_TYPE_SHIFT;
+        for (uint32_t k = 0; k < n; k++) r->pay_end[(r->submitted + k) & mask] = head;
+    }
+    if (n >= 16384) pool_run(&j); else fill_range(&j, 0, n);
+    free(tos); free(poss);
+    r->pay_head = head;
+    if (first_ticket) *first_ticket = r->submitted + 1;
+    r->submitted += n;
+    if (!r->defer) return ring_flush(r);
+    return APUS_OK;
+}
+
+/* ---- device-generated requests ---------------------------------------------------------------------- */
+__global__ void apus_synth_kernel(apus_slot_t *ring, uint32_t mask, uint8_t *pay, uint64_t first_slot, uint32_t n,
+                                  uint32_t type, uint32_t conn, uint64_t first_req, uint32_t len, uint32_t seed,
+                                  uint64_t pay_pos0, uint32_t need)
+{
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint64_t s = first_slot + k, req = first_req + k;
+        apus_slot_t *d = &ring[s & mask];
+        const uint32_t nb = 2u + len;
+        uint32_t type_off = (type & APUS_SLOT_TYPE_MASK) << APUS_SLOT_TYPE_SHIFT;
+        uint8_t *dst0 = d->inl0, *dst1 = d->inl1;
+        if (need) {
+            const uint64_t pos = pay_pos0 + (uint64_t)k * need;
+            type_off |= APUS_SLOT_EXT | (uint32_t)(pos / 16);
+            uint8_t *p = pay + pos;
+            p[0] = (uint8_t)len; p[1] = (uint8_t)(len >> 8);
+            for (uint32_t q = 0; q < len; q++) p[2 + q] = synth_byte(seed, req, q);
+        } else {
+            for (uint32_t q = 0; q < nb; q++) {
+                const uint8_t v = q == 0 ? (uint8_t)len : q == 1 ? (uint8_t)(len >> 8) : synth_byte(seed, req, q - 2);
+                if (q < 32) dst0[q] = v; else dst1[q - 32] = v;
+            }
+        }
+        d->req_id = req; d->type_off = type_off; d->len = (uint16_t)len; d->clt_id = (uint16_t)conn;
+        d->stamp0 = s + 1; d->stamp1 = s + 1; d->rsv0 = 0; d->rsv1 = 0;
+    }
+}
+
+extern "C" int apus_submit_synth(apus_replica_t *r, uint32_t n, uint8_t type, uint16_t connection_id,
+                                 uint64_t first_req_id, uint16_t len, uint32_t seed, uint64_t *first_ticket)
+{
+    if (!r) return fail("null argument");
+    if (!is_leader(r)) return fail("submit on a follower");
+    if (r->cfg.ring_mode != APUS_RING_DEVICE) return fail("apus_submit_synth needs the device submission ring");
+    if (type == APUS_NOOP || type == APUS_CONFIG || type == APUS_HEAD) return fail("apus_submit_synth: request types only");
+    if (n == 0) return APUS_OK;
+    const uint64_t consumed = r->hw->consumed;
+    if (r->submitted + n - consumed > r->ring_slots) { snprintf(g_err, sizeof g_err, "submission ring full"); return APUS_RETRY; }
+    if (r->flushed != r->submitted) { int rc = ring_push(r); if (rc != APUS_OK) return rc; }
+    const uint32_t mask = r->ring_slots - 1;
+    const uint32_t nb = 2u + len;
+    uint32_t need = 0;
+    uint64_t pos0 = 0, head = r->pay_head;
+    if (nb > APUS_SLOT_INLINE) {
+        need = (nb + 15u) & ~15u;
+        const uint64_t R = r->ring_bytes;
+        pos0 = head % R;
+        const uint64_t tail = consumed ? r->pay_end[(consumed - 1) & mask] : 0;
+        if (pos0 + (uint64_t)n * need > R || (head - tail) + (uint64_t)n * need > R)
+            return fail("apus_submit_synth: %u images of %u B do not fit the payload ring without wrapping", n, need);
+    }
+    DeviceGuard g(r->cfg.device);
+    const int threads = 256;
+    int blocks = (int)((n + threads - 1) / threads);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    apus_synth_kernel<<<blocks, threads, 0, r->copy_stream>>>(r->ring_desc_dev, mask, r->ring_pay_dev, r->submitted, n, type,
+                                                              connection_id, first_req_id, len, seed, pos0, need);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(r->copy_stream));
+    for (uint32_t k = 0; k < n; k++) { head += need; r->pay_end[(r->submitted + k) & mask] = head; }
+    r->pay_head = head; r->pay_flushed = head;
+    if (first_ticket) *first_ticket = r->submitted + 1;
+    r->submitted += n;
+    r->flushed = r->submitted;
+    if (!r->defer) return ring_bell(r, r->submitted);
+    return APUS_OK;
+}
+
 extern "C" int apus_submit_defer(apus_replica_t *r, int defer)
 {
     if (!r) return fail("null argument");
@@ -518,17 +828,27 @@ extern "C" int apus_submit_flush(apus_replica_t *r)
     if (!r) return fail("null argument");
     return ring_flush(r);
 }
+extern "C" int apus_submit_release(apus_replica_t *r, uint64_t ticket)
+{
+    if (!r) return fail("null argument");
+    if (ticket > r->submitted) return fail("release beyond what was submitted");
+    int rc = ring_push(r);
+    if (rc != APUS_OK) return rc;
+    DeviceGuard g(r->cfg.device);
+    return ring_bell(r, ticket);
+}
 
 extern "C" uint64_t apus_committed_tickets(apus_replica_t *r) { return r ? r->hw->committed_tickets : 0; }
 
 extern "C" int apus_progress(apus_replica_t *r, uint64_t *offset, uint64_t *count)
 {
     if (!r) return fail("null argument");
-    /* count first: the kernel writes the offset before the count */
-    const uint64_t c = r->hw->committed_tickets;
-    __sync_synchronize();
-    if (count) *count = c;
-    if (offset) *offset = r->hw->commit_off;
+    /* {commit_off, committed_tickets} is written by the kernel with ONE 16 B store: read it with one 16 B load */
+    const __m128i v = _mm_load_si128((const __m128i *)(const void *)&r->hw->commit_off);
+    uint64_t w[2];
+    _mm_storeu_si128((__m128i *)w, v);
+    if (offset) *offset = w[0];
+    if (count) *count = w[1];
     return r->hw->error ? fail("kernel reported protocol error %llu", (unsigned long long)r->hw->error) : APUS_OK;
 }
 
@@ -602,10 +922,42 @@ extern "C" int apus_log_read(apus_replica_t *r, uint64_t off, uint64_t len, void
     if (!r || !dst) return fail("null argument");
     if (off + len > r->log_len) return fail("range beyond the log");
     DeviceGuard g(r->cfg.device);
-    CK(cudaMemcpyAsync(dst, r->region + r->entries_off + off, len, cudaMemcpyDeviceToHost, r->copy_stream));
-    CK(cudaStreamSynchronize(r->copy_stream));
+    /* through the pinned bounce buffer: a pageable destination would make every copy a synchronous staged one */
+    uint8_t *out = (uint8_t *)dst;
+    while (len) {
+        const uint64_t run = len < r->stage_bytes ? len : r->stage_bytes;
+        CK(cudaMemcpyAsync(r->stage, r->region + r->entries_off + off, run, cudaMemcpyDeviceToHost, r->copy_stream));
+        CK(cudaStreamSynchronize(r->copy_stream));
+        memcpy(out, r->stage, run);
+        out += run; off += run; len -= run;
+    }
     return APUS_OK;
 }
+
+extern "C" int apus_log_read_range(apus_replica_t *r, uint64_t from, uint64_t to, void *dst, uint64_t cap, uint64_t *got)
+{
+    if (!r || !dst || !got) return fail("null argument");
+    if (from >= r->log_len || to >= r->log_len) return fail("range beyond the log");
+    const uint64_t L = r->log_len;
+    uint64_t n1 = to >= from ? to - from : L - from, n2 = to >= from ? 0 : to;
+    if (n1 > cap) { n1 = cap; n2 = 0; }
+    if (n1 + n2 > cap) n2 = cap - n1;
+    int rc = n1 ? apus_log_read(r, from, n1, dst) : APUS_OK;
+    if (rc == APUS_OK && n2) rc = apus_log_read(r, 0, n2, (uint8_t *)dst + n1);
+    *got = n1 + n2;
+    return rc;
+}
+
+extern "C" int apus_set_applied(apus_replica_t *r, uint64_t offset)
+{
+    if (!r) return fail("null argument");
+    if (offset >= r->log_len) return fail("offset beyond the log");
+    r->hw->host_apply = offset;          /* the follower kernel forwards it to the leader's pruning rule */
+    return APUS_OK;
+}
+
+extern "C" uint64_t apus_leader_suspect(apus_replica_t *r) { return r ? r->hw->leader_suspect : 0; }
+extern "C" uint64_t apus_last_commit_ns(apus_replica_t *r) { return r ? r->hw->last_commit_ns : 0; }
 
 extern "C" int apus_get_stats(apus_replica_t *r, apus_stats_t *out)
 {

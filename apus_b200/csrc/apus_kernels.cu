@@ -162,7 +162,7 @@ struct LeaderShared {
     uint8_t  ty[MAXB];
     uint8_t  flg[MAXB];        // bit0 EXT, bit1 WRAP
     // claim
-    uint32_t n_fetch, finish;
+    uint32_t n_fetch, finish, abort, pad_a;
     uint32_t avg_es, avg_xb;   // log / staged bytes per entry seen in this worker's last claim (sizes the next one)
     uint64_t slot0, my_seq, t_dequeue, st_head, t_place_acq, pub_h, pub_tail_seen;
     // placement state while this CTA holds the place turn (mirrors apus_seq_t.p_*)
@@ -178,7 +178,7 @@ struct LeaderShared {
 
 #define LS_BYTES ((sizeof(LeaderShared) + 127u) & ~127u)
 #define L_SLOTS_OFF LS_BYTES
-#define L_EXT_OFF   (L_SLOTS_OFF + MAXB * APUS_SLOT_BYTES)
+#define L_EXT_OFF   (L_SLOTS_OFF + MAXB * APUS_CSLOT_BYTES)
 #define L_IMG_OFF   (L_EXT_OFF + APUS_LEADER_EXT_BYTES)
 #define L_TOTAL     (L_IMG_OFF + APUS_LEADER_IMG_BYTES + 16)
 
@@ -190,6 +190,8 @@ struct FollowerShared {
     uint64_t head_val, head_end;             // last HEAD entry of the window (head_end == len: none)
     uint64_t end_seen, cum_seen, commit_seen;
     uint32_t head_j;                         // index mode: 1 + position of the last HEAD entry of the batch
+    uint32_t cert;                           // the publish being processed was self-certifying: ONE entry at cert_start
+    uint64_t cert_start;
 };
 #define FS_BYTES ((sizeof(FollowerShared) + 127u) & ~127u)
 #define F_TOTAL (FS_BYTES + APUS_FOLLOWER_WIN_BYTES + 16)
@@ -203,10 +205,47 @@ __device__ __forceinline__ uint64_t ld_acquire_gpu(const volatile void *p)
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void ld_acquire_gpu_2x64(const volatile void *p, uint64_t &a, uint64_t &b)
+{
+    asm volatile("ld.acquire.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void st_release_gpu(volatile void *p, uint64_t v)
 {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+
+// ---------------------------------------------------------------------------------
+// Self-certifying publishes.  A lone request is pushed to the followers WITHOUT a writer-side
+// fence (a system fence costs 1.5-1.7 us here, more than the NVLink hop it orders): the publish
+// record carries a checksum of the entry bytes, the follower re-reads the bytes from its own HBM
+// until they add up (FaRM-style object validation).  The checksum is LINEAR over 8-byte words with
+// position-dependent odd weights, so "the bytes that were there before" only pass if they are the
+// bytes that were sent -- in which case accepting them is harmless.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t cs_weight(uint64_t word_index)
+{
+    uint64_t z = word_index * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27;
+    return z | 1ull;
+}
+// bytes of the 8-byte word at log offset o that lie inside [a, b)
+__device__ __forceinline__ uint64_t cs_mask(uint64_t o, uint64_t a, uint64_t b)
+{
+    const uint64_t lo = a > o ? a - o : 0, hi = b < o + 8 ? (b > o ? b - o : 0) : 8;
+    if (hi <= lo) return 0;
+    const uint64_t mh = hi >= 8 ? ~0ull : ((1ull << (8 * hi)) - 1ull);
+    const uint64_t ml = (1ull << (8 * lo)) - 1ull;          // lo < 8 here
+    return mh & ~ml;
+}
+// contribution of the 16 B chunk at log offset lo (16 B aligned), restricted to the bytes inside [a, b)
+__device__ __forceinline__ uint64_t cs_chunk(const uint4 v, uint64_t lo, uint64_t a, uint64_t b)
+{
+    const uint64_t w0 = (uint64_t)v.x | ((uint64_t)v.y << 32), w1 = (uint64_t)v.z | ((uint64_t)v.w << 32);
+    return (w0 & cs_mask(lo, a, b)) * cs_weight(lo >> 3) + (w1 & cs_mask(lo + 8, a, b)) * cs_weight((lo >> 3) + 1);
+}
+// the key that ties a certificate to ITS publish (a certificate half from an older publish must not verify)
+__device__ __forceinline__ uint64_t cs_key(uint64_t cum_term) { return cs_weight(cum_term ^ 0x5851F42D4C957F2Dull); }
 
 // ---------------------------------------------------------------------------------
 // LEADER
@@ -306,33 +345,41 @@ __device__ __forceinline__ void note_desc(LeaderShared *S, uint32_t k, const uin
     S->xb[k] = (to & APUS_SLOT_EXT) ? ((data_bytes(ty, len) + 15u) & ~15u) : 0u;
 }
 
-// fetch `cnt` slots starting at ring slot `s` into shared slot `k0` onward
+// fetch `cnt` slots starting at ring slot `s` into shared slot `k0` onward.  A 128 B ring slot is kept as a
+// 96 B compact slot: its two stamp chunks (3 and 7) are neither loaded nor stored, so that the inline image
+// is contiguous in shared memory (and a quarter of the PCIe / HBM read traffic is saved).
 __device__ __noinline__ void cta_fetch_slots(LeaderShared *S, uint8_t *slots, const apus_slot_t *ring, uint64_t s, uint32_t k0,
                                                 uint32_t cnt, int tid)
 {
     const uint8_t *src = reinterpret_cast<const uint8_t *>(ring + s);
-    uint8_t *dst = slots + (size_t)k0 * APUS_SLOT_BYTES;
-    const uint32_t nchunks = cnt * 8u;
-    uint32_t c = (tid >= 32) ? tid - 32 : tid + NT - 32;      // warp 1 takes the first chunks (warp 0 is busy with the locks)
-    for (; c + 3u * NT < nchunks; c += 4u * NT) {
-        const uint4 v0 = ld_relaxed_sys_v4(src + 16ull * c);
-        const uint4 v1 = ld_relaxed_sys_v4(src + 16ull * (c + NT));
-        const uint4 v2 = ld_relaxed_sys_v4(src + 16ull * (c + 2u * NT));
-        const uint4 v3 = ld_relaxed_sys_v4(src + 16ull * (c + 3u * NT));
-        reinterpret_cast<uint4 *>(dst)[c] = v0;
-        reinterpret_cast<uint4 *>(dst)[c + NT] = v1;
-        reinterpret_cast<uint4 *>(dst)[c + 2u * NT] = v2;
-        reinterpret_cast<uint4 *>(dst)[c + 3u * NT] = v3;
-        if ((c & 7u) == 0) note_desc(S, k0 + (c >> 3), v0);
-        if (((c + NT) & 7u) == 0) note_desc(S, k0 + ((c + NT) >> 3), v1);
-        if (((c + 2u * NT) & 7u) == 0) note_desc(S, k0 + ((c + 2u * NT) >> 3), v2);
-        if (((c + 3u * NT) & 7u) == 0) note_desc(S, k0 + ((c + 3u * NT) >> 3), v3);
+    uint8_t *dst = slots + (size_t)k0 * APUS_CSLOT_BYTES;
+    const uint32_t nq = cnt * 6u;                                  // compact chunks
+    uint32_t q = (tid >= 32) ? tid - 32 : tid + NT - 32;           // warp 1 takes the first chunks (warp 0 is busy with the turns)
+#define SRC_OF(qq, kk, rr) const uint32_t kk = (qq) / 6u, rr = (qq) - 6u * kk; const uint8_t *p_##qq = src + (size_t)kk * APUS_SLOT_BYTES + 16u * (rr < 3u ? rr : rr + 1u)
+    for (; q + 3u * NT < nq; q += 4u * NT) {
+        const uint32_t q0 = q, q1 = q + NT, q2 = q + 2u * NT, q3 = q + 3u * NT;
+        SRC_OF(q0, ka, ra); SRC_OF(q1, kb, rb); SRC_OF(q2, kc, rc); SRC_OF(q3, kd, rd);
+        const uint4 v0 = ld_relaxed_sys_v4(p_q0);
+        const uint4 v1 = ld_relaxed_sys_v4(p_q1);
+        const uint4 v2 = ld_relaxed_sys_v4(p_q2);
+        const uint4 v3 = ld_relaxed_sys_v4(p_q3);
+        reinterpret_cast<uint4 *>(dst)[q0] = v0;
+        reinterpret_cast<uint4 *>(dst)[q1] = v1;
+        reinterpret_cast<uint4 *>(dst)[q2] = v2;
+        reinterpret_cast<uint4 *>(dst)[q3] = v3;
+        if (ra == 0) note_desc(S, k0 + ka, v0);
+        if (rb == 0) note_desc(S, k0 + kb, v1);
+        if (rc == 0) note_desc(S, k0 + kc, v2);
+        if (rd == 0) note_desc(S, k0 + kd, v3);
     }
-    for (; c < nchunks; c += NT) {
-        const uint4 v = ld_relaxed_sys_v4(src + 16ull * c);
-        reinterpret_cast<uint4 *>(dst)[c] = v;
-        if ((c & 7u) == 0) note_desc(S, k0 + (c >> 3), v);
+    for (; q < nq; q += NT) {
+        const uint32_t q0 = q;
+        SRC_OF(q0, ka, ra);
+        const uint4 v = ld_relaxed_sys_v4(p_q0);
+        reinterpret_cast<uint4 *>(dst)[q0] = v;
+        if (ra == 0) note_desc(S, k0 + ka, v);
     }
+#undef SRC_OF
 }
 
 __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
@@ -352,7 +399,8 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
     uint64_t seen = 0;                       // records [tail, seen) are valid and not committed yet
     uint64_t published = ctrl->published;    // entries published = cum of the newest valid record
     uint64_t last_progress = globaltimer_ns();
-    uint32_t spins = 0;
+    uint32_t spins = 0, hb_spins = 0;
+    uint64_t last_hb = 0, hb_beat = globaltimer_ns() >> 10;   // beats keep growing across launches
     bool S_rec_ok = false;
     volatile uint64_t *peer_commit = nullptr;
     if (lane < N && lane != me && cx->peer[lane])
@@ -429,9 +477,11 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
             if (any) {
                 if (peer_commit) st_relaxed_sys(peer_commit, off);          // dare_ibv_rc.c:1810
                 if (lane == 0) {
-                    st_relaxed_sys(&hw->commit_off, off);
-                    st_relaxed_sys(&hw->committed_tickets, tickets);        // releases proxy.c:160 spinners
+                    // {commit offset, committed tickets}: ONE 16 B store into pinned host memory -- this is what
+                    // releases the proxy.c:160 spinners; a 16 B host load sees a consistent pair
+                    st_relaxed_sys_2x64(&hw->commit_off, off, tickets);
                     st_relaxed_sys(&hw->consumed, tickets);                 // submission-ring space
+                    st_relaxed_sys(&hw->last_commit_ns, globaltimer_ns());
                     st_relaxed_sys(&seq->pub_tail, tail);                   // publish-ring space
                     // the leader's bookkeeping, in publish order (single writer)
                     hdr->commit = off;
@@ -444,6 +494,17 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
                 committed_tickets = tickets;
                 last_progress = globaltimer_ns();
                 __syncwarp();
+            }
+        }
+        // heartbeat (dare_ibv_rc.c:868-958: the leader writes its SID into every follower's ctrl_data.hb[]): the
+        // commit warp is the leader's liveness -- when the hosting process dies the context goes with it and the beats stop
+        if (cx->hb_period_ns && (++hb_spins & 0x1fu) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (now - last_hb >= cx->hb_period_ns) {
+                last_hb = now; hb_beat++;
+                if (lane < N && lane != me && cx->peer[lane])
+                    st_relaxed_sys(&reinterpret_cast<apus_ctrl_t *>(cx->peer[lane])->hb,
+                                   ((cx->term & 0xffffull) << APUS_PUB_TERM_SHIFT) | (hb_beat & APUS_PUB_CUM_MASK));
             }
         }
         const bool rec_ok = S_rec_ok;
@@ -519,7 +580,7 @@ __device__ __noinline__ void leader_prescan(const apus_devctx_t *__restrict__ cx
 // T2b (inside the place turn): place the next sub-tile of the fetched batch (entries kbase..nf) --
 // log_append_entry's offset rules, free-space rule E2 and the pruning rule, on the placement
 // state this CTA holds.  Kept short: everything state independent was done by leader_prescan.
-__device__ __noinline__ void leader_place(const apus_devctx_t *__restrict__ cx, LeaderShared *S, const apus_slot_t *sl, int lane)
+__device__ __noinline__ void leader_place(const apus_devctx_t *__restrict__ cx, LeaderShared *S, const apus_cslot_t *sl, int lane)
 {
     const int N = cx->group_size;
     apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_HDR_OFF);
@@ -631,6 +692,227 @@ __device__ __noinline__ void leader_place(const apus_devctx_t *__restrict__ cx, 
     }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Express path: ONE request, handled by warp 0 alone while the rest of the CTA stays parked at its barrier.
+// This is the closed-loop commit-latency path (proxy.c:108-161: an application thread enqueues one request and
+// spins until it is committed): slot already in registers (worker 0 polls the slot itself), placement state
+// cached from the previous request, the 64+len bytes composed in a 256 B scratch, pushed with one 16 B store per
+// chunk and follower, and published with a SELF-CERTIFYING record -- no system fence anywhere on the way.
+// The publish turn is then HELD (nobody is waiting for it) and handed on, after a fence, when somebody else claims.
+// Anything unusual (wrap, pruning due, payload in the byte ring, no room) returns 1: the tile machine takes the claim.
+// ---------------------------------------------------------------------------------
+struct Express {
+    uint64_t next_seq;                 // slot number right after my latest claim
+    uint64_t placed, end, tf, head;    // placement state I handed on under stamp next_seq
+    uint64_t pub_h;                    // publish-ring record number that goes with publish turn next_seq
+    uint32_t have_place;               // the four values above are what the sequencer records hold
+    uint32_t hold;                     // I still hold publish turn next_seq (self-certified data, not fenced yet)
+    uint64_t pub_tail_seen;            // publish-ring tail as last read (lane 0)
+};
+
+__device__ __forceinline__ void express_release(apus_seq_t *seq, Express &X, int lane)
+{
+    // the data of my self-certified publishes becomes ordinary fenced data before anybody else may publish behind it
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_system();
+        st_relaxed_sys_2x64(seq->pub_turn, X.next_seq, X.pub_h);
+    }
+    X.hold = 0;
+    __syncwarp();
+}
+
+__device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx, const LeaderShared *S, Express &X,
+                                              const uint64_t claimed, uint4 sv, const bool have_slot, uint8_t *scratch,
+                                              const int lane)
+{
+    const int N = cx->group_size, me = cx->idx;
+    const uint64_t L = cx->log_len;
+    apus_ctrl_t *ctrl = reinterpret_cast<apus_ctrl_t *>(cx->region);
+    apus_seq_t *seq = reinterpret_cast<apus_seq_t *>(cx->region + APUS_SEQ_OFF);
+    apus_pubrec_t *pubring = reinterpret_cast<apus_pubrec_t *>(cx->region + APUS_PUBRING_OFF);
+    apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_HDR_OFF);
+    uint8_t *entries = cx->region + cx->entries_off;
+    uint32_t *lindex = reinterpret_cast<uint32_t *>(cx->region + APUS_INDEX_OFF);
+    const uint64_t t_deq = globaltimer_ns();
+
+    if (!have_slot && lane < 8)
+        sv = ld_relaxed_sys_v4(reinterpret_cast<const uint8_t *>(cx->sub_slots + (claimed & cx->sub_mask)) + 16u * lane);
+    const uint32_t to = __shfl_sync(0xffffffffu, sv.z, 0), lw = __shfl_sync(0xffffffffu, sv.w, 0);
+    const uint32_t ty = (to >> APUS_SLOT_TYPE_SHIFT) & APUS_SLOT_TYPE_MASK, len = lw & 0xffffu, clt = lw >> 16;
+    const uint64_t req_id = (uint64_t)__shfl_sync(0xffffffffu, sv.x, 0) | ((uint64_t)__shfl_sync(0xffffffffu, sv.y, 0) << 32);
+    if (!has_cmd(ty) || (to & APUS_SLOT_EXT)) return 1;
+    const uint32_t es = APUS_HDR_BYTES + len, nb = 2u + len;
+
+    // loads that do not depend on the placement, all in flight together: the followers' ack counts (is everybody
+    // caught up?), the apply offsets (is the pruning rule due?), a head moved by the host
+    const bool isf = lane < N && lane != me && cx->peer[lane];
+    uint64_t ackv = 0, apv = 0;
+    if (isf) ackv = ld_relaxed_sys(&ctrl->ack[lane]);
+    if (lane < N) apv = (lane == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[lane]);
+    const uint64_t hh = ld_relaxed_sys(&hdr->head);
+
+    // ---- place turn ----
+    uint64_t placed = X.placed, end = X.end, tf = X.tf, headv = X.head;
+    if (!(X.have_place && X.next_seq == claimed)) {
+        uint32_t ab = 0;
+        if (lane == 0) {
+            uint64_t s0, s1, s2, s3;
+            uint32_t spins = 0;
+            for (;;) {
+                ld_relaxed_sys_2x64(seq->rec_placed, s0, placed);
+                ld_relaxed_sys_2x64(seq->rec_end, s1, end);
+                ld_relaxed_sys_2x64(seq->rec_tail, s2, tf);
+                ld_relaxed_sys_2x64(seq->rec_head, s3, headv);
+                if (s0 == claimed && s1 == claimed && s2 == claimed && s3 == claimed) break;
+                if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) { ab = 1; break; }
+            }
+        }
+        ab = __shfl_sync(0xffffffffu, ab, 0);
+        if (ab) return 2;
+        placed = __shfl_sync(0xffffffffu, placed, 0); end = __shfl_sync(0xffffffffu, end, 0);
+        tf = __shfl_sync(0xffffffffu, tf, 0); headv = __shfl_sync(0xffffffffu, headv, 0);
+        X.placed = placed; X.end = end; X.tf = tf; X.head = headv; X.have_place = 1; X.next_seq = claimed;
+    }
+    const bool wrapped = (tf & APUS_REC_WRAPPED) != 0, prevh = (tf & APUS_REC_PREV_HEAD) != 0;
+    if (end != L && ring_dist(hh, end, L) < ring_dist(headv, end, L)) headv = hh;
+    const uint64_t pos0 = (end == L) ? 0 : end;
+    const uint64_t used = (end == L) ? 0 : ring_dist(headv, end, L);
+    const bool autoprune = (cx->flags & APUS_FLAG_AUTOPRUNE) != 0;
+    const uint64_t reserve = autoprune ? APUS_HDR_BYTES : 0;
+    if (autoprune && end != L && used >= (L >> 2) && !prevh && L - pos0 >= APUS_HDR_BYTES) {
+        // the pruning rule of leader_place, evaluated by the whole warp; when it is due the tile machine appends the HEAD entry
+        uint64_t d = 0;
+        if (lane < N) { d = ring_dist(apv, end, L); if (d > used) d = used; }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) { const uint64_t o = __shfl_xor_sync(0xffffffffu, d, sft); d = o > d ? o : d; }
+        if (d == 0) d = ring_dist(tf & ~(APUS_REC_WRAPPED | APUS_REC_PREV_HEAD), end, L);
+        if (d <= used && used - d >= (L >> 3)) return 1;
+    }
+    if (pos0 + es > L || used + es + reserve >= L) return 1;          // wrap / no room: general placement
+
+    const uint64_t a = pos0, b = pos0 + es;
+    const uint64_t ne = (b == L) ? 0 : b;                             // rule E1
+    const bool nw = wrapped || b == L;
+    const uint64_t cum = placed + 1;
+    // hand the place turn on at once (stamp = next slot number) and remember what I wrote
+    if (lane == 0) {
+        st_relaxed_sys_2x64(seq->rec_placed, claimed + 1, cum);
+        st_relaxed_sys_2x64(seq->rec_end, claimed + 1, ne);
+        st_relaxed_sys_2x64(seq->rec_tail, claimed + 1, a | (nw ? APUS_REC_WRAPPED : 0ull));
+        st_relaxed_sys_2x64(seq->rec_head, claimed + 1, headv);
+    }
+    X.placed = cum; X.end = ne; X.tf = a | (nw ? APUS_REC_WRAPPED : 0ull); X.head = headv; X.have_place = 1;
+    const uint64_t idx = S->idx_base + placed + 1;
+
+    // ---- compose: prefill (holes keep what the log held), header, data image ----
+    const uint64_t a16 = a & ~15ull;
+    const uint32_t nch = (uint32_t)(((b + 15ull) & ~15ull) - a16) >> 4;          // <= 11
+    uint8_t *img = scratch, *xsl = scratch + 256;
+    if (lane < (int)nch)
+        reinterpret_cast<uint4 *>(img)[lane] = wrapped ? ld_relaxed_sys_v4(entries + a16 + 16ull * lane) : make_uint4(0, 0, 0, 0);
+    if (lane == 1 || lane == 2) reinterpret_cast<uint4 *>(xsl)[lane - 1] = sv;   // inline image bytes 0..31
+    if (lane >= 4 && lane <= 6) reinterpret_cast<uint4 *>(xsl)[lane - 2] = sv;   // ... 32..79
+    __syncwarp();
+    uint8_t *e = img + (a - a16);
+    group_write_header(e, lane, 32, idx, cx->term, req_id, clt, ty, me, false);
+    group_copy_smem(e + E_DATA, xsl, nb, lane, 32);
+    __syncwarp();
+
+    // ---- push: local log first, then every follower; checksum of exactly the bytes [a, b) ----
+    uint64_t cs = 0;
+    if (lane < (int)nch) {
+        const uint4 v = reinterpret_cast<const uint4 *>(img)[lane];
+        const uint64_t lo = a16 + 16ull * lane;
+        cs = cs_chunk(v, lo, a, b);
+        if (lo >= a && lo + 16 <= b) {
+            st_v4(entries + lo, v);
+#pragma unroll 1
+            for (int f = 0; f < N; f++)
+                if (S->peer_entries[f]) st_v4(S->peer_entries[f] + lo, v);
+        } else {
+#pragma unroll 1
+            for (uint32_t j = 0; j < 16; j++) {
+                const uint64_t o = lo + j;
+                if (o < a || o >= b) continue;
+                const uint32_t w = (j < 4) ? v.x : (j < 8) ? v.y : (j < 12) ? v.z : v.w;
+                const uint32_t byte = (w >> (8 * (j & 3))) & 0xff;
+                st_u8(entries + o, byte);
+#pragma unroll 1
+                for (int f = 0; f < N; f++)
+                    if (S->peer_entries[f]) st_u8(S->peer_entries[f] + o, byte);
+            }
+        }
+    }
+    if (lane == 31) {
+        const uint32_t at = (uint32_t)cum & cx->idx_mask;
+        lindex[at] = (uint32_t)a;
+#pragma unroll 1
+        for (int f = 0; f < N; f++)
+            if (S->peer_index[f]) S->peer_index[f][at] = (uint32_t)a;
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, sft);
+    // self-certify only when every follower has acked everything before this entry: each of them is then at
+    // exactly `a` and can verify the one entry; a follower that lags is served by a fenced publish (it may skip records)
+    const bool caught = __ballot_sync(0xffffffffu, isf && ackv != placed) == 0;
+
+    // ---- publish turn (mine already when I held it) ----
+    uint64_t h = X.pub_h;
+    if (!X.hold) {
+        uint32_t ab = 0;
+        if (lane == 0) {
+            uint64_t sq;
+            uint32_t spins = 0;
+            for (;;) {
+                ld_acquire_gpu_2x64(seq->pub_turn, sq, h);
+                if (sq == claimed) break;
+                if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) { ab = 1; break; }
+            }
+        }
+        ab = __shfl_sync(0xffffffffu, ab, 0);
+        if (ab) return 2;
+        h = __shfl_sync(0xffffffffu, h, 0);
+    }
+    if (lane == 0) {
+        uint32_t spins = 0;
+        while (h - X.pub_tail_seen >= APUS_PUBRING_RECORDS - 2) {
+            X.pub_tail_seen = ld_relaxed_sys(&seq->pub_tail);
+            if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
+        }
+    }
+    __syncwarp();
+    const uint64_t cumt = cum | ((cx->term & 0xffffull) << APUS_PUB_TERM_SHIFT);
+    const bool cert = caught && !(cx->flags & APUS_FLAG_NO_EXPRESS);
+    if (isf) {
+        apus_ctrl_t *pc = reinterpret_cast<apus_ctrl_t *>(cx->peer[lane]);
+        if (cert) {
+            st_relaxed_sys_2x64(&pc->pub_csum, cs + cs_key(cumt), a);
+            st_relaxed_sys_2x64(&pc->pub_end, ne | APUS_PUB_CERT, cumt);
+        } else {
+            __threadfence_system();                                  // data before tail (I1), the classic way
+            st_relaxed_sys_2x64(&pc->pub_end, ne, cumt);
+        }
+    }
+    if (lane >= 16 && lane < 24) {
+        const int q = lane - 16;
+        const uint64_t val = q == PR_CUM ? cum : q == PR_END ? ne : q == PR_TICKETS ? claimed + 1
+                           : q == PR_T0 ? t_deq : q == PR_TAIL ? a : q == PR_HWM ? (nw ? L : b)
+                           : q == PR_NEXTIDX ? idx + 1 : (uint64_t)es * (uint64_t)(N - 1);
+        st_relaxed_sys_2x64(&pubring[h & PUBMASK].w[2 * q], h + 1, val);
+    }
+    X.next_seq = claimed + 1; X.pub_h = h + 1;
+    if (cert) {
+        X.hold = 1;                    // nobody is waiting: keep the turn, skip the fence
+    } else {
+        X.hold = 0;
+        __syncwarp();
+        if (lane == 0) st_relaxed_sys_2x64(seq->pub_turn, claimed + 1, h + 1);
+    }
+    return 0;
+}
+
 __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t wid)
 {
     LeaderShared *S = reinterpret_cast<LeaderShared *>(smem_raw);
@@ -652,7 +934,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
         if (wid == 0) {
             seq->claimed_slots = ctrl->consumed;
             seq->doorbell = ctrl->consumed;
-            seq->place_seq = 0; seq->workers_done = 0; seq->abort_flag = 0;
+            seq->place_seq = 0; seq->workers_done = 0; seq->abort_flag = 0; seq->w0_idle = 0;
             for (uint32_t i = 0; i < APUS_PUBRING_RECORDS; i++)
                 for (int q = 0; q < 8; q++) pubring[i].w[2 * q] = 0;          // no valid record
             // the turns are stamped with slot numbers: the first claim of this launch starts at ctrl->consumed
@@ -670,7 +952,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
         } else {
             while (ld_acquire_gpu(&seq->ready_epoch) != cx->epoch) { }
         }
-        S->finish = 0; S->avg_es = 128; S->avg_xb = 0; S->pub_tail_seen = 0; S->ap_valid = 0;
+        S->finish = 0; S->abort = 0; S->avg_es = 128; S->avg_xb = 0; S->pub_tail_seen = 0; S->ap_valid = 0;
         S->idx_base = ctrl->next_idx - 1 - ctrl->published;
         for (int i = 0; i < APUS_MAX_SERVERS; i++) {
             S->peer_entries[i] = (i < N && i != me && cx->peer[i]) ? cx->peer[i] + cx->entries_off : nullptr;
@@ -688,7 +970,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             uint32_t spins = 0;
             for (;;) {
                 const uint64_t t = ld_acquire_sys(cx->sub_tail);
-                if (t != last) { st_relaxed_sys(&seq->doorbell, t); last = t; }
+                if (t != last) { st_release_gpu(&seq->doorbell, t); last = t; }   // slots were written before the doorbell
                 if ((++spins & 0x3fu) == 0 &&
                     (ld_relaxed_sys(&seq->abort_flag) || ld_relaxed_sys(&seq->workers_done) >= cx->n_workers)) break;
             }
@@ -702,56 +984,113 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
     uint64_t ph[8], tn[8], tprev = globaltimer_ns();
     for (int i = 0; i < 8; i++) { ph[i] = ctrl->phase_ns[i]; tn[i] = ctrl->turn_ns[i]; }
 #define PHASE(i) do { if (prof) { const uint64_t _t = globaltimer_ns(); ph[i] += _t - tprev; tprev = _t; } } while (0)
+    Express X;
+    X.next_seq = 0; X.placed = 0; X.end = 0; X.tf = 0; X.head = 0; X.pub_h = 0; X.have_place = 0; X.hold = 0; X.pub_tail_seen = 0;
+    uint64_t xguess = ctrl->consumed;          // worker 0: the slot it expects to be claimed next
 
     for (;;) {
         // ---- T0: claim the next slots of the submission ring: lock-free, one compare-and-swap on the
         //      claimed-slots counter.  The claimed range [slot0, slot0+n) is also the worker's place in
         //      the order: the place and publish turns are stamped with slot numbers ----
-        if (tid == 0) {
+        if (warp == 0) {
             uint32_t n = 0, fin = 0, spins = 0;
             const uint64_t tw0 = prof ? globaltimer_ns() : 0;
             uint64_t claimed = 0;
+            const bool poll_slot = cx->slot_poll != 0 && wid == 0;
+            const bool express_on = (cx->flags & APUS_FLAG_NO_EXPRESS) == 0;
+            if (wid == 0 && lane == 0) st_relaxed_sys(&seq->w0_idle, 1);
             for (;;) {
-                if (ld_relaxed_sys(&seq->abort_flag)) { fin = 1; break; }
-                claimed = ld_relaxed_sys(&seq->claimed_slots);
-                if (claimed >= cx->target) { fin = 1; break; }
-                // slots + payload were written before the doorbell (read directly, or through the relay's mirror)
-                const uint64_t t = cx->doorbell_relay ? ld_relaxed_sys(&seq->doorbell) : ld_acquire_sys(cx->sub_tail);
-                uint64_t avail = t - claimed;
-                if (t > claimed) {
+                // worker 0 polls the NEXT SLOT itself (lanes 0..7, one 128 B read over PCIe) while lane 0 looks at the
+                // claim counter and the doorbell: a lone request is in registers one PCIe round trip after the host wrote it
+                uint4 sv = make_uint4(0, 0, 0, 0);
+                if (poll_slot && lane < 8)
+                    sv = ld_relaxed_sys_v4(reinterpret_cast<const uint8_t *>(cx->sub_slots + (xguess & cx->sub_mask)) + 16u * lane);
+                uint32_t ctl = 0;
+                uint64_t t = 0, w0i = 0;
+                if (lane == 0) {
+                    if (ld_relaxed_sys(&seq->abort_flag)) ctl = 1;
+                    claimed = ld_relaxed_sys(&seq->claimed_slots);
+                    if (claimed >= cx->target) ctl = 1;
+                    // slots + payload were written before the doorbell (read directly, or through the relay's mirror)
+                    t = cx->doorbell_relay ? ld_acquire_gpu(&seq->doorbell) : ld_acquire_sys(cx->sub_tail);
+                    if (wid != 0) w0i = ld_relaxed_sys(&seq->w0_idle);
+                }
+                ctl = __shfl_sync(0xffffffffu, ctl, 0);
+                claimed = __shfl_sync(0xffffffffu, claimed, 0);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                w0i = __shfl_sync(0xffffffffu, w0i, 0);
+                // a held publish turn is passed on as soon as anybody else has claimed slots (or I am leaving)
+                if (X.hold && (ctl || claimed != X.next_seq)) express_release(seq, X, lane);
+                if (ctl) { fin = 1; break; }
+                bool slot_ok = false;
+                if (poll_slot) {
+                    const uint64_t stamp = (uint64_t)sv.x | ((uint64_t)sv.y << 32);
+                    slot_ok = (__ballot_sync(0xffffffffu, (lane == 3 || lane == 7) && stamp == xguess + 1) == 0x88u) && xguess == claimed;
+                    xguess = claimed;
+                }
+                uint64_t avail = t > claimed ? t - claimed : 0;
+                if (slot_ok && avail == 0) avail = 1;
+                // lone requests belong to worker 0 while it is polling (express path)
+                if (avail == 1 && wid != 0 && w0i) avail = 0;
+                if (avail) {
                     const uint64_t room = cx->target - claimed;
                     if (avail > room) avail = room;
-                    // share a shallow queue between the workers instead of one big tile
-                    uint64_t want = (avail + cx->n_workers - 1) / cx->n_workers;
-                    if (want < 32) want = avail < 32 ? avail : 32;
-                    // a claim should fit ONE tile image / staging buffer (else it is placed in pieces
-                    // while holding the place turn, which serializes the workers)
-                    uint64_t aes = ld_relaxed_sys(&seq->avg_es), axb = ld_relaxed_sys(&seq->avg_xb);
-                    if (aes < 64) aes = 128;
-                    uint64_t fit = (APUS_LEADER_IMG_BYTES - 256u) / aes;
-                    if (axb) { const uint64_t xf = APUS_LEADER_EXT_BYTES / axb; if (xf < fit) fit = xf; }
-                    if (fit < 1) fit = 1;
-                    if (want > fit) want = fit;
-                    const uint32_t nn = want > MAXB ? MAXB : (uint32_t)want;
-                    if (atomicCAS(reinterpret_cast<unsigned long long *>(&seq->claimed_slots), (unsigned long long)claimed,
-                                  (unsigned long long)(claimed + nn)) == (unsigned long long)claimed) {
-                        n = nn;
-                        break;
+                    uint32_t nn = 0, won = 0;
+                    if (lane == 0) {
+                        // share a shallow queue between the workers instead of one big tile
+                        uint64_t want = (avail + cx->n_workers - 1) / cx->n_workers;
+                        if (want < 32) want = avail < 32 ? avail : 32;
+                        // a claim should fit ONE tile image / staging buffer (else it is placed in pieces
+                        // while holding the place turn, which serializes the workers)
+                        uint64_t aes = ld_relaxed_sys(&seq->avg_es), axb = ld_relaxed_sys(&seq->avg_xb);
+                        if (aes < 64) aes = 128;
+                        uint64_t fit = (APUS_LEADER_IMG_BYTES - 256u) / aes;
+                        if (axb) { const uint64_t xf = APUS_LEADER_EXT_BYTES / axb; if (xf < fit) fit = xf; }
+                        if (fit < 1) fit = 1;
+                        if (want > fit) want = fit;
+                        nn = want > MAXB ? MAXB : (uint32_t)want;
+                        won = atomicCAS(reinterpret_cast<unsigned long long *>(&seq->claimed_slots), (unsigned long long)claimed,
+                                        (unsigned long long)(claimed + nn)) == (unsigned long long)claimed;
                     }
-                    continue;      // somebody else took these slots: look again
+                    nn = __shfl_sync(0xffffffffu, nn, 0);
+                    won = __shfl_sync(0xffffffffu, won, 0);
+                    if (!won) continue;                   // somebody else took these slots: look again
+                    if (nn == 1 && express_on) {
+                        const int rc = leader_express(cx, S, X, claimed, sv, slot_ok, img, lane);
+                        if (rc == 0) {
+                            xguess = claimed + 1; last_progress = globaltimer_ns();
+                            if (prof) { tn[5]++; ph[7]++; }
+                            continue;
+                        }
+                        if (rc == 2) { fin = 1; break; }
+                        // rc == 1: the tile machine places this claim; the cached placement state is still what the records hold
+                    }
+                    n = nn;
+                    break;
                 }
                 if ((++spins & 0xffu) == 0) {
-                    if (ld_relaxed_sys_u32(&hw->stop)) { fin = 1; break; }
-                    if (cx->target != ~0ull && globaltimer_ns() - last_progress > WATCHDOG_NS) {
-                        st_relaxed_sys(&hw->error, APUS_KERR_WATCHDOG_LEADER);
-                        st_relaxed_sys(&seq->abort_flag, 1); fin = 1; break;
+                    uint32_t stopf = 0;
+                    if (lane == 0) {
+                        if (ld_relaxed_sys_u32(&hw->stop)) stopf = 1;
+                        else if (cx->target != ~0ull && globaltimer_ns() - last_progress > WATCHDOG_NS) {
+                            st_relaxed_sys(&hw->error, APUS_KERR_WATCHDOG_LEADER);
+                            st_relaxed_sys(&seq->abort_flag, 1); stopf = 1;
+                        }
+                        if (prof) for (int i = 0; i < 8; i++) { ctrl->phase_ns[i] = ph[i]; ctrl->turn_ns[i] = tn[i]; }
                     }
+                    stopf = __shfl_sync(0xffffffffu, stopf, 0);
+                    if (stopf) { fin = 1; break; }
                 }
             }
-            if (prof) { tn[0] += globaltimer_ns() - tw0; tn[6]++; }
-            if (n) { S->slot0 = claimed; S->my_seq = claimed; }
-            S->n_fetch = n; S->finish = fin;
-            S->t_dequeue = globaltimer_ns();
+            if (X.hold) express_release(seq, X, lane);
+            X.have_place = 0;                                  // other workers may place in between
+            if (lane == 0) {
+                if (wid == 0) st_relaxed_sys(&seq->w0_idle, 0);
+                if (prof) { tn[0] += globaltimer_ns() - tw0; tn[6]++; }
+                if (n) { S->slot0 = claimed; S->my_seq = claimed; }
+                S->n_fetch = n; S->finish = fin;
+                S->t_dequeue = globaltimer_ns();
+            }
         }
         bar_sync(1, NT);
         if (S->finish) break;
@@ -776,7 +1115,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             for (int sft = 16; sft > 0; sft >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, sft); sx += __shfl_xor_sync(0xffffffffu, sx, sft); }
             if (lane == 0) { st_relaxed_sys(&seq->avg_es, (se + nf - 1) / nf); st_relaxed_sys(&seq->avg_xb, (sx + nf - 1) / nf); }
         }
-        const apus_slot_t *sl = reinterpret_cast<const apus_slot_t *>(slots);
+        const apus_cslot_t *sl = reinterpret_cast<const apus_cslot_t *>(slots);
         bool have_pub_turn = false, have_place_turn = false, aborted = false;
         uint64_t gap_bytes = 0;      // bytes of a wrap gap replicated ahead of the next publish
 
@@ -811,9 +1150,11 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                             ld_relaxed_sys_2x64(seq->rec_tail, s2, tf);
                             ld_relaxed_sys_2x64(seq->rec_head, s3, headv);
                             if (s0 == S->my_seq && s1 == S->my_seq && s2 == S->my_seq && s3 == S->my_seq) break;
-                            if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
+                            if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) { S->abort = 1; break; }
                         }
                         if (prof) { tn[1] += globaltimer_ns() - tw0; S->t_place_acq = globaltimer_ns(); }
+                        if (S->abort) { S->fast = 1; S->blocked = 0; goto place_done; }   // no stamp: nothing may be placed
+                        {
                         const uint64_t L = cx->log_len;
                         const bool wrapped = (tf & APUS_REC_WRAPPED) != 0, prevh = (tf & APUS_REC_PREV_HEAD) != 0;
                         const uint64_t tail = tf & ~(APUS_REC_WRAPPED | APUS_REC_PREV_HEAD);
@@ -876,6 +1217,8 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                             S->fast = 0;
                             if (prof) tn[4]++;
                         }
+                        }
+                    place_done:;
                     }
                     __syncwarp();
                     placed_fast = S->fast != 0;
@@ -902,6 +1245,9 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             have_place_turn = true;
             bar_sync(1, NT);
             PHASE(2);
+            // stop / watchdog while waiting for a turn: this worker holds no valid placement -- it must not hand a turn
+            // on, store a byte or publish (a stale placement would overwrite entries that are already acked)
+            if (S->abort) { aborted = true; break; }
             if (S->blocked) {   // no space before head: poll again
                 if (tid == 0) {
                     if (ld_relaxed_sys_u32(&hw->stop) || ld_relaxed_sys(&seq->abort_flag)) { st_relaxed_sys(&seq->abort_flag, 1); S->finish = 1; }
@@ -1039,9 +1385,10 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         const uint64_t tw0 = prof ? globaltimer_ns() : 0;
                         uint64_t sq, h;
                         for (;;) {
-                            ld_relaxed_sys_2x64(seq->pub_turn, sq, h);
+                            // acquire: a predecessor that published self-certified data fenced it before this hand-over
+                            ld_acquire_gpu_2x64(seq->pub_turn, sq, h);
                             if (sq == S->my_seq) break;
-                            if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
+                            if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) { S->abort = 1; break; }
                         }
                         if (prof) tn[2] += globaltimer_ns() - tw0;
                         S->pub_h = h;
@@ -1049,17 +1396,18 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     // room in the publish ring (the commit warp drains it); the tail is re-read only when the
                     // last value seen would not leave room
                     uint32_t spins = 0;
-                    while (S->pub_h - S->pub_tail_seen >= APUS_PUBRING_RECORDS - 2) {
+                    while (!S->abort && S->pub_h - S->pub_tail_seen >= APUS_PUBRING_RECORDS - 2) {
                         S->pub_tail_seen = ld_relaxed_sys(&seq->pub_tail);
-                        if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) break;
+                        if ((++spins & 0x3ffu) == 0 && ld_relaxed_sys(&seq->abort_flag)) { S->abort = 1; break; }
                     }
                 }
                 __syncwarp();
-                if (pubs) {
+                const bool pub_ok = S->abort == 0;
+                if (pubs && pub_ok) {
                     apus_ctrl_t *pc = reinterpret_cast<apus_ctrl_t *>(cx->peer[lane]);
-                    st_relaxed_sys_2x64(&pc->pub_end, S->new_end, S->cum_after);
+                    st_relaxed_sys_2x64(&pc->pub_end, S->new_end, S->cum_after | ((cx->term & 0xffffull) << APUS_PUB_TERM_SHIFT));
                 }
-                if (lane >= 16 && lane < 24) {
+                if (pub_ok && lane >= 16 && lane < 24) {
                     const int q = lane - 16;
                     const uint64_t h = S->pub_h;
                     const uint64_t val = q == PR_CUM ? S->cum_after : q == PR_END ? S->new_end : q == PR_TICKETS ? S->slot0 + kbase + m
@@ -1068,7 +1416,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     st_relaxed_sys_2x64(&pubring[h & PUBMASK].w[2 * q], h + 1, val);
                 }
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && pub_ok) {
                     S->pub_h += 1;
                     if (S->last) st_relaxed_sys_2x64(seq->pub_turn, S->my_seq + S->n_fetch, S->pub_h);
                     S->kbase = kbase + m;
@@ -1078,6 +1426,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             gap_bytes = 0;
             last_progress = globaltimer_ns();
             bar_sync(1, NT);
+            if (S->abort) { aborted = true; break; }
             if (prof) {
                 PHASE(6); ph[7]++;
                 for (int i = 0; i < 8; i++) { ctrl->phase_ns[i] = ph[i]; ctrl->turn_ns[i] = tn[i]; }
@@ -1117,35 +1466,100 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
     uint64_t last_progress = globaltimer_ns();
     uint32_t spins = 0;
 
+    const uint64_t myterm16 = cx->term & 0xffffull;
+    const bool host_apply = (cx->flags & APUS_FLAG_HOST_APPLY) != 0;
+    uint64_t host_applied = hdr->apply;  // HOST_APPLY: the offset the application has replayed (what the leader may prune behind)
+    uint64_t last_hb = ld_relaxed_sys(&ctrl->hb), last_hb_t = globaltimer_ns();
+    bool suspected = false;
+
     for (;;) {
-        if (tid == 0) {
-            uint64_t e, cum, c;
-            uint32_t done = 0;
+        if (tid < 32) {
+            // warp 0 polls: lane 0 the tail publish {end, entries|term} (one 16 B acquire load), lane 1 its certificate half,
+            // lane 2 the commit offset, lane 3 the heartbeat word
+            const int lane = tid;
+            uint64_t e = 0, cumt = 0, c = 0, cert_start = 0;
+            uint32_t done = 0, is_cert = 0;
             for (;;) {
-                ld_acquire_sys_2x64(&ctrl->pub_end, e, cum);        // {end, entries} written as one 16 B store
-                c = ld_relaxed_sys(&hdr->commit);
-                const bool new_entries = cum > acked;
+                uint64_t x0 = 0, x1 = 0;
+                if (lane == 0) ld_acquire_sys_2x64(&ctrl->pub_end, x0, x1);
+                else if (lane == 1) ld_relaxed_sys_2x64(&ctrl->pub_csum, x0, x1);
+                else if (lane == 2) x0 = ld_relaxed_sys(&hdr->commit);
+                else if (lane == 3) x0 = ld_relaxed_sys(&ctrl->hb);
+                e = __shfl_sync(0xffffffffu, x0, 0); cumt = __shfl_sync(0xffffffffu, x1, 0);
+                const uint64_t csum = __shfl_sync(0xffffffffu, x0, 1);
+                cert_start = __shfl_sync(0xffffffffu, x1, 1);
+                c = __shfl_sync(0xffffffffu, x0, 2);
+                const uint64_t hbw = __shfl_sync(0xffffffffu, x0, 3);
+                // term fence: a publish stamped with another term (a deposed leader still storing) is not looked at
+                uint64_t cum = cumt & APUS_PUB_CUM_MASK;
+                if ((cumt >> APUS_PUB_TERM_SHIFT) != myterm16) cum = 0;
+                is_cert = (e & APUS_PUB_CERT) ? 1u : 0u;
+                e &= ~APUS_PUB_CERT;
+                bool new_entries = cum > acked;
+                if (new_entries && is_cert) {
+                    // self-certifying publish of ONE entry at cert_start: the bytes may still be in flight -- read them back
+                    // from my own HBM until they add up to the certificate
+                    const uint64_t a = cert_start, b = (e == 0) ? L : e;
+                    bool ok = cum == acked + 1 && a == ((old_end == L) ? 0 : old_end) && b > a && b - a <= 32u * 16u - 16u;
+                    if (ok) {
+                        const uint64_t a16 = a & ~15ull;
+                        const uint32_t nch = (uint32_t)(((b + 15ull) & ~15ull) - a16) >> 4;
+                        uint64_t cs = 0;
+                        if (lane < (int)nch) cs = cs_chunk(ld_relaxed_sys_v4(entries + a16 + 16ull * lane), a16 + 16ull * lane, a, b);
+#pragma unroll
+                        for (int sft = 16; sft > 0; sft >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, sft);
+                        ok = (cs + cs_key(cumt)) == csum;
+                    }
+                    if (!ok) new_entries = false;          // not there yet (or not verifiable: a fenced publish will follow)
+                }
                 // commit moved, and I hold entries beyond what I applied
                 const bool new_commit = (c != applied) && (old_end != L) && (applied != old_end);
-                if (new_entries || new_commit) break;
+                if (new_entries || new_commit) { cumt = cum; break; }
                 // bounded launch: the leader says how many entries exist in total
-                if (cx->target != ~0ull && ld_acquire_sys(&ctrl->fin_target) == cx->target) {
-                    const uint64_t fe = ld_relaxed_sys(&ctrl->fin_entries);
-                    if (acked >= fe && (old_end == L || (applied == old_end && c == old_end))) { done = 1; break; }
-                }
-                if ((++spins & 0xffu) == 0) {
-                    if (ld_relaxed_sys_u32(&hw->stop)) { done = 1; break; }
-                    if (cx->target != ~0ull && globaltimer_ns() - last_progress > WATCHDOG_NS) {
-                        st_relaxed_sys(&hw->error, APUS_KERR_WATCHDOG_FOLLOWER);
-                        done = 1; break;
+                if (cx->target != ~0ull) {
+                    uint64_t ft = 0;
+                    if (lane == 0) ft = ld_acquire_sys(&ctrl->fin_target);
+                    ft = __shfl_sync(0xffffffffu, ft, 0);
+                    if (ft == cx->target) {
+                        const uint64_t fe = ld_relaxed_sys(&ctrl->fin_entries);
+                        if (acked >= fe && (old_end == L || (applied == old_end && c == old_end))) { done = 1; cumt = acked; break; }
                     }
                 }
+                if (hbw != last_hb) { last_hb = hbw; last_hb_t = globaltimer_ns(); if (lane == 0) st_relaxed_sys(&hw->hb_seen, hbw); }
+                if ((++spins & 0xffu) == 0) {
+                    uint32_t stopf = 0;
+                    uint64_t ha = host_applied;
+                    if (lane == 0) {
+                        if (ld_relaxed_sys_u32(&hw->stop)) stopf = 1;
+                        else if (cx->target != ~0ull && globaltimer_ns() - last_progress > WATCHDOG_NS) {
+                            st_relaxed_sys(&hw->error, APUS_KERR_WATCHDOG_FOLLOWER);
+                            stopf = 1;
+                        }
+                        // failure detector (hb_receive_cb, dare_server.c:866-993): the leader's beats stopped
+                        if (cx->hb_timeout_ns && !suspected && globaltimer_ns() - last_hb_t > cx->hb_timeout_ns)
+                            st_relaxed_sys(&hw->leader_suspect, 1 + cx->term);
+                        if (host_apply) ha = ld_relaxed_sys(&hw->host_apply);
+                    }
+                    if (cx->hb_timeout_ns && globaltimer_ns() - last_hb_t > cx->hb_timeout_ns) suspected = true;
+                    stopf = __shfl_sync(0xffffffffu, stopf, 0);
+                    ha = __shfl_sync(0xffffffffu, ha, 0);
+                    if (host_apply && ha != host_applied) {
+                        // apply_committed_entries advances `apply` only after do_action (dare_server.c:1939-1962): what this
+                        // replica reports to the leader's pruning rule is what the HOST has replayed
+                        host_applied = ha;
+                        if (lane == 0) { hdr->apply = ha; st_relaxed_sys(&lctrl->apply_off[me], ha); }
+                    }
+                    if (stopf) { done = 1; cumt = acked; break; }
+                }
             }
-            // early ack: the tail publish was observed with acquire semantics, so every entry up
-            // to it is resident and visible here (invariant I2); the reply bytes follow behind
-            // the ack word unless APUS_F_FENCED_ACK asks for them first
-            if (!done && !fenced && cum > acked) st_relaxed_sys(&lctrl->ack[me], cum);
-            S->end_seen = e; S->cum_seen = cum; S->commit_seen = c; S->done = done;
+            // early ack: the tail publish was observed with acquire semantics (or its certificate verified), so every
+            // entry up to it is resident and visible here (invariant I2); the reply bytes follow behind the ack word
+            // unless APUS_F_FENCED_ACK asks for them first
+            if (lane == 0) {
+                if (!done && !fenced && cumt > acked) st_relaxed_sys(&lctrl->ack[me], cumt);
+                S->end_seen = e; S->cum_seen = cumt; S->commit_seen = c; S->done = done;
+                S->cert = (cumt > acked) ? is_cert : 0u; S->cert_start = cert_start;
+            }
         }
         __syncthreads();
         if (S->done) break;
@@ -1158,7 +1572,8 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
             if (tid == 0) S->head_j = 0;
             __syncthreads();
             for (uint64_t j = tid; j < n; j += nthr) {
-                const uint32_t w = ld_relaxed_sys_u32(&index[(uint32_t)(acked + 1 + j) & cx->idx_mask]);
+                // (a self-certified publish names its one entry itself: its index word may still be in flight)
+                const uint32_t w = S->cert ? (uint32_t)S->cert_start : ld_relaxed_sys_u32(&index[(uint32_t)(acked + 1 + j) & cx->idx_mask]);
                 const uint64_t at = (uint64_t)(w & ~APUS_IDX_HEAD_FLAG) + E_REPLY + (uint64_t)me;
                 st_relaxed_sys_u8(entries + at, 1);         // reply[me] = 1 in my copy and in the
                 st_relaxed_sys_u8(lentries + at, 1);        // leader's (dare_ibv_rc.c:1833-1854)
@@ -1303,10 +1718,12 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
                 }
                 applied = to;
                 if (tid == 0) {
-                    hdr->apply = applied;               // host-side apply (do_action) drains behind this
-                    st_relaxed_sys(&lctrl->apply_off[me], applied);
-                    st_relaxed_sys(&hw->commit_off, applied);
-                    st_relaxed_sys(&hw->committed_tickets, acked);
+                    if (!host_apply) {
+                        hdr->apply = applied;           // library use: nothing replays the log on the host
+                        st_relaxed_sys(&lctrl->apply_off[me], applied);
+                    }
+                    // the host may replay [its apply, applied): everything before `applied` is committed and held here
+                    st_relaxed_sys_2x64(&hw->commit_off, applied, acked);
                 }
                 last_progress = globaltimer_ns();
             }

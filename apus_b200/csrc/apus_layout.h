@@ -97,9 +97,15 @@ typedef struct apus_ctrl {
     uint64_t fin_entries;        /* end of a launch: entries the leader has published in total */
     uint64_t fin_target;         /* ... and the launch (its ticket target) this refers to */
     uint64_t pad1[14];
-    uint64_t pub_end;            /* tail publish: the follower's new `end` (dare_ibv_rc.c:1549-1573) ... */
-    uint64_t pub_cum;            /* ... and the entries that exist up to it; one 16 B store */
-    uint64_t pad2[14];
+    uint64_t pub_end;            /* tail publish: the follower's new `end` (dare_ibv_rc.c:1549-1573) | APUS_PUB_CERT ... */
+    uint64_t pub_cum;            /* ... and the entries that exist up to it | term << 48; one 16 B store */
+    uint64_t pub_csum;           /* self-certifying publish (APUS_PUB_CERT): checksum of the bytes [start, end), keyed
+                                    with pub_cum ... */
+    uint64_t pub_start;          /* ... and the offset of the (single) entry; one 16 B store, NO fence before either */
+    uint64_t pad2[4];
+    uint64_t hb;                 /* leader -> follower heartbeat: term << 48 | beat counter (dare_ibv_rc.c:868-958 writes
+                                    the leader's SID into ctrl_data.hb[]); its own 64 B half line */
+    uint64_t pad3[7];
     /* --- leader profiling (APUS_F_DEVICE_STATS): ns spent per phase of the tile loop --- */
     uint64_t phase_ns[8];        /* [0] wait for requests, [1..6] T1..T6, [7] tiles */
     uint64_t turn_ns[8];         /* worker 0: [0] claim-lock wait, [1] place-turn wait, [2] publish-turn wait (ns),
@@ -133,7 +139,8 @@ typedef struct apus_seq {
                                     kept across launches) */
     uint64_t doorbell;           /* device-memory mirror of a host-mapped doorbell, kept by ONE relay warp so that
                                     idle workers do not all poll over PCIe */
-    uint64_t pad_i[5];
+    uint64_t w0_idle;            /* worker 0 is polling the next slot: it takes lone requests (express path) */
+    uint64_t pad_i[4];
 } apus_seq_t;
 #define APUS_REC_PREV_HEAD (1ull << 62)   /* the last placed entry is a HEAD entry of the pruning rule */
 #define APUS_REC_WRAPPED   (1ull << 63)   /* the ring has wrapped at least once (no fresh bytes left) */
@@ -155,10 +162,15 @@ typedef struct apus_pubrec {
 
 /* submission slot, 128 B: the fields of tailq_entry_t (message.h:11-17).  Requests
  * whose data image (sm_cmd_t {u16 len; cmd[]}, dare_cid_t or head offset) is at most
- * 112 B travel inline, so that one coalesced read brings descriptor and payload;
- * larger images live in the payload byte ring at pay_off16 * 16. */
+ * 80 B travel inline, so that one coalesced read brings descriptor and payload;
+ * larger images live in the payload byte ring at pay_off16 * 16.
+ * Each 64 B half carries the slot's ticket number as a stamp, written LAST by the host: a
+ * cache line is read as one snapshot, so a half whose stamp matches is complete.  The leader
+ * can therefore poll the slot itself -- ONE PCIe round trip from "host wrote the request" to
+ * "request in registers" instead of doorbell-then-fetch. */
 #define APUS_SLOT_BYTES   128u
-#define APUS_SLOT_INLINE  112u
+#define APUS_SLOT_INLINE  80u
+#define APUS_CSLOT_BYTES  96u     /* a slot as the leader keeps it in shared memory: descriptor + inline image */
 #define APUS_SLOT_OFF_MASK 0x00ffffffu
 #define APUS_SLOT_TYPE_SHIFT 24
 #define APUS_SLOT_TYPE_MASK 0x1fu
@@ -169,27 +181,50 @@ typedef struct apus_slot {
     uint32_t type_off;           /* WRAP | EXT | type << 24 | payload offset in 16 B units */
     uint16_t len;                /* cmd length (CSM-like) */
     uint16_t clt_id;             /* connection_id */
-    uint8_t  inl[APUS_SLOT_INLINE];
+    uint8_t  inl0[32];           /* image bytes 0..31 */
+    uint64_t stamp0, rsv0;       /* ticket number (1-based position in the submission order) */
+    uint8_t  inl1[48];           /* image bytes 32..79 */
+    uint64_t stamp1, rsv1;
 } apus_slot_t;
+/* the same slot without its stamp chunks (shared memory of the leader) */
+typedef struct apus_cslot {
+    uint64_t req_id;
+    uint32_t type_off;
+    uint16_t len;
+    uint16_t clt_id;
+    uint8_t  inl[APUS_SLOT_INLINE];
+} apus_cslot_t;
 
 /* words in pinned, mapped host memory shared with the kernels */
 typedef struct apus_hostwords {
     volatile uint64_t sub_tail;          /* host -> kernel doorbell (RING_HOST_MAPPED) */
     uint64_t pad0[15];
-    volatile uint64_t committed_tickets; /* kernel -> host */
+    volatile uint64_t commit_off;        /* kernel -> host: {commit offset, committed tickets} is ONE 16 B store, */
+    volatile uint64_t committed_tickets; /* ... so a 16 B host load sees a consistent pair */
     volatile uint64_t consumed;          /* kernel -> host (ring space) */
-    volatile uint64_t commit_off;
-    uint64_t pad1[13];
+    volatile uint64_t last_commit_ns;    /* kernel -> host: %globaltimer of the latest commit */
+    uint64_t pad1[12];
     volatile uint32_t stop;              /* host -> kernel */
     uint32_t pad2[31];
+    volatile uint64_t host_apply;        /* host -> follower kernel (APUS_FLAG_HOST_APPLY): offset up to which the
+                                            application has replayed the log (dare_server.c:1939-1962) */
+    uint64_t pad3[15];
     volatile uint64_t heartbeat;         /* kernel liveness (debug) */
     volatile uint64_t error;             /* kernel-detected protocol error code */
+    volatile uint64_t leader_suspect;    /* follower kernel -> host: 1 + term whose leader stopped sending heartbeats */
+    volatile uint64_t hb_seen;           /* follower kernel -> host: last heartbeat word observed */
 } apus_hostwords_t;
 
 #define APUS_FLAG_FENCED_ACK 0x1u
 #define APUS_FLAG_STATS      0x2u
 #define APUS_FLAG_AUTOPRUNE  0x4u
 #define APUS_FLAG_WALK       0x8u   /* follower parses the byte stream itself (reference behaviour) */
+#define APUS_FLAG_HOST_APPLY 0x10u  /* follower: the apply offset it reports is the one the HOST has replayed */
+#define APUS_FLAG_NO_EXPRESS 0x20u  /* leader: no single-warp express path / self-certifying publishes */
+
+#define APUS_PUB_CERT      (1ull << 63)          /* pub_end: this publish is self-certifying (no writer fence) */
+#define APUS_PUB_TERM_SHIFT 48                   /* pub_cum / hb: term in the top 16 bits */
+#define APUS_PUB_CUM_MASK  ((1ull << 48) - 1)
 
 #define APUS_ROLE_NONE     0
 #define APUS_ROLE_LEADER   1
@@ -208,8 +243,10 @@ typedef struct apus_devctx {
     uint64_t target;                      /* cumulative ticket / entry target of this launch */
     uint32_t n_workers;                   /* leader CTAs of this launch */
     uint32_t doorbell_relay;              /* 1: workers poll seq.doorbell, a relay warp polls the host word */
-    uint32_t pad_r;
+    uint32_t slot_poll;                   /* 1: worker 0 polls the next slot itself (host-mapped ring) */
     uint32_t epoch;                       /* launch counter (sequencer reset handshake) */
+    uint64_t hb_period_ns;                /* leader: heartbeat period (0 = no heartbeats) */
+    uint64_t hb_timeout_ns;               /* follower: silence after which the leader is suspected (0 = never) */
     uint8_t *region;                      /* own region */
     uint8_t *peer[APUS_MAX_SERVERS];      /* peers' regions as mapped here (NULL = absent) */
     /* leader submission ring */

@@ -126,6 +126,8 @@ static void leader_pump(void)
 {
     uint64_t submitted = 0, applied = 0;
     uint8_t image[64];
+    struct apus_tailhead_t pending;                 /* popped from the shared queue, not yet in the engine */
+    TAILQ_INIT(&pending);
     if (g_n > 1) {
         /* the election winner's blank CONFIG entry (dare_server.c:1412-1421) */
         uint8_t cid[16];
@@ -142,30 +144,40 @@ static void leader_pump(void)
     g_leader = 1;
     apus_submit_defer(g_rep, 1);
     while (!g_terminate) {
-        /* get_tailq_message (dare_ibv_ud.c:780-790): lock, pop FIFO, append, free */
-        int any = 0;
-        pthread_spin_lock(&tailq_lock);
-        while (!TAILQ_EMPTY(&tailhead) && submitted - applied < TK_RING - 2) {
-            tailq_entry_t *n3 = TAILQ_FIRST(&tailhead);
+        /* get_tailq_message (dare_ibv_ud.c:780-790): lock, pop FIFO, append, free -- the lock (a spinlock every
+         * application thread takes in proxy.c:108-161) is held only to unhook what is queued: O(1), no engine call,
+         * no BerkeleyDB put under it */
+        if (!TAILQ_EMPTY(&tailhead)) {               /* (racy peek; the splice below is under the lock) */
+            pthread_spin_lock(&tailq_lock);
+            TAILQ_CONCAT(&pending, &tailhead, entries);
+            pthread_spin_unlock(&tailq_lock);
+        }
+        /* pass 1: hand the requests to the engine in FIFO order and ring the doorbell ONCE */
+        tailq_entry_t *batch[256];
+        int nb = 0;
+        while (nb < 256 && !TAILQ_EMPTY(&pending) && submitted - applied < TK_RING - 2) {
+            tailq_entry_t *n3 = TAILQ_FIRST(&pending);
             uint64_t t = 0;
             int rc = apus_submit(g_rep, n3->type, n3->connection_id, n3->req_id, n3->cmd.cmd, n3->cmd.len, &t);
             if (rc == APUS_RETRY) break;                       /* ring full: flush, drain commits, retry */
             if (rc != APUS_OK) { LOGT("apus_submit: %s\n", apus_last_error()); g_terminate = 1; break; }
             g_tk_type[t & (TK_RING - 1)] = n3->type;
             submitted = t;
-            any = 1;
-            /* persist_new_entries (dare_server.c:1802): store_cmd(&entry->clt_id): the bytes of
-             * the entry from clt_id on, as they are when the leader persists (sender/reply unset) */
+            TAILQ_REMOVE(&pending, n3, entries);
+            batch[nb++] = n3;
+        }
+        if (nb) apus_submit_flush(g_rep);
+        /* pass 2: while the GPUs replicate, persist.  persist_new_entries (dare_server.c:1802): store_cmd(&entry->clt_id):
+         * the bytes of the entry from clt_id on, as they are when the leader persists (sender/reply unset) */
+        for (int k = 0; k < nb; k++) {
+            tailq_entry_t *n3 = batch[k];
             memset(image, 0, sizeof image);
             memcpy(image, &n3->connection_id, 2);
             image[2] = n3->type;
             memcpy(image + 24, &n3->cmd.len, 2);
             if (g_in.store_cmd) g_in.store_cmd(image, g_in.up_para);
-            TAILQ_REMOVE(&tailhead, n3, entries);
             free(n3);
         }
-        pthread_spin_unlock(&tailq_lock);
-        if (any) apus_submit_flush(g_rep);
         /* apply_committed_entries, leader branch (dare_server.c:1851-1861, 1951-1952) */
         uint64_t c = apus_committed_tickets(g_rep);
         while (applied < c) {
@@ -178,34 +190,55 @@ static void leader_pump(void)
 /* ---- follower pump: apply_committed_entries, follower branch (dare_server.c:1815-1967) -------- */
 static void follower_pump(uint64_t L)
 {
-    uint64_t apply = 0;
-    uint8_t *buf = (uint8_t *)malloc(1u << 20);
-    size_t cap = 1u << 20;
+    uint64_t apply = 0, next_idx = 0;
+    const size_t cap = 1u << 20;
+    uint8_t *buf = (uint8_t *)malloc(cap + 65536 + 64);
+    uint32_t idle = 0;
     while (!g_terminate) {
         uint64_t off = 0, cnt = 0;
         if (apus_progress(g_rep, &off, &cnt) != APUS_OK) { LOGT("%s\n", apus_last_error()); break; }
-        if (off == apply) { usleep(20); continue; }
-        /* entries [apply, off), possibly wrapped; walk with the reference's rules */
-        while (apply != off && !g_terminate) {
-            if (L - apply < APUS_ENTRY_HDR) { apply = 0; if (apply == off) break; }      /* log_get_entry */
-            uint8_t hdr[64];
-            if (apus_log_read(g_rep, apply, 64, hdr) != APUS_OK) { g_terminate = 1; break; }
-            uint8_t type = hdr[26];
-            uint16_t len; memcpy(&len, hdr + 48, 2);
-            uint32_t stride = csm_like(type) ? 64u + len : 64u;                        /* log_entry_len */
-            if (L - apply < stride) { apply = 0; continue; }                             /* ghost header */
+        if (off == apply) {
+            if (++idle > 2000) usleep(20);       /* spin first: the commit word is plain host memory */
+            continue;
+        }
+        idle = 0;
+        /* everything in [apply, off) is committed and held by this replica: ONE range read (two copies when the
+         * range wraps) into a pinned buffer, then walk it with the reference's rules */
+        uint64_t got = 0;
+        if (apus_log_read_range(g_rep, apply, off, buf, cap + 65536 + 64, &got) != APUS_OK) { LOGT("%s\n", apus_last_error()); break; }
+        uint64_t o = apply, p = 0;               /* log offset / buffer position */
+        while (p < got && !g_terminate) {
+            if (L - o < APUS_ENTRY_HDR) { p += L - o; o = 0; continue; }               /* log_get_entry: no room for a header */
+            if (got - p < APUS_ENTRY_HDR) break;
+            const uint8_t *e = buf + p;
+            const uint8_t type = e[26];
+            uint16_t len; memcpy(&len, e + 48, 2);
+            const uint32_t stride = csm_like(type) ? 64u + len : 64u;                  /* log_entry_len */
+            if (L - o < stride) { p += L - o; o = 0; continue; }                       /* ghost header: the entry is at 0 */
+            if (got - p < stride) break;                                                 /* cut by the buffer: next round */
+            uint64_t idx; memcpy(&idx, e, 8);
+            if (next_idx && idx != next_idx) {
+                /* the bytes are not the entry that should be here: the host fell a whole ring behind (cannot happen
+                 * while the leader prunes by the replayed offset, APUS_F_HOST_APPLY) -- never replay garbage */
+                LOGT("FATAL: apply walk expected idx %llu, found %llu at offset %llu\n", (unsigned long long)next_idx,
+                     (unsigned long long)idx, (unsigned long long)o);
+                g_terminate = 1;
+                break;
+            }
+            next_idx = idx + 1;
             if (csm_like(type)) {
-                if (stride > cap) { cap = stride; buf = (uint8_t *)realloc(buf, cap); }
-                if (apus_log_read(g_rep, apply, stride, buf) != APUS_OK) { g_terminate = 1; break; }
-                uint16_t clt; memcpy(&clt, buf + 24, 2);
-                if (g_in.store_cmd) g_in.store_cmd(buf + 24, g_in.up_para);
-                if (g_in.do_action) g_in.do_action(clt, type, len, buf + 50, g_in.up_para);
-                uint64_t idx; memcpy(&idx, buf, 8);
-                if (idx % 10000 == 0) { uint64_t term; memcpy(&term, buf + 8, 8);
+                uint16_t clt; memcpy(&clt, e + 24, 2);
+                if (g_in.store_cmd) g_in.store_cmd((void *)(e + 24), g_in.up_para);
+                if (g_in.do_action) g_in.do_action(clt, type, len, (void *)(e + 50), g_in.up_para);
+                if (idx % 10000 == 0) { uint64_t term; memcpy(&term, e + 8, 8);
                     LOGT("APPLY LOG ENTRY: (%llu; %llu)\n", (unsigned long long)idx, (unsigned long long)term); }
             }
-            apply += stride;
-            if (apply == L) apply = 0;
+            p += stride; o += stride;
+            if (o == L) o = 0;
+        }
+        if (o != apply) {
+            apply = o;
+            apus_set_applied(g_rep, apply);      /* log->apply moves only after do_action (dare_server.c:1939-1962) */
         }
     }
     free(buf);
@@ -236,7 +269,7 @@ void *dare_server_init(void *arg)
     cfg.device = g_env_gpu >= 0 ? g_env_gpu : (int)(g_idx % (unsigned)ndev);
     cfg.server_idx = g_idx; cfg.group_size = g_n; cfg.leader_idx = g_leader_idx;
     cfg.ring_mode = APUS_RING_HOST_MAPPED;
-    cfg.flags = APUS_F_EXPLICIT | APUS_F_DEVICE_STATS | APUS_F_AUTOPRUNE;
+    cfg.flags = APUS_F_EXPLICIT | APUS_F_DEVICE_STATS | APUS_F_AUTOPRUNE | APUS_F_HOST_APPLY;
     cfg.term = 1;                                      /* term of a clean first election */
     cfg.log_size = g_env_log_size;
     cfg.leader_ctas = 2;

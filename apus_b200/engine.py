@@ -17,6 +17,7 @@ RING_HOST_MAPPED, RING_DEVICE = 0, 1
 LOG_SIZE = 16384 * 4096
 MAX_SERVERS = 13
 F_FENCED_ACK, F_DEVICE_STATS, F_AUTOPRUNE, F_FOLLOWER_WALK, F_EXPLICIT = 0x1, 0x2, 0x4, 0x8, 0x80000000
+F_HOST_APPLY, F_NO_EXPRESS = 0x10, 0x20
 UINT64_MAX = (1 << 64) - 1
 
 u64, u32, u16, u8, i64, i32 = C.c_uint64, C.c_uint32, C.c_uint16, C.c_uint8, C.c_int64, C.c_int32
@@ -29,7 +30,8 @@ class ApusError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [("struct_size", u32), ("device", i32), ("server_idx", u8), ("group_size", u8),
                 ("leader_idx", u8), ("ring_mode", u8), ("flags", u32), ("term", u64),
-                ("log_size", u64), ("ring_slots", u32), ("ring_bytes", u32), ("leader_ctas", u32), ("reserved", u32)]
+                ("log_size", u64), ("ring_slots", u32), ("ring_bytes", u32), ("leader_ctas", u32), ("reserved", u32),
+                ("hb_period_us", u32), ("hb_timeout_us", u32)]
 
 
 class PeerHandle(C.Structure):
@@ -55,6 +57,8 @@ EXPORTS = [
     "apus_submit_batch", "apus_submit_defer", "apus_submit_flush", "apus_committed_tickets",
     "apus_progress", "apus_wait_committed", "apus_closed_loop", "apus_log_offsets", "apus_log_read", "apus_get_stats",
     "apus_latency_samples", "apus_set_head", "apus_remote_apply_offsets",
+    "apus_submit_uniform", "apus_submit_synth", "apus_synth_byte", "apus_submit_release", "apus_set_applied",
+    "apus_log_read_range", "apus_leader_suspect", "apus_last_commit_ns",
 ]
 
 
@@ -95,6 +99,18 @@ def load_library(path=LIB_PATH):
     L.apus_latency_samples.argtypes = [vp, vp, u32, C.POINTER(u32)]
     L.apus_set_head.argtypes = [vp, u64]
     L.apus_remote_apply_offsets.argtypes = [vp, C.POINTER(u64)]
+    if hasattr(L, "apus_submit_uniform"):       # ABI 2
+        L.apus_submit_uniform.argtypes = [vp, u32, u8, u16, u64, u16, vp, C.c_size_t, C.POINTER(u64)]
+        L.apus_submit_synth.argtypes = [vp, u32, u8, u16, u64, u16, u32, C.POINTER(u64)]
+        L.apus_synth_byte.argtypes = [u32, u64, u32]
+        L.apus_synth_byte.restype = u8
+        L.apus_submit_release.argtypes = [vp, u64]
+        L.apus_set_applied.argtypes = [vp, u64]
+        L.apus_log_read_range.argtypes = [vp, u64, u64, vp, u64, C.POINTER(u64)]
+        L.apus_leader_suspect.argtypes = [vp]
+        L.apus_leader_suspect.restype = u64
+        L.apus_last_commit_ns.argtypes = [vp]
+        L.apus_last_commit_ns.restype = u64
     _lib = L
     return L
 
@@ -114,10 +130,12 @@ def _ck(rc, what):
 
 class Replica:
     def __init__(self, device, server_idx, group_size, leader_idx=0, term=1, log_size=0,
-                 ring_mode=RING_HOST_MAPPED, ring_slots=0, ring_bytes=0, flags=None, leader_ctas=0):
+                 ring_mode=RING_HOST_MAPPED, ring_slots=0, ring_bytes=0, flags=None, leader_ctas=0,
+                 hb_period_us=0, hb_timeout_us=0):
         cfg = Config()
         cfg.leader_ctas = leader_ctas
-        cfg.struct_size = C.sizeof(Config)
+        cfg.hb_period_us, cfg.hb_timeout_us = hb_period_us, hb_timeout_us
+        cfg.struct_size = C.sizeof(Config) if lib().apus_abi_version() >= 2 else 48
         cfg.device, cfg.server_idx, cfg.group_size, cfg.leader_idx = device, server_idx, group_size, leader_idx
         cfg.ring_mode, cfg.term, cfg.log_size = ring_mode, term, log_size
         cfg.ring_slots, cfg.ring_bytes = ring_slots, ring_bytes
@@ -178,6 +196,41 @@ class Replica:
                                     lens.ctypes.data, pp, stride, C.byref(t)), "apus_submit_batch")
         return int(t.value)
 
+    def submit_uniform(self, n, typ, conn, first_req_id, length, payloads, stride=None):
+        """n requests of one shape, filled by the engine's host threads (apus_submit_uniform)."""
+        pp = None
+        if payloads is not None and length:
+            payloads = np.ascontiguousarray(payloads, dtype=np.uint8)
+            pp = payloads.ctypes.data
+        t = u64()
+        _ck(lib().apus_submit_uniform(self.h, n, typ, conn, first_req_id, length, pp, length if stride is None else stride,
+                                      C.byref(t)), "apus_submit_uniform")
+        return int(t.value)
+
+    def submit_synth(self, n, typ, conn, first_req_id, length, seed):
+        """n device-generated requests written straight into the HBM submission ring."""
+        t = u64()
+        _ck(lib().apus_submit_synth(self.h, n, typ, conn, first_req_id, length, seed, C.byref(t)), "apus_submit_synth")
+        return int(t.value)
+
+    def release(self, ticket):
+        _ck(lib().apus_submit_release(self.h, ticket), "apus_submit_release")
+
+    def set_applied(self, offset):
+        _ck(lib().apus_set_applied(self.h, offset), "apus_set_applied")
+
+    def read_range(self, start, stop, cap=1 << 20):
+        out = np.empty(cap, dtype=np.uint8)
+        got = u64()
+        _ck(lib().apus_log_read_range(self.h, start, stop, out.ctypes.data, cap, C.byref(got)), "apus_log_read_range")
+        return out[: got.value].copy()
+
+    def leader_suspect(self):
+        return int(lib().apus_leader_suspect(self.h))
+
+    def last_commit_ns(self):
+        return int(lib().apus_last_commit_ns(self.h))
+
     def defer(self, on=True):
         _ck(lib().apus_submit_defer(self.h, 1 if on else 0), "apus_submit_defer")
 
@@ -236,6 +289,21 @@ class Replica:
         return [int(x) for x in arr]
 
 
+def synth_payload(seed: int, req_id: int, length: int) -> bytes:
+    """Payload of the device-generated request `req_id` (apus_submit_synth), computed on the host with numpy --
+    the same integer mix the fill kernel runs (apus_engine.cu: synth_word)."""
+    if length == 0:
+        return b""
+    w = np.arange((length + 3) // 4, dtype=np.uint64)
+    x = (np.uint64(seed) ^ np.uint64((req_id * 0x9E3779B1) & 0xFFFFFFFF) ^ np.uint64(((req_id >> 32) * 0x7F4A7C15) & 0xFFFFFFFF)
+         ^ ((w * np.uint64(0x85EBCA77)) & np.uint64(0xFFFFFFFF)))
+    M = np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16); x = (x * np.uint64(0x7FEB352D)) & M
+    x ^= x >> np.uint64(15); x = (x * np.uint64(0x846CA68B)) & M
+    x ^= x >> np.uint64(16)
+    return x.astype(np.uint32).view(np.uint8)[:length].tobytes()
+
+
 def cid_image(n: int) -> bytes:
     """dare_cid_t of a fresh stable group (dare_server.c:285-291)."""
     return (0).to_bytes(8, "little") + bytes([n, 0, 0, 0]) + ((1 << n) - 1).to_bytes(4, "little")
@@ -245,7 +313,7 @@ class Group:
     """All replicas of one Paxos group inside this process (tests, 1..8 GPUs)."""
 
     def __init__(self, n, devices=None, leader=0, term=1, log_size=0, ring_mode=RING_HOST_MAPPED,
-                 ring_slots=0, ring_bytes=0, flags=None, leader_ctas=0):
+                 ring_slots=0, ring_bytes=0, flags=None, leader_ctas=0, hb_period_us=0, hb_timeout_us=0):
         ndev = lib().apus_device_count()
         if ndev <= 0:
             raise ApusError("no CUDA device visible: the engine has no CPU fallback")
@@ -253,7 +321,7 @@ class Group:
             devices = [i % ndev for i in range(n)]
         self.n, self.leader_idx, self.devices = n, leader, list(devices)
         self.replicas = [Replica(devices[i], i, n, leader, term, log_size, ring_mode, ring_slots, ring_bytes, flags,
-                                 leader_ctas) for i in range(n)]
+                                 leader_ctas, hb_period_us, hb_timeout_us) for i in range(n)]
         blobs = [r.export() for r in self.replicas]
         for r in self.replicas:
             for j, b in enumerate(blobs):

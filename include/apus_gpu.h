@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define APUS_ABI_VERSION 1
+#define APUS_ABI_VERSION 2
 
 #define APUS_OK       0
 #define APUS_ERROR    1
@@ -73,6 +73,11 @@ extern "C" {
 #define APUS_F_FOLLOWER_WALK 0x8u /* follower: find entry boundaries by walking the byte stream
                                      (log_get_entry/log_entry_len, as the reference follower does)
                                      instead of reading the leader-written offset index */
+#define APUS_F_HOST_APPLY   0x10u /* follower: the apply offset reported to the leader's pruning rule is the one the
+                                     HOST has replayed (apus_set_applied), as apply_committed_entries advances
+                                     log->apply only after do_action (dare_server.c:1939-1962); off = apply follows
+                                     commit on the device (nothing replays the log on the host) */
+#define APUS_F_NO_EXPRESS   0x20u /* leader: no single-warp express path, every publish is fenced (A/B switch) */
 #define APUS_F_EXPLICIT     0x80000000u /* flags are exactly as given (no defaults OR-ed in) */
 
 typedef struct apus_replica apus_replica_t;
@@ -91,7 +96,12 @@ typedef struct apus_config {
     uint32_t ring_bytes;       /* payload ring bytes, multiple of 4096; 0 -> default */
     uint32_t leader_ctas;      /* leader: worker CTAs (SMs) building tiles in parallel; 0 -> default */
     uint32_t reserved;
+    /* ---- ABI 2 (struct_size tells which fields exist) ---- */
+    uint32_t hb_period_us;     /* leader: heartbeat period, microseconds (hb_period of the config file,
+                                  dare_server.c:763-791); 0 = no heartbeats */
+    uint32_t hb_timeout_us;    /* follower: silence after which the leader is suspected (hb_timeout); 0 = never */
 } apus_config_t;
+#define APUS_CONFIG_SIZE_V1 48u
 
 /* Opaque blob a replica publishes so that peers can map its HBM region.
  * Same process: carries the pointer; other process: a cudaIpcMemHandle_t. */
@@ -161,10 +171,23 @@ int  apus_submit_batch(apus_replica_t *leader, uint32_t n, const uint8_t *types,
                        const uint16_t *connection_ids, const uint64_t *req_ids,
                        const uint16_t *lens, const void *payloads, size_t stride,
                        uint64_t *first_ticket);
+/* n requests of ONE shape (type, connection, len; req_id = first_req_id + k; payload k at payloads + k*stride):
+ * the bulk form of proxy.c:108-161's enqueue, filled by several host threads (env apus_submit_threads, default 4). */
+int  apus_submit_uniform(apus_replica_t *leader, uint32_t n, uint8_t type, uint16_t connection_id,
+                         uint64_t first_req_id, uint16_t len, const void *payloads, size_t stride,
+                         uint64_t *first_ticket);
+/* Device-generated requests (APUS_RING_DEVICE only): a fill kernel writes n SEND-like requests straight into the
+ * HBM submission ring -- payload byte k of request req_id is apus_synth_byte(seed, req_id, k) -- so that a
+ * benchmark can have its whole input resident in HBM without a host copy. */
+int  apus_submit_synth(apus_replica_t *leader, uint32_t n, uint8_t type, uint16_t connection_id,
+                       uint64_t first_req_id, uint16_t len, uint32_t seed, uint64_t *first_ticket);
+uint8_t apus_synth_byte(uint32_t seed, uint64_t req_id, uint32_t k);
 /* make everything submitted so far visible to the kernel (doorbell); apus_submit*
  * ring it themselves unless the replica was put in deferred mode */
 int  apus_submit_defer(apus_replica_t *leader, int defer);
 int  apus_submit_flush(apus_replica_t *leader);
+/* ring the doorbell only up to `ticket` (<= submitted): requests beyond it stay resident but unseen */
+int  apus_submit_release(apus_replica_t *leader, uint64_t ticket);
 
 /* ---- commit observation (what update_state / do_action hang off) ---------------- */
 uint64_t apus_committed_tickets(apus_replica_t *leader);
@@ -188,6 +211,16 @@ int  apus_log_read(apus_replica_t *r, uint64_t off, uint64_t len, void *dst);
 int  apus_get_stats(apus_replica_t *r, apus_stats_t *out);
 /* device-side commit latencies (ns), newest `max` samples; returns count in *n */
 int  apus_latency_samples(apus_replica_t *r, uint32_t *dst_ns, uint32_t max, uint32_t *n);
+
+/* follower, APUS_F_HOST_APPLY: the application has replayed the log up to `offset` (do_action done) */
+int  apus_set_applied(apus_replica_t *r, uint64_t offset);
+/* copy the committed-and-held range [from, to) of the circular log (it may wrap) into dst (capacity cap);
+ * *got = bytes copied.  One or two device->host copies through a pinned buffer. */
+int  apus_log_read_range(apus_replica_t *r, uint64_t from, uint64_t to, void *dst, uint64_t cap, uint64_t *got);
+/* failure detector: 0 while the leader's heartbeats arrive, else 1 + the term whose leader fell silent */
+uint64_t apus_leader_suspect(apus_replica_t *follower);
+/* %globaltimer (ns) of the leader kernel's latest commit (device clock; step timing of resident kernels) */
+uint64_t apus_last_commit_ns(apus_replica_t *leader);
 
 /* control plane hooks used by pruning (log_pruning, dare_server.c:1996-2067) */
 int  apus_set_head(apus_replica_t *r, uint64_t head);

@@ -32,7 +32,7 @@ def test_header_symbols_exported(built):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/apus_gpu.h but not exported"
     assert sorted(built.EXPORTS) == syms
-    assert lib.apus_abi_version() == 1
+    assert lib.apus_abi_version() == 2
 
 
 def test_nm_shows_kernel_and_c_abi(built):
@@ -57,7 +57,7 @@ def test_no_cpu_fallback(built):
 
 def test_config_struct_matches_header(built):
     # struct_size is checked by the library itself; this pins the Python mirror
-    assert C.sizeof(built.Config) == 48
+    assert C.sizeof(built.Config) == 56          # ABI 2: + hb_period_us, hb_timeout_us (48 B ABI-1 configs are accepted)
     assert C.sizeof(built.PeerHandle) == 128
     assert C.sizeof(built.LogOffsets) == 64
     assert C.sizeof(built.Stats) == 208
