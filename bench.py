@@ -8,10 +8,14 @@ A *step* is one pass of the hot path over one batch of synthetic requests:
 `--batch` SEND requests of `--payload` bytes are appended to the leader's log,
 replicated to every follower, acked, and committed by majority.
 
-  value      requests already resident in HBM (device submission ring) when the timed
-             region starts; one fused kernel launch per GPU per step
-  e2e        the same metric through the C ABI with HOST buffers: apus_submit_batch()
+  value      requests already resident in HBM (device submission ring, written there by the
+             engine's fill kernel: apus_submit_synth) when the timed region starts; one fused
+             kernel launch per GPU per step, a step = 2^20 requests (>= 2^24 per default run)
+  e2e        the same metric through the C ABI with HOST buffers: apus_submit_uniform()
              from host memory + apus_wait_committed(); the kernels stay resident
+  parity     outside every timed region: the same placement runs a bounded stream that the CPU
+             oracle can follow; every replica's whole log is compared byte for byte (across
+             ranks: hashes gathered over gloo) -- the cross-GPU parity evidence of the run
   roofline   algorithmic bytes (N-1)*(64+L) per committed op / CUDA-event time of the
              replica kernel, against MEASURED_PEAKS.json (HBM copy bandwidth: with all
              replicas on one GPU the "peer" stores land in local HBM; NVLink peer-copy
@@ -53,14 +57,17 @@ NVLINK_PEER_GBS = 770.0     # measured peer copy per direction (B200_PROFILING.m
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replicas", type=int, default=5)
     ap.add_argument("--payload", type=int, default=64)
-    ap.add_argument("--batch", type=int, default=65536, help="requests per step")
+    ap.add_argument("--batch", type=int, default=0, help="requests per step (0 = 2^20 for <= 256 B requests, else 16 MiB worth)")
     ap.add_argument("--log-size", type=int, default=0, help="bytes of entries[]; 0 = reference LOG_SIZE (64 MiB)")
-    ap.add_argument("--lat-requests", type=int, default=3000, help="closed-loop requests for p50/p99")
+    ap.add_argument("--lat-requests", type=int, default=20000, help="closed-loop requests for p50/p99")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-proxy-leg", action="store_true", help="skip the 16-connection closed-loop leg through the reference's proxy.c")
+    ap.add_argument("--no-express", action="store_true", help="A/B: every publish fenced, no single-warp express path")
     ap.add_argument("--e2e-ring", default="mapped", choices=["mapped", "device"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -159,6 +166,10 @@ def cpu_run(oracle, n, payload, nreq, clients=64):
     secs = C.c_double()
     ops = oracle.bench_run(n, payload, nreq, clients, C.byref(secs))
     return float(ops), float(secs.value)
+
+
+def default_batch(args):
+    return args.batch or ((1 << 20) if args.payload <= 256 else max(4096, (16 << 20) // (64 + args.payload)))
 
 
 def cpu_nreq(payload, batch):
@@ -262,7 +273,7 @@ def run_reference(args):
                                 "clock": "host, around proxy_on_read (returns at commit)"}}
     else:
         oracle, kind = cpu_library()
-        nreq = cpu_nreq(payload, args.batch)
+        nreq = cpu_nreq(payload, default_batch(args))
         for _ in range(args.warmup):
             cpu_run(oracle, n, payload, nreq)
         t = 0.0
@@ -385,21 +396,22 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local)
 
-    n, payload, batch = args.replicas, args.payload, args.batch
+    n, payload = args.replicas, args.payload
     K, W = args.steps, args.warmup
     L = args.log_size or A.LOG_SIZE
     stride = 64 + payload
-    if batch * stride * 4 > L * 3:
-        raise SystemExit("batch too large for the log ring")
-    inline = (2 + payload) <= 112                      # APUS_SLOT_INLINE: image rides in the 128 B slot
+    batch = default_batch(args)
+    inline = (2 + payload) <= 80                       # APUS_SLOT_INLINE: image rides in the 128 B slot
     img = 0 if inline else (2 + payload + 15) // 16 * 16
     total_req = (K + W) * batch + 64
     slots = 1 << max(16, (total_req - 1).bit_length())
     ring_bytes = ((total_req * img + (1 << 20)) + 4095) // 4096 * 4096
     if ring_bytes // 16 > 0xFFFFFF:
-        raise SystemExit("steps*batch*payload too large for the device submission ring (256 MiB)")
-    flags = E.F_DEVICE_STATS | E.F_AUTOPRUNE
-    vflags = E.F_AUTOPRUNE if args.no_stats else flags
+        raise SystemExit("steps*batch*payload too large for the device payload ring (256 MiB): lower --batch or --steps")
+    xflag = E.F_NO_EXPRESS if args.no_express else 0
+    flags = E.F_DEVICE_STATS | E.F_AUTOPRUNE | xflag
+    vflags = (E.F_AUTOPRUNE | xflag) if args.no_stats else flags
+    SEED = 0xA5A50000 + payload
 
     def barrier():
         torch.cuda.synchronize()
@@ -433,7 +445,16 @@ def run_ours(args):
         return float(t.item())
 
     conn = 0
-    payloads = np.random.default_rng(0xA5A50000 + payload).integers(0, 256, size=batch * max(payload, 1), dtype=np.uint8)
+
+    # =========================== parity: the placement of this run against the oracle =====
+    parity = None
+    if not args.no_parity:
+        parity = parity_leg(A, E, args, dist, gloo, rank, world, local, log)
+        if parity and not (parity["replicas_equal"] and parity["oracle_equal"]):
+            if rank == 0:
+                print(json.dumps({"metric": "committed ops/s", "value": 0, "parity": parity,
+                                  "error": "PARITY MISMATCH: replica logs differ from the oracle"}), flush=True)
+            raise SystemExit(3)
 
     # =========================== value: inputs resident in HBM ===========================
     cell = Cell(A, E, args, A.RING_DEVICE, slots, ring_bytes, vflags, dist, rank, world, local)
@@ -445,10 +466,11 @@ def run_ours(args):
     targets = []
     cell.leader.defer(True)
     for s in range(W + K):
-        cell.submit_uniform(batch, payload, conn, req, payloads)
+        t0 = cell.leader.submit_synth(batch, SEND, conn, req, payload, SEED)     # fill kernel: straight into the HBM ring
+        cell.tickets = t0 + batch - 1
         req += batch
         targets.append(cell.tickets)
-    cell.leader.flush()            # every step's requests are now in the HBM ring
+    cell.leader.flush()            # every step's requests are now in the HBM ring, doorbell rung
     cell.leader.defer(False)
     for s in range(W):
         barrier()
@@ -475,15 +497,18 @@ def run_ours(args):
     lat_dev = cell.leader.latency_ns()
     auto_heads = st["auto_heads"]
     log(f"leader phases (ns, cumulative): {st['phase_ns']}")
-    log(f"worker-0 turns [claim-wait ns, place-wait ns, publish-wait ns, fast placements, slow placements, -, -, place-hold ns]: {st['turn_ns'][:8]}")
+    log(f"worker-0 turns [claim-wait ns, place-wait ns, publish-wait ns, fast placements, slow placements, express, claims, place-hold ns]: {st['turn_ns'][:8]}")
     batches = st["batches"]
     off = cell.leader.offsets()
+    # every replica this rank hosts holds the leader's live log (size-independent property of the timed run itself)
+    live = live_log_check(cell, dist, gloo, rank, world, n, L) if not args.no_parity else None
     cell.close()
 
     # =========================== e2e: host buffers through the C ABI =====================
     e2e = None
     lat_host = None
     if not args.no_e2e:
+        payloads = np.random.default_rng(SEED).integers(0, 256, size=batch * max(payload, 1), dtype=np.uint8)
         mode = A.RING_HOST_MAPPED if args.e2e_ring == "mapped" else A.RING_DEVICE
         e_slots = 1 << max(16, (2 * batch - 1).bit_length())
         e_bytes = ((2 * batch * img + (1 << 20)) + 4095) // 4096 * 4096
@@ -496,43 +521,59 @@ def run_ours(args):
         t = cell.submit(CONNECT, conn, 1, b"")
         cell.leader.wait_committed(t, 20_000_000)
         req = 2
+
+        def e2e_step():
+            nonlocal req
+            t0_ = cell.leader.submit_uniform(batch, SEND, conn, req, payload, payloads)
+            req += batch
+            cell.leader.wait_committed(t0_ + batch - 1, 120_000_000)
+
         for s in range(W):
-            t = cell.submit_uniform(batch, payload, conn, req, payloads); req += batch
-            cell.leader.wait_committed(t, 60_000_000)
+            e2e_step()
         host_barrier()
         t0 = time.perf_counter()
         for s in range(K):
-            t = cell.submit_uniform(batch, payload, conn, req, payloads); req += batch
-            cell.leader.wait_committed(t, 60_000_000)
+            e2e_step()
         t1 = time.perf_counter()
         host_barrier()
         e_elapsed = max_over_ranks_host(t1 - t0)
         e2e = {"value": round(world * K * batch / e_elapsed, 1), "unit": "ops/s",
-               "h2d_bytes_per_step": batch * (128 + img), "d2h_bytes_per_step": 8,
-               "path": f"apus_submit_batch(host numpy buffers) -> {args.e2e_ring} submission ring -> resident kernels "
-                       f"-> apus_wait_committed (pinned commit word)"}
+               "h2d_bytes_per_step": batch * (96 + img), "d2h_bytes_per_step": 16,
+               "ms_per_step": round(1e3 * e_elapsed / K, 4),
+               "submit_threads": int(os.environ.get("apus_submit_threads", "4")),
+               "path": f"apus_submit_uniform(host numpy buffer, engine host threads) -> {args.e2e_ring} submission ring "
+                       f"(pinned host memory read by the kernel over PCIe: 96 of the 128 slot bytes) -> resident kernels "
+                       f"-> apus_wait_committed (16 B pinned commit record)"}
         # closed loop, one request in flight: host-view commit latency (proxy.c:160 spin)
         if rank == 0 and args.lat_requests > 0:
-            ph0 = cell.leader.stats()["phase_ns"]
+            st0 = cell.leader.stats()
             lats = cell.leader.closed_loop(args.lat_requests, payload, conn, req)
-            ph1 = cell.leader.stats()["phase_ns"]
-            tiles = max(1, ph1[7] - ph0[7])
-            log("closed loop, worker 0 ns per tile [wait,T1,T2,T3,T4,T5,T6]: "
-                f"{[round((b - a) / tiles) for a, b in zip(ph0[:7], ph1[:7])]} over {tiles} tiles")
+            st1 = cell.leader.stats()
             req += args.lat_requests
             lats = np.sort(lats[args.lat_requests // 10:].astype(np.float64)) / 1e3
             lat_host = {"p50_us": round(float(lats[len(lats) // 2]), 2), "p99_us": round(float(lats[int(len(lats) * 0.99)]), 2),
-                        "n": int(len(lats)), "what": "apus_closed_loop (C ABI): enqueue one request, spin on the pinned "
-                                                      "commit word until it is committed; host clock, one request in flight"}
+                        "p999_us": round(float(lats[int(len(lats) * 0.999)]), 2), "min_us": round(float(lats[0]), 2),
+                        "n": int(len(lats)), "express_requests": st1["turn_ns"][5] - st0["turn_ns"][5],
+                        "what": "apus_closed_loop (C ABI): enqueue one request, spin on the pinned "
+                                "commit word until it is committed; host clock, one request in flight"}
             d = cell.leader.latency_ns(args.lat_requests - args.lat_requests // 10)
             if len(d):
                 d = np.sort(d.astype(np.float64)) / 1e3
                 lat_host["device_p50_us"] = round(float(d[len(d) // 2]), 2)
                 lat_host["device_p99_us"] = round(float(d[int(len(d) * 0.99)]), 2)
+            log(f"closed loop: {lat_host}")
         host_barrier()
         cell.stop()
         cell.close()
         log(f"e2e done: {e2e}")
+
+    # =========================== the reference's own proxy.c on the engine, 16 connections ==========
+    proxy_leg = None
+    if rank == 0 and world == 1 and not args.no_proxy_leg and not args.no_e2e:
+        try:
+            proxy_leg = proxy_closed_loop_leg(args, n, payload, log)
+        except Exception as ex:                                   # noqa: BLE001 - reported in the JSON line
+            proxy_leg = {"unavailable": f"{type(ex).__name__}: {str(ex)[:200]}"}
 
     # =========================== CPU baseline, JSON line ==================================
     if rank != 0:
@@ -552,27 +593,28 @@ def run_ours(args):
         "steps": K, "warmup": W, "ms_per_step": round(1e3 * elapsed / K, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {
-            "workload": f"{n}-replica Paxos group, {payload} B SEND requests, {batch} requests per step, "
-                        f"device-resident submission ring",
+            "workload": f"{n}-replica Paxos group, {payload} B SEND requests, {batch} requests per step "
+                        f"({K * batch} in the timed region), device-resident submission ring",
             "replicas": n, "payload_bytes": payload, "batch": batch, "groups": world,
             "placement": ("all replicas of the group on GPU 0" if world == 1 and not args.spread else
                           ("replica r on GPU r % visible GPUs, one process" if world == 1 else
                            f"group g led by GPU g, replica r on GPU (g + r) % {world}, one process per GPU, CUDA IPC")),
             "log_ring_bytes": L, "log_pruning": "device-side HEAD entries (APUS_F_AUTOPRUNE)",
             "cache": f"inputs larger than L2: {(K + W) * batch * (128 + img) >> 20} MiB of requests stream through once; "
-                     f"log writes cover the 64 MiB ring x {n} replicas",
+                     f"every step writes {batch * stride >> 20} MiB into each replica's {L >> 20} MiB log ring",
         },
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": launches,
+        "parity": parity if parity is None else dict(parity, live_log=live),
         "roofline": {"bound": bound, "achieved": round(ach, 3), "peak": peak, "unit": "GB/s",
                      "frac": round(ach / peak, 6),
                      "traffic": (ncu_traffic(n, payload, batch) if world == 1 and not args.spread else None),
-                     "traffic_note": "bytes per launch (dram read+write), profiles/r1_ncu_v5.json; algorithmic bytes per launch = "
-                                     f"{alg_bytes_per_op * batch}",
+                     "traffic_note": "bytes per launch (dram read+write) from the committed ncu capture of this configuration, when one "
+                                     f"exists; algorithmic bytes per launch = {alg_bytes_per_op * batch}",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_op": alg_bytes_per_op,
-                     "kernel": "apus_replica_kernel (one fused launch per step: leader CTA + follower CTAs)",
+                     "kernel": "apus_replica_kernel (one fused launch per step: leader CTAs + follower CTAs)",
                      "kernel_ms_per_launch": round(kernel_ms / K, 4)},
         "cpu_baseline": cpu,
         "latency": {"device_commit_us": (None if dl is None else
@@ -580,11 +622,181 @@ def run_ours(args):
                                           "n": int(len(dl)), "what": "per replicate step: dequeue -> majority observed (%globaltimer), "
                                                                      "open-loop run (queueing included)"}),
                     "closed_loop": lat_host},
+        "proxy_closed_loop": proxy_leg,
         "engine": {"replicate_steps": batches, "auto_head_entries": auto_heads, "final_offsets": off,
                    "leader_phase_ns": dict(zip(["wait", "T1_fetch", "T2_place", "T3_prefill", "T4_compose", "T5_store",
                                                 "T6_publish", "tiles"], st["phase_ns"]))},
     }
     print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------
+# parity legs (outside every timed region; the oracle is the checker, never the thing measured)
+# ------------------------------------------------------------------------------------
+PARITY_REQ = 1 << 16
+
+
+def parity_stream(n, payload, leader_idx=0):
+    import streams as S
+    nreq = max(2048, min(PARITY_REQ, (24 << 20) // (64 + payload)))
+    return S.uniform_stream(nreq, payload, conns=4, leader=leader_idx)
+
+
+def parity_leg(A, E, args, dist, gloo, rank, world, local, log):
+    """A bounded stream (prologue + 4 connections x up to 2^16 requests of the benchmark's size) through the SAME
+    placement the timed run uses; every replica's log ring is compared byte for byte with the oracle's image of that
+    replica (reply bytes included).  Under torchrun every rank checks the replicas it hosts and the verdicts are
+    gathered over gloo -- followers of group g live on other GPUs than its leader, so equality here is equality
+    across NVLink."""
+    import hashlib
+    import orc as O
+    n, payload = args.replicas, args.payload
+    Lp = 1 << 25                                           # 32 MiB ring: the stream stays inside one lap (no pruning)
+    stream = parity_stream(n, payload)
+    flags = E.F_DEVICE_STATS | (E.F_NO_EXPRESS if args.no_express else 0)
+    pargs = argparse.Namespace(**vars(args))
+    pargs.log_size = Lp
+    cell = Cell(A, E, pargs, A.RING_HOST_MAPPED, 1 << 17, 64 << 20, flags, dist, rank, world, local)
+    try:
+        if n > 1:
+            cell.submit(E.CONFIG, 0, 0, E.cid_image(n))
+        lead = cell.leader
+        lead.defer(True)
+        for typ, clt, rid, pl in stream:
+            cell.tickets = lead.submit(typ, clt, rid, pl)
+        lead.flush(); lead.defer(False)
+        import torch
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        cell.launch(cell.tickets); cell.wait()
+        # the oracle's image of every replica index (the same stream in every group)
+        O.build_oracle()
+        orc = O.Oracle("orc")
+        orc.set_rules(O.RULES_ENGINE)
+        c = O.Cluster(orc, n, leader=0, term=1, length=Lp)
+        if n > 1:
+            c.prologue()
+        for typ, clt, rid, pl in stream:
+            assert c.submit(typ, clt, rid, O.cmd_image(pl))
+        c.round(); c.round()
+        mine = []
+        for r in cell.local:
+            img = r.image()
+            oi = c.image(r.idx)
+            oo, eo = c.offsets(r.idx), r.offsets()
+            ok = bool(np.array_equal(img, oi)) and all(eo[k] == oo[k] for k in ("end", "commit", "apply", "head"))
+            mine.append({"rank": rank, "device": r.device, "replica": r.idx, "oracle_equal": ok,
+                         "sha": hashlib.sha256(img.tobytes()).hexdigest()[:16], "end": eo["end"]})
+        c.close()
+    finally:
+        cell.close()
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=gloo)
+        allr = [x for part in gathered for x in part]
+    else:
+        allr = mine
+    # replicas_equal: per replica index every group produced the same image (same stream), and all ends agree
+    by_idx = {}
+    for x in allr:
+        by_idx.setdefault(x["replica"], set()).add(x["sha"])
+    replicas_equal = all(len(v) == 1 for v in by_idx.values()) and len({x["end"] for x in allr}) == 1
+    res = {"checked": True, "groups": world, "replicas_checked": len(allr),
+           "gpus_holding_replicas": len({(x["rank"], x["device"]) for x in allr}),
+           "replicas_equal": bool(replicas_equal), "oracle_equal": bool(all(x["oracle_equal"] for x in allr)),
+           "stream": f"CONFIG prologue + 4 connections x {len(stream) - 4} SEND requests of {payload} B, {Lp >> 20} MiB ring, "
+                     f"every byte of every replica's ring vs the CPU oracle (ENGINE rules), reply bytes included"}
+    log(f"parity: {res}")
+    return res
+
+
+def live_log_check(cell, dist, gloo, rank, world, n, L):
+    """After the timed (multi-lap, auto-pruned) run: hash of the live log [head, end) with reply bytes masked, per
+    replica; every follower must hold exactly its leader's bytes and entries must parse with consecutive idx."""
+    import hashlib
+    import orc as O
+    TAIL = 4096
+    mine = []
+    for r in cell.local:
+        o = r.offsets()
+        img = r.image()
+        ents = O.walk_entries(img, o["head"], o["end"], L) if o["end"] != L else []
+        first = int.from_bytes(img[ents[0][0]:ents[0][0] + 8].tobytes(), "little") if ents else 0
+        last = int.from_bytes(img[ents[-1][0]:ents[-1][0] + 8].tobytes(), "little") if ents else 0
+        consecutive = (not ents) or (last - first == len(ents) - 1)
+        tail = ents[-TAIL:]
+        m = O.mask_replies(img, tail)
+        h = hashlib.sha256()
+        for e, stride in tail:
+            h.update(m[e:e + stride].tobytes())
+        group = (rank - r.idx) % world if world > 1 else 0
+        mine.append({"group": group, "replica": r.idx, "sha": h.hexdigest()[:16], "end": o["end"], "commit": o["commit"],
+                     "last_idx": last, "tail_entries": len(tail), "entries": len(ents), "consecutive": bool(consecutive)})
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=gloo)
+        allr = [x for part in gathered for x in part]
+    else:
+        allr = mine
+    ok = True
+    for g in {x["group"] for x in allr}:
+        grp = [x for x in allr if x["group"] == g]
+        ok = (ok and len(grp) == n and all(x["consecutive"] for x in grp)
+              and len({(x["sha"], x["end"], x["commit"], x["last_idx"], x["tail_entries"]) for x in grp}) == 1)
+    return {"followers_equal_leader": bool(ok), "entries_compared_per_replica": int(allr[0]["tail_entries"]) if allr else 0,
+            "what": "after the timed multi-lap run: the newest entries of every replica's live log (reply bytes masked), end, commit "
+                    "and last idx equal within each group; entries parse with consecutive idx from head to end"}
+
+
+def proxy_closed_loop_leg(args, n, payload, log, conns=16, nreq=20000, steps=3):
+    """The reference's UNMODIFIED proxy.c (oracle/_ref/libref_proxy.so) on libapus_dare.so/libapus_gpu.so, one process per
+    replica, driven by the same multi-threaded closed-loop application driver the reference arm uses on its own stack
+    (oracle/app_driver.inc): 16 connections, every proxy_on_read returns at commit.  This is the like-for-like
+    counterpart of `bench.py --impl reference`."""
+    import tempfile
+    refproxy = os.path.join(ROOT, "oracle", "_ref", "libref_proxy.so")
+    if not os.path.exists(refproxy):
+        return {"unavailable": "oracle/_ref/libref_proxy.so absent"}
+    import apus_b200 as A
+    nd = max(1, A.lib().apus_device_count())
+    cores = host_cores()
+    threads = max(1, min(conns, cores - n))
+    with tempfile.TemporaryDirectory() as d:
+        env = dict(os.environ, apus_rendezvous=os.path.join(d, "rdv"), PROXY_RUN_TIMEOUT="120", APUS_NO_BUILD="1")
+        procs = []
+        for i in range(n):
+            e = dict(env, apus_gpu=str(i % nd) if args.spread else "0")
+            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "proxy_worker.py"), str(i), str(n), str(conns),
+                                           str(nreq), str(payload), d, str(threads), str(steps)], env=e,
+                                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+        outs = []
+        try:
+            for p in procs:
+                outs.append(p.communicate(timeout=300)[0].decode(errors="replace"))
+        finally:
+            for p in procs:
+                if p.poll() is None:
+                    p.kill()
+        path = os.path.join(d, "result0.json")
+        if not os.path.exists(path):
+            return {"unavailable": "leader process produced no result: " + outs[0][-300:]}
+        r0 = json.load(open(path))
+        followers_ok = 0
+        for i in range(1, n):
+            fp = os.path.join(d, f"result{i}.json")
+            if os.path.exists(fp) and json.load(open(fp)).get("bytes") == nreq * payload * steps:
+                followers_ok += 1
+    timed = r0["steps"][1:]
+    ops = sum(s_["requests"] + 2 * conns for s_ in timed) / sum(s_["seconds"] for s_ in timed)
+    res = {"value": round(ops, 1), "unit": "ops/s", "connections": conns, "app_threads": threads, "replica_processes": n,
+           "p50_us": round(statistics.median(s_["p50_us"] for s_ in timed), 2), "p99_us": round(max(s_["p99_us"] for s_ in timed), 2),
+           "followers_replayed_everything": followers_ok == n - 1,
+           "what": f"unmodified src/proxy/proxy.c on the engine, {n} replica processes ({'one GPU each' if args.spread else 'all on GPU 0'}), "
+                   f"{conns} connections closed loop on {threads} application threads, {len(timed)} x {nreq} requests of {payload} B "
+                   f"after one warm-up session; latency = proxy_on_read call (returns at commit); same driver and shape as --impl reference"}
+    log(f"proxy leg: {res}")
+    return res
 
 
 def main():

@@ -55,3 +55,12 @@ int proxy_read_config(struct proxy_node_t *cur_node, const char *config_path)
 /* what the test reads back from proxy_node_t */
 uint64_t stub_highest_rec(struct proxy_node_t *p) { return p->highest_rec; }
 uint64_t stub_cur_rec(struct proxy_node_t *p) { return p->cur_rec; }
+
+/* the application-side driver of oracle/app_driver.inc on THIS proxy (the reference's unmodified proxy.c linked on the
+ * GPU engine): the same closed-loop load the reference arm runs on its own stack (refstack_drive) */
+#define refstack_ragged_len stub_ragged_len
+#include "app_driver.inc"
+int stub_drive(void *proxy, int threads, int nconn, int64_t nreq, int plen, uint64_t *lat_ns, double *seconds, int accept_close)
+{
+    return app_drive(proxy, threads, nconn, nreq, plen, lat_ns, seconds, accept_close);
+}

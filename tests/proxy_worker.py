@@ -20,6 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def main():
     idx, n, nconn, nreq, plen, outdir = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]),
                                           int(sys.argv[5]), sys.argv[6])
+    nthreads = int(sys.argv[7]) if len(sys.argv) > 7 else 0      # > 0: the C driver of oracle/app_driver.inc (stub_drive)
+    nsteps = int(sys.argv[8]) if len(sys.argv) > 8 else 1
     leader = idx == 0
     received = {}
     lock = threading.Lock()
@@ -32,16 +34,17 @@ def main():
         port_holder.append(srv.getsockname()[1])
 
         def serve(conn, k):
-            buf = bytearray()
+            h, nbytes = hashlib.sha256(), 0
+            with lock:
+                received[k] = [0, h]
             while True:
                 d = conn.recv(1 << 16)
                 if not d:
                     break
-                buf += d
+                h.update(d)
+                nbytes += len(d)
                 with lock:
-                    received[k] = bytes(buf)
-            with lock:
-                received[k] = bytes(buf)
+                    received[k][0] = nbytes
 
         k = 0
         while True:
@@ -82,39 +85,56 @@ def main():
         while not dare.is_leader():
             assert time.time() - t0 < 60, "leader never came up"
             time.sleep(0.01)
+        if nthreads > 0:
+            # the same multi-threaded closed-loop driver the reference arm runs on its own stack (refstack_drive)
+            px.stub_drive.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_double), C.c_int]
+            lat = (C.c_uint64 * max(nreq, 1))()
+            secs = C.c_double(0.0)
+            steps = []
+            for _ in range(nsteps):
+                assert px.stub_drive(proxy, nthreads, nconn, nreq, plen, lat, C.byref(secs), 3) == 0
+                al = sorted(int(x) for x in lat[:nreq])
+                steps.append(dict(seconds=secs.value, requests=nreq, threads=nthreads,
+                                  p50_us=al[len(al) // 2] / 1e3, p99_us=al[int(len(al) * 0.99)] / 1e3))
+            result["steps"] = steps
+            result["highest_rec"] = int(px.stub_highest_rec(proxy))
+            result["p50_us"], result["p99_us"] = steps[-1]["p50_us"], steps[-1]["p99_us"]
+            nreq_total = nreq * nsteps
         lat = []
-        for c in range(nconn):
+        for c in range(nconn if nthreads == 0 else 0):
             px.proxy_on_accept(proxy, 100 + c)            # spec_hooks.cpp:116
-        for i in range(nreq):
+        for i in range(nreq if nthreads == 0 else 0):
             c = i % nconn
             payload = bytes(((i * 31 + k) & 0xFF) for k in range(plen))
             buf = C.create_string_buffer(payload, plen)
             a = time.perf_counter_ns()
             px.proxy_on_read(proxy, buf, plen, 100 + c)   # spec_hooks.cpp:174: returns once committed
             lat.append(time.perf_counter_ns() - a)
-        for c in range(nconn):
+        for c in range(nconn if nthreads == 0 else 0):
             px.proxy_on_close(proxy, 100 + c)             # spec_hooks.cpp:150
-        result["highest_rec"] = int(px.stub_highest_rec(proxy))
-        lat.sort()
-        result["p50_us"] = lat[len(lat) // 2] / 1e3
-        result["p99_us"] = lat[int(len(lat) * 0.99)] / 1e3
+        if nthreads == 0:
+            result["highest_rec"] = int(px.stub_highest_rec(proxy))
+            lat.sort()
+            result["p50_us"] = lat[len(lat) // 2] / 1e3
+            result["p99_us"] = lat[int(len(lat) * 0.99)] / 1e3
     else:
-        want = nreq * plen
+        want = nreq * plen * nsteps
         t0 = time.time()
         while True:
             with lock:
-                got = sum(len(v) for v in received.values())
+                got = sum(v[0] for v in received.values())
                 nc = len(received)
-            if got >= want and nc >= nconn:
+            if got >= want and nc >= nconn * nsteps:
                 break
-            if time.time() - t0 > 90:
+            if time.time() - t0 > float(os.environ.get("PROXY_RUN_TIMEOUT", "90")):
                 break
             time.sleep(0.01)
         time.sleep(0.3)
         with lock:
             result["conns"] = len(received)
-            result["bytes"] = sum(len(v) for v in received.values())
-            result["sha"] = [hashlib.sha256(received[k]).hexdigest() for k in sorted(received)]
+            result["bytes"] = sum(v[0] for v in received.values())
+            result["sha"] = [received[k][1].hexdigest() for k in sorted(received)]
     cnt = int(px.stub_db_count())
     sizes = {}
     for i in range(cnt):
