@@ -132,6 +132,28 @@ static int ensure_host_ring(apus_replica *r)
     return APUS_OK;
 }
 
+static int leader_ring_init(apus_replica *r)
+{
+    if (r->pay_end) return APUS_OK;                      /* already a leader once */
+    if (!r->ring_slots) { r->ring_slots = r->cfg.ring_slots ? r->cfg.ring_slots : (1u << 16);
+                          r->ring_bytes = r->cfg.ring_bytes ? r->cfg.ring_bytes : (16u << 20); }
+    r->pay_end = (uint64_t *)calloc(r->ring_slots, sizeof(uint64_t));
+    if (!r->pay_end) return fail("out of memory");
+    if (r->cfg.ring_mode == APUS_RING_HOST_MAPPED) {
+        if (ensure_host_ring(r) != APUS_OK) return APUS_ERROR;
+        memset(r->ring_desc_host, 0, sizeof(apus_slot_t) * r->ring_slots);     /* no stamp matches ticket 0 */
+        CK(cudaHostGetDevicePointer(&r->ring_desc_dev, r->ring_desc_host, 0));
+        CK(cudaHostGetDevicePointer(&r->ring_pay_dev, r->ring_pay_host, 0));
+    } else {
+        CK(cudaMalloc(&r->ring_desc_dev, sizeof(apus_slot_t) * r->ring_slots));
+        CK(cudaMalloc(&r->ring_pay_dev, r->ring_bytes));
+        CK(cudaMalloc(&r->sub_tail_dev, 128));
+        CK(cudaMemset(r->sub_tail_dev, 0, 128));
+        CK(cudaHostAlloc(&r->sub_tail_stage, 64, cudaHostAllocPortable));
+    }
+    return APUS_OK;
+}
+
 static int replica_init(apus_replica *r, const apus_config_t *cfg, uint64_t log_len)
 {
     r->log_len = log_len;
@@ -167,21 +189,14 @@ static int replica_init(apus_replica *r, const apus_config_t *cfg, uint64_t log_
     CK(cudaEventCreate(&r->ev_start));
     CK(cudaEventCreate(&r->ev_stop));
 
-    if (is_leader(r)) {
-        r->pay_end = (uint64_t *)calloc(r->ring_slots, sizeof(uint64_t));
-        if (!r->pay_end) return fail("out of memory");
-        if (cfg->ring_mode == APUS_RING_HOST_MAPPED) {
-            if (ensure_host_ring(r) != APUS_OK) return APUS_ERROR;
-            memset(r->ring_desc_host, 0, sizeof(apus_slot_t) * r->ring_slots);     /* no stamp matches ticket 0 */
-            CK(cudaHostGetDevicePointer(&r->ring_desc_dev, r->ring_desc_host, 0));
-            CK(cudaHostGetDevicePointer(&r->ring_pay_dev, r->ring_pay_host, 0));
-        } else {
-            CK(cudaMalloc(&r->ring_desc_dev, sizeof(apus_slot_t) * r->ring_slots));
-            CK(cudaMalloc(&r->ring_pay_dev, r->ring_bytes));
-            CK(cudaMalloc(&r->sub_tail_dev, 128));
-            CK(cudaMemset(r->sub_tail_dev, 0, 128));
-            CK(cudaHostAlloc(&r->sub_tail_stage, 64, cudaHostAllocPortable));
-        }
+    if (is_leader(r) && leader_ring_init(r) != APUS_OK) return APUS_ERROR;
+    /* control-plane words: SID of a group whose leader is known from the start, no votes */
+    {
+        apus_ctlwords_t w;
+        memset(&w, 0, sizeof w);
+        w.sid = (r->cfg.term << 9) | (1ull << 8) | r->cfg.leader_idx;      /* [TERM|L|IDX], dare_server.h:46-61 */
+        for (int i = 0; i < 16; i++) w.vote_ack[i] = log_len;
+        CK(cudaMemcpy(r->region + APUS_CTL_OFF, &w, sizeof w, cudaMemcpyHostToDevice));
     }
     r->peer_ptr[cfg->server_idx] = r->region;
     return APUS_OK;
@@ -999,6 +1014,272 @@ extern "C" int apus_latency_samples(apus_replica_t *r, uint32_t *dst, uint32_t m
         dst[k] = tmp[(c.lat_count - take + k) & (APUS_LAT_RING - 1)];
     free(tmp);
     *n = take;
+    return APUS_OK;
+}
+
+
+/* ==================================================================================================
+ * Control plane on NVLink words.  Transport and log surgery only; the election policy
+ * (dare_server.c:1264-1743) lives with the caller, apus_b200/csrc/dare_entry.c.
+ * ================================================================================================== */
+#define SID_TERM(s) ((s) >> 9)
+
+static int own_read(apus_replica *r, size_t off, void *dst, size_t len)
+{
+    CK(cudaMemcpyAsync(r->stage, r->region + off, len, cudaMemcpyDeviceToHost, r->copy_stream));
+    CK(cudaStreamSynchronize(r->copy_stream));
+    memcpy(dst, r->stage, len);
+    return APUS_OK;
+}
+static int own_write(apus_replica *r, size_t off, const void *src, size_t len)
+{
+    memcpy(r->stage, src, len);
+    CK(cudaMemcpyAsync(r->region + off, r->stage, len, cudaMemcpyHostToDevice, r->copy_stream));
+    CK(cudaStreamSynchronize(r->copy_stream));
+    return APUS_OK;
+}
+/* a peer's region through the mapping the kernels store through (peer access or CUDA IPC): host-initiated copies */
+static int peer_read(apus_replica *r, uint8_t peer, size_t off, void *dst, size_t len)
+{
+    if (!r->peer_ptr[peer]) return fail("peer %u is not connected", (unsigned)peer);
+    CK(cudaMemcpyAsync(r->stage, (uint8_t *)r->peer_ptr[peer] + off, len, cudaMemcpyDefault, r->copy_stream));
+    CK(cudaStreamSynchronize(r->copy_stream));
+    memcpy(dst, r->stage, len);
+    return APUS_OK;
+}
+static int peer_write(apus_replica *r, uint8_t peer, size_t off, const void *src, size_t len)
+{
+    if (!r->peer_ptr[peer]) return fail("peer %u is not connected", (unsigned)peer);
+    memcpy(r->stage, src, len);
+    CK(cudaMemcpyAsync((uint8_t *)r->peer_ptr[peer] + off, r->stage, len, cudaMemcpyDefault, r->copy_stream));
+    CK(cudaStreamSynchronize(r->copy_stream));
+    return APUS_OK;
+}
+
+extern "C" int apus_ctl_read(apus_replica_t *r, apus_ctl_view_t *out)
+{
+    if (!r || !out) return fail("null argument");
+    DeviceGuard g(r->cfg.device);
+    apus_ctlwords_t w;
+    if (own_read(r, APUS_CTL_OFF, &w, sizeof w) != APUS_OK) return APUS_ERROR;
+    memset(out, 0, sizeof *out);
+    out->sid = w.sid; out->leader_sid = w.leader_sid; out->adj_end = w.adj_end; out->adj_count = w.adj_count;
+    for (int i = 0; i < APUS_MAX_SERVER_COUNT; i++) {
+        out->vote_ack[i] = w.vote_ack[i];
+        out->vote_req[i].sid = w.vote_req[i].sid; out->vote_req[i].index = w.vote_req[i].index;
+        out->vote_req[i].term = w.vote_req[i].term;
+        out->vote_req[i].cid[0] = w.vote_req[i].cid[0]; out->vote_req[i].cid[1] = w.vote_req[i].cid[1];
+    }
+    return APUS_OK;
+}
+
+extern "C" int apus_ctl_set_sid(apus_replica_t *r, uint64_t sid)
+{
+    if (!r) return fail("null argument");
+    DeviceGuard g(r->cfg.device);
+    return own_write(r, APUS_CTL_OFF + offsetof(apus_ctlwords_t, sid), &sid, 8);
+}
+
+extern "C" int apus_ctl_reset_votes(apus_replica_t *r)
+{
+    if (!r) return fail("null argument");
+    DeviceGuard g(r->cfg.device);
+    uint64_t v[16];
+    for (int i = 0; i < 16; i++) v[i] = r->log_len;              /* dare_server.c:1300: vote_ack[i] = log->len */
+    return own_write(r, APUS_CTL_OFF + offsetof(apus_ctlwords_t, vote_ack), v, sizeof v);
+}
+
+extern "C" int apus_ctl_clear_vote_request(apus_replica_t *r, uint8_t from_idx)
+{
+    if (!r || from_idx >= APUS_MAX_SERVER_COUNT) return fail("bad argument");
+    DeviceGuard g(r->cfg.device);
+    uint64_t z = 0;
+    return own_write(r, APUS_CTL_OFF + offsetof(apus_ctlwords_t, vote_req) + sizeof(apus_vote_req_t) * from_idx, &z, 8);
+}
+
+extern "C" int apus_ctl_send_vote_request(apus_replica_t *r, uint8_t peer_idx, uint64_t sid, uint64_t index, uint64_t term,
+                                          const void *cid16)
+{
+    if (!r || peer_idx >= r->cfg.group_size) return fail("bad argument");
+    DeviceGuard g(r->cfg.device);
+    apus_vote_req_t q;
+    memset(&q, 0, sizeof q);
+    q.index = index; q.term = term;
+    if (cid16) memcpy(q.cid, cid16, 16);
+    /* the sid word is what the voter polls: the rest of the record goes first */
+    const size_t base = APUS_CTL_OFF + offsetof(apus_ctlwords_t, vote_req) + sizeof(apus_vote_req_t) * r->cfg.server_idx;
+    if (peer_write(r, peer_idx, base + 8, (uint8_t *)&q + 8, sizeof q - 8) != APUS_OK) return APUS_ERROR;
+    return peer_write(r, peer_idx, base, &sid, 8);
+}
+
+extern "C" int apus_ctl_send_vote_ack(apus_replica_t *r, uint8_t candidate_idx, uint64_t commit)
+{
+    if (!r || candidate_idx >= r->cfg.group_size) return fail("bad argument");
+    DeviceGuard g(r->cfg.device);
+    return peer_write(r, candidate_idx, APUS_CTL_OFF + offsetof(apus_ctlwords_t, vote_ack) + 8u * r->cfg.server_idx, &commit, 8);
+}
+
+/* the entry with cumulative number `cum` (== its idx: every entry ever appended is counted, idx starts at 1):
+ * offset from the offset index, {idx, term} and stride from its header */
+static int entry_at(apus_replica *r, int peer, uint64_t cum, uint64_t *off, uint64_t *idx, uint64_t *term, uint32_t *stride)
+{
+    uint32_t w = 0;
+    const size_t ioff = APUS_INDEX_OFF + 4ull * (cum & (r->idx_cap - 1));
+    int rc = peer < 0 ? own_read(r, ioff, &w, 4) : peer_read(r, (uint8_t)peer, ioff, &w, 4);
+    if (rc != APUS_OK) return rc;
+    const uint64_t o = w & ~APUS_IDX_HEAD_FLAG;
+    if (o + APUS_HDR_BYTES > r->log_len) return fail("offset index names an offset beyond the log");
+    uint8_t h[64];
+    rc = peer < 0 ? own_read(r, r->entries_off + o, h, 64) : peer_read(r, (uint8_t)peer, r->entries_off + o, h, 64);
+    if (rc != APUS_OK) return rc;
+    memcpy(idx, h + E_IDX, 8); memcpy(term, h + E_TERM, 8);
+    uint16_t len; memcpy(&len, h + E_DATA, 2);
+    const uint8_t ty = h[E_TYPE];
+    *stride = (ty == T_NOOP || ty == T_CONFIG || ty == T_HEAD) ? APUS_HDR_BYTES : APUS_HDR_BYTES + len;
+    *off = o;
+    return APUS_OK;
+}
+
+extern "C" int apus_ctl_last_entry(apus_replica_t *r, uint64_t *idx, uint64_t *term, uint64_t *commit, uint64_t *end)
+{
+    if (!r || !idx || !term) return fail("null argument");
+    if (r->in_flight) return fail("the replica's kernel must be stopped (exclusive log access)");
+    DeviceGuard g(r->cfg.device);
+    apus_loghdr_t h; apus_ctrl_t c;
+    if (own_read(r, APUS_HDR_OFF, &h, sizeof h) != APUS_OK || own_read(r, 0, &c, sizeof c) != APUS_OK) return APUS_ERROR;
+    if (commit) *commit = h.commit;
+    if (end) *end = h.end;
+    const uint64_t count = is_leader(r) ? c.published : c.acked;
+    *idx = 0; *term = 0;
+    if (h.end == r->log_len || count == 0) return APUS_OK;            /* empty log */
+    uint64_t off; uint32_t stride;
+    if (entry_at(r, -1, count, &off, idx, term, &stride) != APUS_OK) return APUS_ERROR;
+    if (*idx != count) return fail("entry counter %llu does not match the idx %llu of the last entry", (unsigned long long)count, (unsigned long long)*idx);
+    return APUS_OK;
+}
+
+static int copy_to_peer(apus_replica *r, uint8_t peer, size_t off, size_t len)
+{
+    if (!len) return APUS_OK;
+    CK(cudaMemcpyAsync((uint8_t *)r->peer_ptr[peer] + off, r->region + off, len, cudaMemcpyDefault, r->copy_stream));
+    return APUS_OK;
+}
+
+extern "C" int apus_ctl_adjust_follower(apus_replica_t *r, uint8_t peer, uint64_t sid, uint64_t *resent)
+{
+    if (!r || peer >= r->cfg.group_size || peer == r->cfg.server_idx) return fail("bad argument");
+    if (!is_leader(r)) return fail("log adjustment is the leader's job");
+    if (r->in_flight) return fail("the leader's kernel must be stopped");
+    if (!r->peer_ptr[peer]) return fail("peer %u is not connected", (unsigned)peer);
+    DeviceGuard g(r->cfg.device);
+    const uint64_t L = r->log_len;
+    apus_loghdr_t mh, fh; apus_ctrl_t mc, fc;
+    if (own_read(r, APUS_HDR_OFF, &mh, sizeof mh) != APUS_OK || own_read(r, 0, &mc, sizeof mc) != APUS_OK) return APUS_ERROR;
+    if (peer_read(r, peer, APUS_HDR_OFF, &fh, sizeof fh) != APUS_OK || peer_read(r, peer, 0, &fc, sizeof fc) != APUS_OK) return APUS_ERROR;
+    const uint64_t mine = mc.published, theirs = fc.acked;      /* idx of the last entry each of us holds */
+    /* last entry we share: walk down from min(mine, theirs) comparing {offset, idx, term} (the leader's log is the
+     * truth, log_find_remote_end_offset, dare_log.h:362-394).  Entries up to the follower's commit are shared by
+     * construction (they are committed), so the walk ends there at the latest. */
+    uint64_t j = mine < theirs ? mine : theirs;
+    uint64_t keep_end = (mh.end == L) ? L : 0;                   /* offset right behind the last shared entry */
+    bool found = false;
+    while (j > 0) {
+        uint64_t o1, i1, t1, o2, i2, t2; uint32_t s1, s2;
+        if (entry_at(r, -1, j, &o1, &i1, &t1, &s1) != APUS_OK || entry_at(r, peer, j, &o2, &i2, &t2, &s2) != APUS_OK) return APUS_ERROR;
+        if (o1 == o2 && i1 == i2 && t1 == t2 && i1 == j) { keep_end = o1 + s1; if (keep_end == L) keep_end = 0; found = true; break; }
+        j--;
+    }
+    if (!found) { j = 0; keep_end = 0; }
+    uint64_t bytes = 0;
+    if (mine > j && mh.end != L) {
+        /* everything behind the shared prefix: entry bytes [keep_end, my end) -- a wrapped range is two copies, a wrap
+         * gap (ghost header) travels with it -- and the offset-index words of entries j+1 .. mine */
+        const uint64_t from = (j == 0) ? ((mh.head <= mh.end) ? mh.head : mh.head) : keep_end;
+        const uint64_t to = mh.end;
+        if (to > from) { if (copy_to_peer(r, peer, r->entries_off + from, to - from) != APUS_OK) return APUS_ERROR; bytes += to - from; }
+        else if (to < from || (to == from && mine > j)) {
+            if (copy_to_peer(r, peer, r->entries_off + from, L - from) != APUS_OK) return APUS_ERROR;
+            if (copy_to_peer(r, peer, r->entries_off, to) != APUS_OK) return APUS_ERROR;
+            bytes += L - from + to;
+        }
+        const uint64_t cap = r->idx_cap, a = (j + 1) & (cap - 1), n = mine - j;
+        if (n >= cap) { if (copy_to_peer(r, peer, APUS_INDEX_OFF, 4ull * cap) != APUS_OK) return APUS_ERROR; }
+        else if (a + n <= cap) { if (copy_to_peer(r, peer, APUS_INDEX_OFF + 4ull * a, 4ull * n) != APUS_OK) return APUS_ERROR; }
+        else {
+            if (copy_to_peer(r, peer, APUS_INDEX_OFF + 4ull * a, 4ull * (cap - a)) != APUS_OK) return APUS_ERROR;
+            if (copy_to_peer(r, peer, APUS_INDEX_OFF, 4ull * (a + n - cap)) != APUS_OK) return APUS_ERROR;
+        }
+        CK(cudaStreamSynchronize(r->copy_stream));
+    }
+    /* the follower now holds exactly my log: set its end (LR_SET_END, dare_ibv_rc.c:1396-1412) and its entry counter,
+     * count it as holding everything I hold, then tell it whom to follow */
+    const uint64_t endw[2] = { mh.end, mh.end };
+    if (peer_write(r, peer, APUS_HDR_OFF + offsetof(apus_loghdr_t, end), &endw[0], 8) != APUS_OK) return APUS_ERROR;
+    if (peer_write(r, peer, APUS_HDR_OFF + offsetof(apus_loghdr_t, old_end), &endw[1], 8) != APUS_OK) return APUS_ERROR;
+    if (peer_write(r, peer, offsetof(apus_ctrl_t, acked), &mine, 8) != APUS_OK) return APUS_ERROR;
+    const uint64_t none = L;
+    if (peer_write(r, peer, offsetof(apus_ctrl_t, pend_head_end), &none, 8) != APUS_OK) return APUS_ERROR;
+    if (own_write(r, offsetof(apus_ctrl_t, ack) + 8u * peer, &mine, 8) != APUS_OK) return APUS_ERROR;
+    const uint64_t adj[3] = { sid, mh.end, mine };
+    if (peer_write(r, peer, APUS_CTL_OFF + offsetof(apus_ctlwords_t, adj_end), &adj[1], 16) != APUS_OK) return APUS_ERROR;
+    if (peer_write(r, peer, APUS_CTL_OFF + offsetof(apus_ctlwords_t, leader_sid), &adj[0], 8) != APUS_OK) return APUS_ERROR;
+    if (resent) *resent = bytes;
+    return APUS_OK;
+}
+
+extern "C" int apus_replica_disconnect(apus_replica_t *r, uint8_t peer_idx)
+{
+    if (!r || peer_idx >= APUS_MAX_SERVER_COUNT) return fail("bad argument");
+    if (r->in_flight) return fail("stop the kernel first");
+    /* the mapping itself is left alone (closing a handle whose exporter died is not worth the risk): nothing stores there any more */
+    if (peer_idx != r->cfg.server_idx) r->peer_ptr[peer_idx] = NULL;
+    return APUS_OK;
+}
+
+extern "C" int apus_replica_set_role(apus_replica_t *r, uint8_t leader_idx, uint64_t term)
+{
+    if (!r || leader_idx >= r->cfg.group_size) return fail("bad argument");
+    if (r->in_flight) return fail("stop the kernel first");
+    DeviceGuard g(r->cfg.device);
+    const bool was_leader = is_leader(r);
+    r->cfg.leader_idx = leader_idx;
+    r->cfg.term = term;
+    if (!is_leader(r)) {
+        if (!r->peer_ptr[leader_idx]) return fail("not connected to the new leader");
+        return APUS_OK;              /* the leader's adjustment already set end / old_end / the entry counter */
+    }
+    if (was_leader) return APUS_OK;
+    /* ---- a follower takes the log over as it holds it ---- */
+    if (leader_ring_init(r) != APUS_OK) return APUS_ERROR;
+    r->submitted = r->flushed = r->belled = 0; r->pay_head = r->pay_flushed = 0;
+    r->hw->sub_tail = 0; r->hw->consumed = 0; r->hw->committed_tickets = 0;
+    apus_loghdr_t h; apus_ctrl_t c;
+    if (own_read(r, APUS_HDR_OFF, &h, sizeof h) != APUS_OK || own_read(r, 0, &c, sizeof c) != APUS_OK) return APUS_ERROR;
+    const uint64_t L = r->log_len, last = c.acked;
+    /* entries between my commit offset and my end are published but not committed: count them by walking the offset
+     * index backwards until an entry starts at or before the commit offset */
+    uint64_t unc = 0, tail = L;
+    if (h.end != L && last) {
+        uint64_t off, idx, tm; uint32_t st;
+        if (entry_at(r, -1, last, &off, &idx, &tm, &st) != APUS_OK) return APUS_ERROR;
+        tail = off;
+        uint64_t jj = last;
+        const uint64_t dist_commit = (h.end >= h.commit) ? h.end - h.commit : L - (h.commit - h.end);
+        while (jj > 0) {
+            if (entry_at(r, -1, jj, &off, &idx, &tm, &st) != APUS_OK) return APUS_ERROR;
+            const uint64_t d = (h.end >= off) ? h.end - off : L - (off - h.end);     /* bytes from this entry to my end */
+            if (d > dist_commit || dist_commit == 0) break;
+            unc++; jj--;
+            if (unc > (1u << 20)) return fail("too many uncommitted entries to take over");
+        }
+    }
+    c.next_idx = last + 1; c.published = last; c.committed = last - unc;
+    c.consumed = 0; c.committed_tickets = 0;
+    c.hwm = L;                       /* treat every range as written before: prefill reads the log (zeros where it was never written) */
+    for (int i = 0; i < 16; i++) { c.ack[i] = 0; c.apply_off[i] = h.head; }        /* dare_server.c:1507-1510 */
+    h.tail = tail; h.old_end = h.end;
+    if (own_write(r, 0, &c, offsetof(apus_ctrl_t, fin_entries)) != APUS_OK) return APUS_ERROR;
+    if (own_write(r, APUS_HDR_OFF, &h, sizeof h) != APUS_OK) return APUS_ERROR;
     return APUS_OK;
 }
 

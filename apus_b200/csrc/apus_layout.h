@@ -112,6 +112,25 @@ typedef struct apus_ctrl {
                                     [3] fast placements, [4] slow placements, [7] place-turn hold (ns) */
 } apus_ctrl_t;
 
+/* Control-plane words (N1: election, votes, log adjustment), at APUS_CTL_OFF inside the ctrl block -- the part of the
+ * reference's ctrl_data_t (dare_server.h:121-138: sid, vote_req[], vote_ack[], prv_data) this engine needs.  Written by
+ * HOST-initiated copies over NVLink (peers' blocks) and read by the host; the kernels never touch them. */
+#define APUS_CTL_OFF 1024u
+typedef struct apus_vote_req {       /* vote_req_t, dare_server.h:97-103 */
+    uint64_t sid, index, term;
+    uint64_t cid[2];                 /* dare_cid_t */
+    uint64_t pad[3];
+} apus_vote_req_t;
+typedef struct apus_ctlwords {
+    uint64_t sid;                    /* this replica's SID [TERM|L|IDX] (dare_server.h:46-61); voting = moving it (prv_data_t.vote_sid) */
+    uint64_t leader_sid;             /* written by an elected leader once it has adjusted this replica's log: "follow me" */
+    uint64_t adj_end;                /* ... the end offset ... */
+    uint64_t adj_count;              /* ... and the entry count (== idx of the last entry) it left this replica at */
+    uint64_t pad[4];
+    uint64_t vote_ack[16];           /* written by voters into the CANDIDATE's block: their commit offset (log_len = no vote) */
+    apus_vote_req_t vote_req[APUS_MAX_SERVERS];   /* [i] written by candidate i into everybody's block */
+} apus_ctlwords_t;
+
 /* Sequencer shared by the leader's worker CTAs (device memory, gpu-scope atomics).
  * A worker CLAIMS the next slots of the submission ring (one compare-and-swap), builds its
  * tile in parallel with the others, but PLACES it in the log and PUBLISHES its tail strictly

@@ -222,6 +222,38 @@ uint64_t apus_leader_suspect(apus_replica_t *follower);
 /* %globaltimer (ns) of the leader kernel's latest commit (device clock; step timing of resident kernels) */
 uint64_t apus_last_commit_ns(apus_replica_t *leader);
 
+/* ---- control plane on NVLink words (election, votes, log adjustment) ---------------------
+ * Transport only: WHO votes for whom and when is decided by the caller (libapus_dare.so restates dare_server.c's
+ * start_election / poll_vote_requests / poll_vote_count on top of these).  The words live in every replica's HBM
+ * region next to its ack / tail slots (apus_layout.h: apus_ctlwords_t, the needed part of ctrl_data_t,
+ * dare_server.h:121-138); a peer's words are written with a host-initiated copy through the same mapping the
+ * kernels store through.  Replaces dare_ib_send_vote_request / replicate_vote / send_vote_ack
+ * (dare_ibv_rc.c:969-1170), log_adjustment (dare_ibv_rc.c:1292-1451) and recover_log. */
+typedef struct apus_ctl_view {
+    uint64_t sid, leader_sid, adj_end, adj_count;
+    uint64_t vote_ack[APUS_MAX_SERVER_COUNT];          /* commit offsets granted to me (log size = no vote) */
+    struct { uint64_t sid, index, term, cid[2]; } vote_req[APUS_MAX_SERVER_COUNT];
+} apus_ctl_view_t;
+int  apus_ctl_read(apus_replica_t *r, apus_ctl_view_t *out);
+int  apus_ctl_set_sid(apus_replica_t *r, uint64_t sid);
+int  apus_ctl_reset_votes(apus_replica_t *r);                                  /* start_election: vote_ack[] := none */
+int  apus_ctl_clear_vote_request(apus_replica_t *r, uint8_t from_idx);
+int  apus_ctl_send_vote_request(apus_replica_t *r, uint8_t peer_idx, uint64_t sid, uint64_t index, uint64_t term,
+                                const void *cid16);
+int  apus_ctl_send_vote_ack(apus_replica_t *r, uint8_t candidate_idx, uint64_t commit);
+/* idx and term of the last entry this replica holds (0,0 when the log is empty), its commit and end offsets; the
+ * replica's kernel must be stopped (exclusive access, as dare_ib_revoke_log_access gives the reference) */
+int  apus_ctl_last_entry(apus_replica_t *r, uint64_t *idx, uint64_t *term, uint64_t *commit, uint64_t *end);
+/* elected leader, kernels stopped: bring follower `peer_idx` to my log -- find the last entry we share from its
+ * commit offset on (log_find_remote_end_offset, dare_log.h:362-394), copy everything behind it (entry bytes and
+ * offset index) peer to peer, and tell it to follow `sid` from there.  *resent = bytes copied. */
+int  apus_ctl_adjust_follower(apus_replica_t *leader, uint8_t peer_idx, uint64_t sid, uint64_t *resent);
+/* role and term for the next launch.  Becoming leader takes over the log as this replica holds it (entry counters,
+ * tail, submission ring); becoming follower adopts what the new leader's adjustment left (apus_ctl_view.adj_*). */
+int  apus_replica_set_role(apus_replica_t *r, uint8_t leader_idx, uint64_t term);
+/* stop storing into a peer that is gone (dare_ib_disconnect_server, dare_server.c:1200) */
+int  apus_replica_disconnect(apus_replica_t *r, uint8_t peer_idx);
+
 /* control plane hooks used by pruning (log_pruning, dare_server.c:1996-2067) */
 int  apus_set_head(apus_replica_t *r, uint64_t head);
 int  apus_remote_apply_offsets(apus_replica_t *leader, uint64_t out[APUS_MAX_SERVER_COUNT]);
