@@ -27,6 +27,7 @@
 extern "C" cudaError_t apus_launch_roles(const apus_role_t *d_roles, int n_roles, cudaStream_t stream);
 extern "C" size_t apus_kernel_smem_bytes(void);
 
+#define MAX_ROLES 160          /* CTAs of one fused launch: leader workers + local followers */
 static __thread char g_err[512];
 
 static int fail(const char *fmt, ...)
@@ -181,7 +182,7 @@ static int replica_init(apus_replica *r, const apus_config_t *cfg, uint64_t log_
     r->stage_bytes = 1u << 20;
     CK(cudaHostAlloc(&r->stage, r->stage_bytes, cudaHostAllocPortable));
     CK(cudaMalloc(&r->d_ctx, sizeof(apus_devctx_t)));
-    CK(cudaMalloc(&r->d_roles, sizeof(apus_role_t) * 64));
+    CK(cudaMalloc(&r->d_roles, sizeof(apus_role_t) * MAX_ROLES));
     CK(cudaMalloc(&r->d_lat, sizeof(uint32_t) * APUS_LAT_RING));
     CK(cudaMemset(r->d_lat, 0, sizeof(uint32_t) * APUS_LAT_RING));
     CK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
@@ -331,7 +332,7 @@ static void fill_ctx(apus_replica *r, uint64_t target)
     c->term = r->cfg.term; c->log_len = r->log_len; c->target = target;
     c->entries_off = r->entries_off; c->idx_mask = r->idx_cap - 1;
     c->n_workers = r->cfg.leader_ctas ? r->cfg.leader_ctas : 4;
-    if (c->n_workers > 32) c->n_workers = 32;
+    if (c->n_workers > 96) c->n_workers = 96;
     c->epoch = (uint32_t)(r->launches + 1);
     c->doorbell_relay = (r->cfg.ring_mode == APUS_RING_HOST_MAPPED && c->n_workers >= 2) ? 1u : 0u;
     c->slot_poll = (r->cfg.ring_mode == APUS_RING_HOST_MAPPED) ? 1u : 0u;
@@ -359,7 +360,7 @@ extern "C" int apus_replicas_launch(apus_replica_t **rs, int n, uint64_t target)
         if (!is_leader(rs[i]) && !rs[i]->peer_ptr[rs[i]->cfg.leader_idx]) return fail("follower not connected to its leader");
     }
     DeviceGuard g(owner->cfg.device);
-    apus_role_t roles[64];
+    apus_role_t roles[MAX_ROLES];
     int nroles = 0;
     for (int i = 0; i < n; i++) {
         apus_replica *r = rs[i];
@@ -368,11 +369,11 @@ extern "C" int apus_replicas_launch(apus_replica_t **rs, int n, uint64_t target)
         CK(cudaMemcpyAsync(r->d_ctx, &r->h_ctx, sizeof(apus_devctx_t), cudaMemcpyHostToDevice, owner->stream));
         if (is_leader(r)) {
             for (uint32_t w = 0; w < r->h_ctx.n_workers; w++) {
-                if (nroles >= 64) return fail("too many roles in one launch");
+                if (nroles >= MAX_ROLES) return fail("too many roles in one launch");
                 roles[nroles].kind = APUS_ROLE_LEADER; roles[nroles].worker = w; roles[nroles].ctx = r->d_ctx; nroles++;
             }
         } else {
-            if (nroles >= 64) return fail("too many roles in one launch");
+            if (nroles >= MAX_ROLES) return fail("too many roles in one launch");
             roles[nroles].kind = APUS_ROLE_FOLLOWER; roles[nroles].worker = 0; roles[nroles].ctx = r->d_ctx; nroles++;
         }
     }
@@ -663,6 +664,9 @@ static struct {
     const fill_job *job;
     volatile uint64_t gen;                 /* job generation */
     volatile uint32_t next, done_parts, parts, chunk;
+    volatile uint8_t *done;                /* per part: filled */
+    volatile uint32_t adv, adv_lock;       /* parts [0, adv) are filled and their doorbell has been rung */
+    int progressive;                       /* ring the doorbell as the filled prefix grows (host-mapped ring) */
 } g_pool = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER };
 
 static void pool_work(const fill_job *j)
@@ -672,6 +676,24 @@ static void pool_work(const fill_job *j)
         if (p >= g_pool.parts) break;
         const uint32_t k0 = p * g_pool.chunk, k1 = (k0 + g_pool.chunk < j->n) ? k0 + g_pool.chunk : j->n;
         fill_range(j, k0, k1);
+        if (g_pool.progressive) {
+            /* the kernel may start on the filled PREFIX while the rest is still being written: whoever gets the
+             * advance lock moves the doorbell over every part that is complete and contiguous */
+            __atomic_store_n(&g_pool.done[p], 1, __ATOMIC_RELEASE);
+            if (__sync_bool_compare_and_swap(&g_pool.adv_lock, 0, 1)) {
+                uint32_t a = g_pool.adv;
+                while (a < g_pool.parts && __atomic_load_n(&g_pool.done[a], __ATOMIC_ACQUIRE)) a++;
+                if (a != g_pool.adv) {
+                    uint64_t upto = j->first_slot + (uint64_t)a * g_pool.chunk;
+                    if (upto > j->first_slot + j->n) upto = j->first_slot + j->n;
+                    __sync_synchronize();
+                    j->r->hw->sub_tail = upto;
+                    j->r->belled = upto;
+                    g_pool.adv = a;
+                }
+                __atomic_store_n(&g_pool.adv_lock, 0, __ATOMIC_RELEASE);
+            }
+        }
         __atomic_fetch_add(&g_pool.done_parts, 1, __ATOMIC_ACQ_REL);
     }
 }
@@ -714,6 +736,12 @@ static void pool_run(const fill_job *j)
     g_pool.chunk = 4096;
     g_pool.parts = (j->n + g_pool.chunk - 1) / g_pool.chunk;
     g_pool.next = 0; g_pool.done_parts = 0;
+    g_pool.progressive = (j->r->cfg.ring_mode == APUS_RING_HOST_MAPPED && !j->r->defer && j->r->flushed == j->r->submitted);
+    g_pool.adv = 0; g_pool.adv_lock = 0;
+    static uint8_t *done_buf; static uint32_t done_cap;
+    if (done_cap < g_pool.parts) { free(done_buf); done_cap = g_pool.parts * 2; done_buf = (uint8_t *)malloc(done_cap); }
+    memset(done_buf, 0, g_pool.parts);
+    g_pool.done = done_buf;
     __atomic_fetch_add(&g_pool.gen, 1, __ATOMIC_RELEASE);
     pthread_cond_broadcast(&g_pool.cv);
     pthread_mutex_unlock(&g_pool.mu);

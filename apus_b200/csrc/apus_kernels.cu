@@ -128,6 +128,16 @@ __device__ __forceinline__ uint64_t ring_dist(uint64_t from, uint64_t to, uint64
 {
     return to >= from ? to - from : L - (from - to);
 }
+// A head offset read from the log header (a host control plane may move it, apus_set_head) replaces the one the
+// placement state carries only when it lies INSIDE the used region [head, end]: a header value read a while ago -- the
+// reader may have waited for its turn while almost a whole ring was appended -- lies in the free region by now, and
+// "closer to end" alone would mistake it for an advance and move the head backwards into freshly written bytes.
+__device__ __forceinline__ uint64_t merge_head(uint64_t head, uint64_t hdr_head, uint64_t end, uint64_t L)
+{
+    if (end == L || hdr_head == head) return head;
+    const uint64_t used = ring_dist(head, end, L), at = ring_dist(head, hdr_head, L);
+    return (at <= used) ? hdr_head : head;
+}
 
 #define WATCHDOG_NS (20ull * 1000ull * 1000ull * 1000ull)
 
@@ -268,7 +278,14 @@ __device__ __forceinline__ uint32_t hdr_byte(uint32_t j, uint64_t idx, uint64_t 
 __device__ __noinline__ void group_write_header(uint8_t *e, int sub, int gl, uint64_t idx, uint64_t term, uint64_t req_id,
                                                    uint32_t clt, uint32_t type, uint32_t sender, bool skip_sender)
 {
-    if ((((uint32_t)(uintptr_t)e) & 7u) == 0) {
+    if ((((uint32_t)(uintptr_t)e) & 15u) == 0 && !skip_sender) {
+        // 16 B aligned entry: two 16 B stores, one 8 B store, one byte; bytes 41..47 stay (hole)
+        if (sub == 0) *reinterpret_cast<uint4 *>(e + 0) = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)term, (uint32_t)(term >> 32));
+        else if (sub == 1) *reinterpret_cast<uint4 *>(e + 16) = make_uint4((uint32_t)req_id, (uint32_t)(req_id >> 32),
+                                                                         (clt & 0xffffu) | (type << 16) | (sender << 24), 0u);
+        else if (sub == 2) *reinterpret_cast<uint64_t *>(e + 32) = 0;
+        else if (sub == 3) e[40] = 0;
+    } else if ((((uint32_t)(uintptr_t)e) & 7u) == 0) {
         // aligned entry: 8-byte stores for bytes 0..39, byte 40 separately; bytes 41..47 stay (hole)
         if (sub == 0) *reinterpret_cast<uint64_t *>(e + 0) = idx;
         else if (sub == 1) *reinterpret_cast<uint64_t *>(e + 8) = term;
@@ -709,6 +726,7 @@ struct Express {
     uint32_t have_place;               // the four values above are what the sequencer records hold
     uint32_t hold;                     // I still hold publish turn next_seq (self-certified data, not fenced yet)
     uint64_t pub_tail_seen;            // publish-ring tail as last read (lane 0)
+    uint64_t dt[5];                    // ns of the latest request: place, compose, push, publish turn, publish (profiling)
 };
 
 __device__ __forceinline__ void express_release(apus_seq_t *seq, Express &X, int lane)
@@ -776,7 +794,7 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
         X.placed = placed; X.end = end; X.tf = tf; X.head = headv; X.have_place = 1; X.next_seq = claimed;
     }
     const bool wrapped = (tf & APUS_REC_WRAPPED) != 0, prevh = (tf & APUS_REC_PREV_HEAD) != 0;
-    if (end != L && ring_dist(hh, end, L) < ring_dist(headv, end, L)) headv = hh;
+    headv = merge_head(headv, hh, end, L);
     const uint64_t pos0 = (end == L) ? 0 : end;
     const uint64_t used = (end == L) ? 0 : ring_dist(headv, end, L);
     const bool autoprune = (cx->flags & APUS_FLAG_AUTOPRUNE) != 0;
@@ -805,6 +823,8 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
     }
     X.placed = cum; X.end = ne; X.tf = a | (nw ? APUS_REC_WRAPPED : 0ull); X.head = headv; X.have_place = 1;
     const uint64_t idx = S->idx_base + placed + 1;
+    const bool xprof = (cx->flags & APUS_FLAG_STATS) != 0;
+    const uint64_t t_place = xprof ? globaltimer_ns() : 0;
 
     // ---- compose: prefill (holes keep what the log held), header, data image ----
     const uint64_t a16 = a & ~15ull;
@@ -819,6 +839,7 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
     group_write_header(e, lane, 32, idx, cx->term, req_id, clt, ty, me, false);
     group_copy_smem(e + E_DATA, xsl, nb, lane, 32);
     __syncwarp();
+    const uint64_t t_compose = xprof ? globaltimer_ns() : 0;
 
     // ---- push: local log first, then every follower; checksum of exactly the bytes [a, b) ----
     uint64_t cs = 0;
@@ -858,6 +879,7 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
     // exactly `a` and can verify the one entry; a follower that lags is served by a fenced publish (it may skip records)
     const bool caught = __ballot_sync(0xffffffffu, isf && ackv != placed) == 0;
 
+    const uint64_t t_push = xprof ? globaltimer_ns() : 0;
     // ---- publish turn (mine already when I held it) ----
     uint64_t h = X.pub_h;
     if (!X.hold) {
@@ -883,6 +905,7 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
         }
     }
     __syncwarp();
+    const uint64_t t_turn = xprof ? globaltimer_ns() : 0;
     const uint64_t cumt = cum | ((cx->term & 0xffffull) << APUS_PUB_TERM_SHIFT);
     const bool cert = caught && !(cx->flags & APUS_FLAG_NO_EXPRESS);
     if (isf) {
@@ -903,6 +926,10 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
         st_relaxed_sys_2x64(&pubring[h & PUBMASK].w[2 * q], h + 1, val);
     }
     X.next_seq = claimed + 1; X.pub_h = h + 1;
+    if (xprof) {
+        const uint64_t t_end = globaltimer_ns();
+        X.dt[0] = t_place - t_deq; X.dt[1] = t_compose - t_place; X.dt[2] = t_push - t_compose; X.dt[3] = t_turn - t_push; X.dt[4] = t_end - t_turn;
+    }
     if (cert) {
         X.hold = 1;                    // nobody is waiting: keep the turn, skip the fence
     } else {
@@ -986,6 +1013,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
 #define PHASE(i) do { if (prof) { const uint64_t _t = globaltimer_ns(); ph[i] += _t - tprev; tprev = _t; } } while (0)
     Express X;
     X.next_seq = 0; X.placed = 0; X.end = 0; X.tf = 0; X.head = 0; X.pub_h = 0; X.have_place = 0; X.hold = 0; X.pub_tail_seen = 0;
+    for (int q = 0; q < 5; q++) X.dt[q] = 0;
     uint64_t xguess = ctrl->consumed;          // worker 0: the slot it expects to be claimed next
 
     for (;;) {
@@ -1059,7 +1087,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         const int rc = leader_express(cx, S, X, claimed, sv, slot_ok, img, lane);
                         if (rc == 0) {
                             xguess = claimed + 1; last_progress = globaltimer_ns();
-                            if (prof) { tn[5]++; ph[7]++; }
+                            if (prof) { tn[5]++; ph[7]++; for (int q = 0; q < 5; q++) ph[1 + q] += X.dt[q]; }
                             continue;
                         }
                         if (rc == 2) { fin = 1; break; }
@@ -1160,7 +1188,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         const uint64_t tail = tf & ~(APUS_REC_WRAPPED | APUS_REC_PREV_HEAD);
                         // ---- fast path ----
                         // a host control plane may also move the head (apus_set_head): take the newer of the two
-                        if (end != L && ring_dist(hh, end, L) < ring_dist(headv, end, L)) headv = hh;
+                        headv = merge_head(headv, hh, end, L);
                         S->st_head = headv;
                         const uint64_t pos0 = (end == L) ? 0 : end;
                         const uint64_t used = (end == L) ? 0 : ring_dist(headv, end, L);
@@ -1259,8 +1287,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                 if (tid == 0) {
                     // a host control plane may have moved the head; the apply offsets move all the time
                     const uint64_t hh = ld_relaxed_sys(&hdr->head);
-                    if (S->st_end != cx->log_len && ring_dist(hh, S->st_end, cx->log_len) < ring_dist(S->st_head, S->st_end, cx->log_len))
-                        S->st_head = hh;
+                    S->st_head = merge_head(S->st_head, hh, S->st_end, cx->log_len);
                 }
                 if (tid < N) S->ap[tid] = (tid == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[tid]);
                 bar_sync(1, NT);
@@ -1275,7 +1302,35 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             // ---- T3: prefill the image (zeros when the range is fresh, else the bytes the local
             //      log holds: holes of an entry keep what was there, like the reference) and
             //      stage the payload-ring range of the sub-tile; all loads in flight together
-            if (S->fresh) {
+            // A composed entry overwrites all of its bytes except two HOLES -- bytes 41..47 of the header and the slack
+            // behind the data image ([48 + nb, stride): 14 bytes for a request) -- which keep what the log held
+            // (dare_log.h:507-529 never writes them).  For tiles of large entries only the chunks that overlap a hole are
+            // brought in; small entries are mostly holes' neighbours, the whole range is read in one coalesced sweep.
+            const bool holes_only = !gap && (b - a) >= (uint64_t)(m + autoh) * 512ull;
+            if (holes_only) {
+                for (uint32_t j = tid; j < m + autoh; j += NT) {
+                    uint32_t rel, es_, nb_;
+                    if (autoh && j == 0) { rel = 0; es_ = APUS_HDR_BYTES; nb_ = 8; }
+                    else {
+                        const uint32_t k = kbase + j - autoh;
+                        rel = S->hbytes + (S->cum_es[k] - S->base_es) - S->es[k];
+                        es_ = S->es[k]; nb_ = data_bytes(S->ty[k], sl[k].len);
+                    }
+                    const uint64_t eo = a + rel;
+                    const uint64_t h0 = eo + 41, h1 = eo + 47, g0 = eo + 48 + nb_, g1 = eo + es_ - 1;   // hole byte ranges (inclusive)
+                    const uint64_t cs[4] = { h0 >> 4, h1 >> 4, g0 >> 4, g1 >> 4 };
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (q == 3 && g1 < g0) continue;
+                        if (q == 2 && g1 < g0) continue;
+                        if (q > 0 && cs[q] == cs[q - 1]) continue;
+                        const uint64_t lo = cs[q] << 4;
+                        if (lo < a16 || lo >= a16 + 16ull * nchunks) continue;
+                        reinterpret_cast<uint4 *>(img)[(lo - a16) >> 4] =
+                            S->fresh ? make_uint4(0, 0, 0, 0) : ld_relaxed_sys_v4(entries + lo);
+                    }
+                }
+            } else if (S->fresh) {
                 for (uint32_t c = tid; c < nchunks; c += NT) reinterpret_cast<uint4 *>(img)[c] = make_uint4(0, 0, 0, 0);
             } else {
                 cta_fetch_chunks(img, entries + a16, nchunks, tid);
@@ -1471,6 +1526,8 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
     uint64_t host_applied = hdr->apply;  // HOST_APPLY: the offset the application has replayed (what the leader may prune behind)
     uint64_t last_hb = ld_relaxed_sys(&ctrl->hb), last_hb_t = globaltimer_ns();
     bool suspected = false;
+    const bool fstat = (cx->flags & APUS_FLAG_STATS) != 0;       // follower profiling: phase_ns[0] certificates verified,
+    uint64_t cert_first_cum = 0, cert_first_t = 0;               // [1] ns from first sight to verified, [2] verify retries
 
     for (;;) {
         if (tid < 32) {
@@ -1496,6 +1553,7 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
                 is_cert = (e & APUS_PUB_CERT) ? 1u : 0u;
                 e &= ~APUS_PUB_CERT;
                 bool new_entries = cum > acked;
+                if (new_entries && is_cert && fstat && cum != cert_first_cum) { cert_first_cum = cum; cert_first_t = globaltimer_ns(); }
                 if (new_entries && is_cert) {
                     // self-certifying publish of ONE entry at cert_start: the bytes may still be in flight -- read them back
                     // from my own HBM until they add up to the certificate
@@ -1510,7 +1568,9 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
                         for (int sft = 16; sft > 0; sft >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, sft);
                         ok = (cs + cs_key(cumt)) == csum;
                     }
-                    if (!ok) new_entries = false;          // not there yet (or not verifiable: a fenced publish will follow)
+                    if (fstat && lane == 0) { if (ok) { ctrl->phase_ns[0]++; ctrl->phase_ns[1] += globaltimer_ns() - cert_first_t; } else ctrl->phase_ns[2]++; }
+                    if (!ok) { new_entries = false; cum = acked; }   // not there yet (or not verifiable: a fenced publish will follow);
+                                                                     // nothing of it may be acked or walked
                 }
                 // commit moved, and I hold entries beyond what I applied
                 const bool new_commit = (c != applied) && (old_end != L) && (applied != old_end);

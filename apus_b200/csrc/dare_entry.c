@@ -33,10 +33,29 @@ static FILE *g_log;
 static apus_replica_t *g_rep;
 static volatile int g_leader, g_started, g_terminate;
 static uint8_t g_idx, g_n, g_leader_idx;
+static uint64_t g_term = 1;                 /* term of a clean first election */
+static uint32_t g_live_mask;                /* servers of the configuration (dare_cid_t.bitmask) */
+static uint32_t g_removed_mask;             /* servers a new leader found dead: removed with a CONFIG entry */
+static uint64_t g_log_len = APUS_LOG_SIZE;
+static uint64_t g_apply, g_apply_next_idx;  /* follower apply walk: survives a change of leader */
 static dare_server_input_t g_in;
+
+/* dare_global_config of the libconfig file (config-dare.c:12-52; target/nodes.local.cfg) */
+static double   cfg_hb_period = 0.01;             /* seconds */
+static uint64_t cfg_elec_low = 100000, cfg_elec_high = 300000;   /* microseconds */
+
+/* SID = [TERM|L|IDX] (dare_server.h:46-61) */
+#define SID_IDX(s)   ((uint8_t)((s) & 0xFF))
+#define SID_L(s)     (((s) >> 8) & 1)
+#define SID_TERM(s)  ((s) >> 9)
+#define SID_MAKE(term, l, idx) ((((uint64_t)(term)) << 9) | ((uint64_t)((l) ? 1 : 0) << 8) | (uint64_t)(idx))
 
 #define LOGT(fmt, ...) do { struct timeval _tv; gettimeofday(&_tv, NULL); \
     fprintf(g_log, "[%lu:%06lu] " fmt, (unsigned long)_tv.tv_sec, (unsigned long)_tv.tv_usec, ##__VA_ARGS__); fflush(g_log); } while (0)
+
+/* test / tooling hook: the replica behind this process (inspect it through include/apus_gpu.h) */
+void *apus_dare_replica(void) { return g_rep; }
+uint64_t apus_dare_term(void) { return g_term; }
 
 int is_leader(void) { return g_started && g_leader; }          /* dare_server.c:2299-2302 */
 uint8_t get_node_id(void) { return g_idx; }                    /* dare_server.c:2304-2307 */
@@ -103,6 +122,8 @@ static void segv_trace(int sig)
  * (redis-server's setproctitle does: clearenv + setenv at the top of main), and getenv() racing with that
  * crashes.  The reference reads its variables in proxy.c:33-58 on the main thread for the same reason. */
 static int g_env_gpu = -1, g_env_leader = 0;
+static int g_env_colocate;                 /* 1: this (leader) process also hosts the followers' replicas: kernels only */
+static long g_env_hb_us = -1, g_env_hbto_us = -1, g_env_elec_lo = -1, g_env_elec_hi = -1;
 static unsigned long long g_env_log_size;
 static char g_env_rdv[256];
 __attribute__((constructor)) static void engine_env_init(void)
@@ -111,36 +132,48 @@ __attribute__((constructor)) static void engine_env_init(void)
     if ((s = getenv("apus_gpu"))) g_env_gpu = atoi(s);
     if ((s = getenv("apus_leader"))) g_env_leader = atoi(s);
     if ((s = getenv("apus_log_size"))) g_env_log_size = strtoull(s, NULL, 0);
+    if ((s = getenv("apus_colocate_followers"))) g_env_colocate = atoi(s);
+    if ((s = getenv("apus_hb_period_us"))) g_env_hb_us = atol(s);
+    if ((s = getenv("apus_hb_timeout_us"))) g_env_hbto_us = atol(s);
+    if ((s = getenv("apus_elec_timeout_us"))) { g_env_elec_lo = atol(s); const char *c = strchr(s, ','); g_env_elec_hi = c ? atol(c + 1) : 2 * g_env_elec_lo; }
     if ((s = getenv("apus_rendezvous"))) snprintf(g_env_rdv, sizeof g_env_rdv, "%s", s);
     else snprintf(g_env_rdv, sizeof g_env_rdv, "/tmp/apus-rdv-%u", (unsigned)getuid());
     if (getenv("apus_segv_trace")) { signal(SIGSEGV, segv_trace); signal(SIGBUS, segv_trace); signal(SIGABRT, segv_trace); }
 }
 
+static void cid_image(uint8_t out[16], uint32_t bitmask);
 static int csm_like(uint8_t type) { return !(type == APUS_NOOP || type == APUS_CONFIG || type == APUS_HEAD); }
 
 /* ---- leader pump ---------------------------------------------------------------------------- */
 #define TK_RING (1u << 20)
 static uint8_t *g_tk_type;        /* type of every ticket in flight, indexed by ticket & (TK_RING-1) */
 
-static void leader_pump(void)
+static void leader_pump(int elected)
 {
     uint64_t submitted = 0, applied = 0;
     uint8_t image[64];
     struct apus_tailhead_t pending;                 /* popped from the shared queue, not yet in the engine */
     TAILQ_INIT(&pending);
     if (g_n > 1) {
-        /* the election winner's blank CONFIG entry (dare_server.c:1412-1421) */
+        /* the election winner's blank CONFIG entry (dare_server.c:1412-1421): it is what lets entries of earlier
+         * terms commit, as a prefix of an entry of this term */
         uint8_t cid[16];
-        memset(cid, 0, sizeof cid);
-        cid[8] = g_n;
-        uint32_t bm = (1u << g_n) - 1u;
-        memcpy(cid + 12, &bm, 4);
+        cid_image(cid, g_live_mask);
         uint64_t t = 0;
         if (apus_submit(g_rep, APUS_CONFIG, 0, 0, cid, 0, &t) != APUS_OK) { LOGT("cannot append CONFIG: %s\n", apus_last_error()); return; }
         g_tk_type[t & (TK_RING - 1)] = APUS_CONFIG;
         submitted = t;
+        if (g_removed_mask & g_live_mask) {
+            /* servers that did not take part in the election are removed from the configuration
+             * (check_failure_count, dare_server.c:1189-1228: CID_SERVER_RM + a CONFIG entry) */
+            g_live_mask &= ~g_removed_mask;
+            cid_image(cid, g_live_mask);
+            if (apus_submit(g_rep, APUS_CONFIG, 0, 0, cid, 0, &t) != APUS_OK) { LOGT("cannot append CONFIG: %s\n", apus_last_error()); return; }
+            g_tk_type[t & (TK_RING - 1)] = APUS_CONFIG;
+            submitted = t;
+        }
     }
-    LOGT("[T%llu] LEADER\n", 1ull);              /* benchmarks/run.sh:52 greps for "] LEADER" */
+    if (!elected) LOGT("[T%llu] LEADER\n", (unsigned long long)g_term);   /* benchmarks/run.sh:52 greps for "] LEADER" */
     g_leader = 1;
     apus_submit_defer(g_rep, 1);
     while (!g_terminate) {
@@ -188,9 +221,9 @@ static void leader_pump(void)
 }
 
 /* ---- follower pump: apply_committed_entries, follower branch (dare_server.c:1815-1967) -------- */
-static void follower_pump(uint64_t L)
+static int follower_pump(uint64_t L)
 {
-    uint64_t apply = 0, next_idx = 0;
+    uint64_t apply = g_apply, next_idx = g_apply_next_idx;
     const size_t cap = 1u << 20;
     uint8_t *buf = (uint8_t *)malloc(cap + 65536 + 64);
     uint32_t idle = 0;
@@ -198,6 +231,7 @@ static void follower_pump(uint64_t L)
         uint64_t off = 0, cnt = 0;
         if (apus_progress(g_rep, &off, &cnt) != APUS_OK) { LOGT("%s\n", apus_last_error()); break; }
         if (off == apply) {
+            if (apus_leader_suspect(g_rep)) { g_apply = apply; g_apply_next_idx = next_idx; free(buf); return 1; }
             if (++idle > 2000) usleep(20);       /* spin first: the commit word is plain host memory */
             continue;
         }
@@ -241,7 +275,180 @@ static void follower_pump(uint64_t L)
             apus_set_applied(g_rep, apply);      /* log->apply moves only after do_action (dare_server.c:1939-1962) */
         }
     }
+    g_apply = apply; g_apply_next_idx = next_idx;
     free(buf);
+    return 0;
+}
+
+/* ---- dare_global_config: the three values of the config file this engine uses (config-dare.c:12-52).  The
+ *      interposer links libconfig for proxy.c; the engine only needs `key = number;` inside that one group ---- */
+static void read_dare_config(const char *path)
+{
+    FILE *f = path && path[0] ? fopen(path, "r") : NULL;
+    if (!f) return;
+    char line[512];
+    while (fgets(line, sizeof line, f)) {
+        char *hash = strchr(line, '#');
+        if (hash) *hash = 0;
+        char key[64]; double v;
+        if (sscanf(line, " %63[a-z_] = %lf", key, &v) != 2) continue;
+        if (!strcmp(key, "hb_period")) cfg_hb_period = v;
+        else if (!strcmp(key, "elec_timeout_low")) cfg_elec_low = (uint64_t)v;
+        else if (!strcmp(key, "elec_timeout_high")) cfg_elec_high = (uint64_t)v;
+    }
+    fclose(f);
+}
+
+static uint64_t now_us(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (uint64_t)ts.tv_sec * 1000000ull + (uint64_t)ts.tv_nsec / 1000ull;
+}
+
+/* random_election_timeout (dare_server.c:1237-1250) */
+static uint64_t random_election_timeout_us(void)
+{
+    struct timeval tv;
+    gettimeofday(&tv, NULL);
+    srand48((long)(g_idx + 1) * (long)((tv.tv_sec % 100) * 1000000 + tv.tv_usec));
+    const uint64_t span = cfg_elec_high > cfg_elec_low ? cfg_elec_high - cfg_elec_low : 1;
+    return (uint64_t)(lrand48() % span) + cfg_elec_low;
+}
+
+static void cid_image(uint8_t out[16], uint32_t bitmask)
+{
+    memset(out, 0, 16);
+    out[8] = g_n;                                 /* dare_cid_t {epoch, size[2], state, bitmask}, dare_config.h */
+    memcpy(out + 12, &bitmask, 4);
+}
+
+static int launch_self(void)
+{
+    apus_replica_t *rs[1] = { g_rep };
+    return apus_replicas_launch(rs, 1, UINT64_MAX);
+}
+
+/* ---- leader failure: election, log adjustment, change of role ---------------------------------------
+ * Restates, on the control words of include/apus_gpu.h, the reference's
+ *   start_election      dare_server.c:1264-1320   term+1, SID [t|0|me], votes cleared, vote request (sid, last idx, last term)
+ *   poll_vote_requests  dare_server.c:1524-1743   best SID wins, up-to-date test on (term, idx), one vote per term, vote ack = my commit
+ *   poll_vote_count     dare_server.c:1322-1400   size/2+1 votes incl. my own -> [t|1|me], "[T<t>] LEADER"
+ *   log_adjustment      dare_ibv_rc.c:1292-1451   (apus_ctl_adjust_follower) and the follower's side of it.
+ * Returns 0 when this replica runs again in its new role (g_leader_idx / g_term updated), 1 to give up. */
+static int elect(void)
+{
+    apus_replica_t *rs[1] = { g_rep };
+    apus_replicas_stop(rs, 1);                              /* exclusive access to my log (dare_ib_revoke_log_access) */
+    const uint8_t dead = g_leader_idx;
+    LOGT("[T%llu] leader p%u fell silent: failure detector fired\n", (unsigned long long)g_term, (unsigned)dead);
+    apus_ctl_view_t v;
+    if (apus_ctl_read(g_rep, &v) != APUS_OK) { LOGT("%s\n", apus_last_error()); return 1; }
+    uint64_t sid = v.sid;
+    sid &= ~(1ull << 8);                                    /* no leader known any more */
+    uint64_t last_idx = 0, last_term = 0, commit = 0, end = 0;
+    if (apus_ctl_last_entry(g_rep, &last_idx, &last_term, &commit, &end) != APUS_OK) { LOGT("%s\n", apus_last_error()); return 1; }
+    uint8_t cid[16];
+    cid_image(cid, g_live_mask);
+    int candidate = 0;
+    /* the first round starts at once (hb_receive_cb -> start_election); a split vote is retried after a random timeout */
+    uint64_t deadline = now_us();
+    uint64_t voted_deadline = 0;
+    const uint64_t t_start = now_us();
+    while (!g_terminate) {
+        if (apus_ctl_read(g_rep, &v) != APUS_OK) { LOGT("%s\n", apus_last_error()); return 1; }
+        /* (a) somebody won and has adjusted my log: follow */
+        if (SID_L(v.leader_sid) && SID_TERM(v.leader_sid) >= SID_TERM(sid) && SID_IDX(v.leader_sid) != g_idx &&
+            SID_TERM(v.leader_sid) > g_term) {
+            g_term = SID_TERM(v.leader_sid); g_leader_idx = SID_IDX(v.leader_sid);
+            apus_ctl_set_sid(g_rep, v.leader_sid);
+            if (apus_replica_set_role(g_rep, g_leader_idx, g_term) != APUS_OK || launch_self() != APUS_OK) {
+                LOGT("cannot follow p%u: %s\n", (unsigned)g_leader_idx, apus_last_error()); return 1;
+            }
+            g_removed_mask |= 1u << dead;
+            LOGT("[T%llu] follow p%u (log adjusted to end %llu, %llu entries) after %.1f ms\n", (unsigned long long)g_term,
+                 (unsigned)g_leader_idx, (unsigned long long)v.adj_end, (unsigned long long)v.adj_count, (now_us() - t_start) / 1e3);
+            return 0;
+        }
+        /* (b) candidate: count the votes (poll_vote_count) */
+        if (candidate) {
+            unsigned votes = 1;
+            uint32_t voters = 0;
+            for (unsigned i = 0; i < g_n; i++)
+                if (i != g_idx && v.vote_ack[i] != g_log_len) { votes++; voters |= 1u << i; }
+            if (votes >= (unsigned)g_n / 2 + 1) {
+                /* won.  Give the remaining live servers a moment to answer as well: whoever has not voted by then is
+                 * treated as failed (check_failure_count, dare_server.c:1189-1228) */
+                const uint64_t grace = now_us() + 5000;
+                while (now_us() < grace && votes < g_n - 1u) {
+                    if (apus_ctl_read(g_rep, &v) != APUS_OK) break;
+                    votes = 1; voters = 0;
+                    for (unsigned i = 0; i < g_n; i++)
+                        if (i != g_idx && v.vote_ack[i] != g_log_len) { votes++; voters |= 1u << i; }
+                    usleep(100);
+                }
+                g_term = SID_TERM(sid); g_leader_idx = g_idx;
+                const uint64_t lsid = SID_MAKE(g_term, 1, g_idx);
+                apus_ctl_set_sid(g_rep, lsid);
+                LOGT("[T%llu] LEADER\n", (unsigned long long)g_term);      /* benchmarks/run.sh:52, reconf_bench.sh grep this */
+                if (apus_replica_set_role(g_rep, g_idx, g_term) != APUS_OK) { LOGT("take-over failed: %s\n", apus_last_error()); return 1; }
+                for (unsigned i = 0; i < g_n; i++) {
+                    if (i == g_idx) continue;
+                    if (!(voters & (1u << i))) {
+                        apus_replica_disconnect(g_rep, (uint8_t)i);
+                        if (g_live_mask & (1u << i)) { g_removed_mask |= 1u << i; LOGT("REMOVE SERVER p%u\n", i); }
+                        continue;
+                    }
+                    uint64_t resent = 0;
+                    if (apus_ctl_adjust_follower(g_rep, (uint8_t)i, lsid, &resent) != APUS_OK) {
+                        LOGT("log adjustment of p%u failed: %s\n", i, apus_last_error());
+                        apus_replica_disconnect(g_rep, (uint8_t)i); g_removed_mask |= 1u << i;
+                    } else LOGT("   (p%u: log adjusted, %llu bytes resent)\n", i, (unsigned long long)resent);
+                }
+                if (launch_self() != APUS_OK) { LOGT("launch: %s\n", apus_last_error()); return 1; }
+                LOGT("[T%llu] leading after %.1f ms\n", (unsigned long long)g_term, (now_us() - t_start) / 1e3);
+                return 0;
+            }
+        }
+        /* (c) vote requests (poll_vote_requests): the best SID above mine -- with my L flag set, so that I vote once per term */
+        uint64_t old_sid = sid | (1ull << 8), best = old_sid;
+        int best_i = -1;
+        for (unsigned i = 0; i < g_n; i++) {
+            if (i == g_idx || v.vote_req[i].sid == 0) continue;
+            if (v.vote_req[i].sid <= best) { apus_ctl_clear_vote_request(g_rep, (uint8_t)i); continue; }
+            /* up-to-date test: my log must not be ahead of the candidate's (dare_server.c:1640-1652) */
+            if (last_term > v.vote_req[i].term || (last_term == v.vote_req[i].term && last_idx > v.vote_req[i].index)) {
+                /* my log is better but my term is too low: raise it to improve my own chances (:1663-1676) */
+                if (SID_TERM(v.vote_req[i].sid) > SID_TERM(sid)) { sid = SID_MAKE(SID_TERM(v.vote_req[i].sid), 0, g_idx); apus_ctl_set_sid(g_rep, sid); candidate = 0; }
+                apus_ctl_clear_vote_request(g_rep, (uint8_t)i);
+                continue;
+            }
+            best = v.vote_req[i].sid; best_i = (int)i;
+        }
+        if (best_i >= 0) {
+            sid = best;                                           /* my vote: SID of the candidate (replicated = written to my words) */
+            apus_ctl_set_sid(g_rep, sid);
+            candidate = 0;
+            LOGT("[T%llu] Vote for p%u\n", (unsigned long long)SID_TERM(sid), (unsigned)SID_IDX(sid));
+            apus_ctl_send_vote_ack(g_rep, SID_IDX(sid), commit);
+            apus_ctl_clear_vote_request(g_rep, (uint8_t)best_i);
+            voted_deadline = now_us() + (uint64_t)(10.0 * cfg_hb_period * 1e6);   /* hb_timeout() */
+            deadline = voted_deadline + random_election_timeout_us();
+        }
+        /* (d) nobody leads, nobody I voted for made it: stand myself (start_election) */
+        if (now_us() >= deadline) {
+            sid = SID_MAKE(SID_TERM(sid) + 1, 0, g_idx);
+            apus_ctl_set_sid(g_rep, sid);
+            apus_ctl_reset_votes(g_rep);
+            candidate = 1;
+            LOGT("[T%llu] Start election\n", (unsigned long long)SID_TERM(sid));
+            for (unsigned i = 0; i < g_n; i++)
+                if (i != g_idx && i != dead) apus_ctl_send_vote_request(g_rep, (uint8_t)i, sid, last_idx, last_term, cid);
+            deadline = now_us() + random_election_timeout_us();
+        }
+        usleep(50);
+    }
+    return 1;
 }
 
 void *dare_server_init(void *arg)
@@ -258,6 +465,9 @@ void *dare_server_init(void *arg)
      * starts reading the environment on this thread */
     usleep(10000);
     g_leader_idx = (uint8_t)g_env_leader;
+    read_dare_config(g_in.config_path);
+    if (g_env_elec_lo > 0) { cfg_elec_low = (uint64_t)g_env_elec_lo; cfg_elec_high = (uint64_t)g_env_elec_hi; }
+    if (g_env_hb_us > 0) cfg_hb_period = g_env_hb_us * 1e-6;
     if (g_in.srv_type != SRV_TYPE_START) { LOGT("server_type=join is not supported by the GPU engine yet\n"); return NULL; }
     if (g_n < 1 || g_n > APUS_MAX_SERVER_COUNT || g_idx >= g_n) { LOGT("bad group_size/server_idx\n"); return NULL; }
 
@@ -270,11 +480,44 @@ void *dare_server_init(void *arg)
     cfg.server_idx = g_idx; cfg.group_size = g_n; cfg.leader_idx = g_leader_idx;
     cfg.ring_mode = APUS_RING_HOST_MAPPED;
     cfg.flags = APUS_F_EXPLICIT | APUS_F_DEVICE_STATS | APUS_F_AUTOPRUNE | APUS_F_HOST_APPLY;
-    cfg.term = 1;                                      /* term of a clean first election */
+    cfg.term = g_term;
+    g_live_mask = (1u << g_n) - 1u;
+    /* heartbeats: the leader kernel beats every hb_period, a follower suspects it after hb_timeout() = 10 periods
+     * (dare_server.c:1252-1259) unless the environment says otherwise */
+    cfg.hb_period_us = (uint32_t)(cfg_hb_period * 1e6);
+    cfg.hb_timeout_us = g_env_hbto_us > 0 ? (uint32_t)g_env_hbto_us : (uint32_t)(10.0 * cfg_hb_period * 1e6);
+    if (g_n == 1) { cfg.hb_period_us = 0; cfg.hb_timeout_us = 0; }
     cfg.log_size = g_env_log_size;
     cfg.leader_ctas = 2;
     if (apus_replica_create(&cfg, &g_rep) != APUS_OK) { LOGT("apus_replica_create: %s\n", apus_last_error()); return NULL; }
 
+    if (g_env_colocate && g_idx == g_leader_idx && g_n > 1) {
+        /* One GPU cannot run the persistent kernels of several PROCESSES at once (contexts are time-sliced), so a
+         * single-GPU box can host the followers' replicas inside the leader's process: their kernels ack and follow the
+         * commit exactly as anywhere else, only their host side (do_action replay) does not exist.  Measurement aid for
+         * the leader-side path through proxy.c; real deployments run one process and one GPU per replica. */
+        apus_replica_t *all_r[APUS_MAX_SERVER_COUNT];
+        apus_peer_handle_t hs[APUS_MAX_SERVER_COUNT];
+        for (unsigned i = 0; i < g_n; i++) {
+            if (i == g_idx) { all_r[i] = g_rep; continue; }
+            apus_config_t fc = cfg;
+            fc.server_idx = (uint8_t)i;
+            fc.flags &= ~APUS_F_HOST_APPLY;
+            fc.hb_timeout_us = 0;
+            if (apus_replica_create(&fc, &all_r[i]) != APUS_OK) { LOGT("colocated follower %u: %s\n", i, apus_last_error()); dare_server_shutdown(); }
+        }
+        for (unsigned i = 0; i < g_n; i++) apus_replica_export(all_r[i], &hs[i]);
+        for (unsigned i = 0; i < g_n; i++)
+            for (unsigned j = 0; j < g_n; j++)
+                if (i != j && apus_replica_connect(all_r[i], (uint8_t)j, &hs[j]) != APUS_OK) { LOGT("connect: %s\n", apus_last_error()); dare_server_shutdown(); }
+        /* followers first in the table: one fused launch */
+        apus_replica_t *order[APUS_MAX_SERVER_COUNT];
+        unsigned k = 0;
+        for (unsigned i = 0; i < g_n; i++) if (i != g_idx) order[k++] = all_r[i];
+        order[k++] = g_rep;
+        if (apus_replicas_launch(order, (int)k, UINT64_MAX) != APUS_OK) { LOGT("launch: %s\n", apus_last_error()); dare_server_shutdown(); }
+        LOGT("followers colocated in the leader's process (single-GPU measurement mode)\n");
+    } else {
     apus_peer_handle_t mine, all[APUS_MAX_SERVER_COUNT];
     const char *dir = g_env_rdv;
     if (apus_replica_export(g_rep, &mine) != APUS_OK || rendezvous(dir, &mine, all)) {
@@ -286,12 +529,19 @@ void *dare_server_init(void *arg)
         }
     apus_replica_t *rs[1] = { g_rep };
     if (apus_replicas_launch(rs, 1, UINT64_MAX) != APUS_OK) { LOGT("launch: %s\n", apus_last_error()); dare_server_shutdown(); }
+    }
     g_tk_type = (uint8_t *)calloc(TK_RING, 1);
     g_started = 1;
     LOGT("replica %u/%u up on GPU %d (leader %u)\n", (unsigned)g_idx, (unsigned)g_n, cfg.device, (unsigned)g_leader_idx);
 
-    if (g_idx == g_leader_idx) leader_pump();
-    else follower_pump(cfg.log_size ? cfg.log_size : APUS_LOG_SIZE);
+    g_log_len = cfg.log_size ? cfg.log_size : APUS_LOG_SIZE;
+    int elected = 0;
+    for (;;) {
+        if (g_idx == g_leader_idx) { leader_pump(elected); break; }
+        if (!follower_pump(g_log_len)) break;              /* terminated */
+        if (elect() != 0) break;                           /* new role, kernel running again */
+        elected = 1;
+    }
     LOGT("SIGINT detected; shutdown\n");
     dare_server_shutdown();
     return NULL;

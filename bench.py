@@ -65,6 +65,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="requests per step (0 = 2^20 for <= 256 B requests, else 16 MiB worth)")
     ap.add_argument("--log-size", type=int, default=0, help="bytes of entries[]; 0 = reference LOG_SIZE (64 MiB)")
     ap.add_argument("--lat-requests", type=int, default=20000, help="closed-loop requests for p50/p99")
+    ap.add_argument("--failover", action="store_true",
+                    help="BASELINE config 5: kill the leader process under load, report the recovery latency (reconf_bench.sh analogue)")
+    ap.add_argument("--failover-trials", type=int, default=3)
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-proxy-leg", action="store_true", help="skip the 16-connection closed-loop leg through the reference's proxy.c")
     ap.add_argument("--no-express", action="store_true", help="A/B: every publish fenced, no single-warp express path")
@@ -762,14 +765,19 @@ def proxy_closed_loop_leg(args, n, payload, log, conns=16, nreq=20000, steps=3):
     nd = max(1, A.lib().apus_device_count())
     cores = host_cores()
     threads = max(1, min(conns, cores - n))
+    # one GPU cannot run the persistent kernels of several processes at once (contexts are time-sliced): with fewer GPUs than
+    # replicas the followers' replicas live in the leader's process (kernels only, apus_colocate_followers)
+    colocate = nd < n or not args.spread
     with tempfile.TemporaryDirectory() as d:
         env = dict(os.environ, apus_rendezvous=os.path.join(d, "rdv"), PROXY_RUN_TIMEOUT="120", APUS_NO_BUILD="1")
         procs = []
-        for i in range(n):
-            e = dict(env, apus_gpu=str(i % nd) if args.spread else "0")
-            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "proxy_worker.py"), str(i), str(n), str(conns),
-                                           str(nreq), str(payload), d, str(threads), str(steps)], env=e,
-                                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+        for i in range(1 if colocate else n):
+            e = dict(env, apus_gpu=("0" if colocate else str(i % nd)))
+            if colocate:
+                e["apus_colocate_followers"] = "1"
+            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "proxy_worker.py"), str(i), str(1 if colocate else n),
+                                           str(conns), str(nreq), str(payload), d, str(threads), str(steps)] + ([str(n)] if colocate else []),
+                                          env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
         outs = []
         try:
             for p in procs:
@@ -783,7 +791,7 @@ def proxy_closed_loop_leg(args, n, payload, log, conns=16, nreq=20000, steps=3):
             return {"unavailable": "leader process produced no result: " + outs[0][-300:]}
         r0 = json.load(open(path))
         followers_ok = 0
-        for i in range(1, n):
+        for i in range(1, 1 if colocate else n):
             fp = os.path.join(d, f"result{i}.json")
             if os.path.exists(fp) and json.load(open(fp)).get("bytes") == nreq * payload * steps:
                 followers_ok += 1
@@ -791,16 +799,49 @@ def proxy_closed_loop_leg(args, n, payload, log, conns=16, nreq=20000, steps=3):
     ops = sum(s_["requests"] + 2 * conns for s_ in timed) / sum(s_["seconds"] for s_ in timed)
     res = {"value": round(ops, 1), "unit": "ops/s", "connections": conns, "app_threads": threads, "replica_processes": n,
            "p50_us": round(statistics.median(s_["p50_us"] for s_ in timed), 2), "p99_us": round(max(s_["p99_us"] for s_ in timed), 2),
-           "followers_replayed_everything": followers_ok == n - 1,
-           "what": f"unmodified src/proxy/proxy.c on the engine, {n} replica processes ({'one GPU each' if args.spread else 'all on GPU 0'}), "
+           "followers_replayed_everything": (None if colocate else followers_ok == n - 1),
+           "what": f"unmodified src/proxy/proxy.c on the engine, " + (f"{n} replicas on GPU 0, the followers' replicas hosted by the leader's process "
+                   f"(kernels only: one GPU cannot run kernels of several processes concurrently), " if colocate else f"{n} replica processes, one GPU each, ") +
                    f"{conns} connections closed loop on {threads} application threads, {len(timed)} x {nreq} requests of {payload} B "
                    f"after one warm-up session; latency = proxy_on_read call (returns at commit); same driver and shape as --impl reference"}
     log(f"proxy leg: {res}")
     return res
 
 
+def run_failover(args):
+    """Leader failover mid-run (BASELINE config 5): tools/failover_drill.py, twice -- with the timeouts the reference ships in
+    target/nodes.local.cfg (hb 10 ms, detection after 10 missed beats, election timeout 100-300 ms; its own stack needs
+    ~0.35 s with these, profiles/r1_refstack_failover_buildbox.txt) and with timeouts sized for heartbeats that are
+    written by a GPU kernel every 200 us."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import __graft_entry__ as ge
+    ge.build()
+    import apus_b200 as A
+    import failover_drill as FD
+    nd = max(1, A.lib().apus_device_count())
+    n = args.replicas
+    out = {"metric": "leader failover: kill -> new leader serving", "unit": "ms", "higher_is_better": False, "n_gpus": min(nd, n),
+           "data": "synthetic", "dtype": "u8", "config": {"workload": f"{n} replica processes (unmodified proxy.c on the engine), closed-loop "
+                                                                      f"{args.payload} B requests, leader killed with SIGKILL after 1 s",
+                                                          "replicas": n, "placement": "one GPU per replica" if nd >= n else f"{nd} GPU(s)"}}
+    for name, kw in (("gpu_native_timeouts", dict(hb_us=200, hb_timeout_us=4000, elec_us="2000,6000")),
+                     ("reference_timeouts", dict(hb_us=10000, hb_timeout_us=100000, elec_us="100000,300000"))):
+        trials = []
+        for _ in range(args.failover_trials):
+            r = FD.run(n=n, plen=args.payload, spread=nd > 1, ndev=nd, kill_after_s=1.0, **kw)
+            trials.append({"new_leader": r["new_leader"], "term": r["term"], "kill_to_leader_line_ms": r["recovery_ms_kill_to_leader_line"],
+                           "kill_to_first_commit_ms": r["recovery_ms_kill_to_first_commit"], "requests_before_kill": r["requests_before_kill"]})
+        out[name] = {"hb_period_us": kw["hb_us"], "hb_timeout_us": kw["hb_timeout_us"], "election_timeout_us": kw["elec_us"], "trials": trials,
+                     "median_kill_to_first_commit_ms": statistics.median(t["kill_to_first_commit_ms"] for t in trials)}
+    out["value"] = out["gpu_native_timeouts"]["median_kill_to_first_commit_ms"]
+    print(json.dumps(out), flush=True)
+
+
 def main():
     args = parse()
+    if args.failover:
+        run_failover(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

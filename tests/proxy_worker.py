@@ -22,6 +22,7 @@ def main():
                                           int(sys.argv[5]), sys.argv[6])
     nthreads = int(sys.argv[7]) if len(sys.argv) > 7 else 0      # > 0: the C driver of oracle/app_driver.inc (stub_drive)
     nsteps = int(sys.argv[8]) if len(sys.argv) > 8 else 1
+    group = int(sys.argv[9]) if len(sys.argv) > 9 else n        # apus_colocate_followers: one process, `group` replicas
     leader = idx == 0
     received = {}
     lock = threading.Lock()
@@ -58,7 +59,7 @@ def main():
         time.sleep(0.01)
     os.environ["stub_port"] = str(ph[0])
     os.environ["server_idx"] = str(idx)
-    os.environ["group_size"] = str(n)
+    os.environ["group_size"] = str(group)
     os.environ["server_type"] = "start"
     os.environ["dare_log_file"] = os.path.join(outdir, f"dare{idx}.log")
 
