@@ -46,6 +46,12 @@ static int fail(const char *fmt, ...)
             return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
+struct StageLock {
+    pthread_mutex_t *m;
+    explicit StageLock(pthread_mutex_t *mu) : m(mu) { pthread_mutex_lock(m); }
+    ~StageLock() { pthread_mutex_unlock(m); }
+};
+
 struct DeviceGuard {
     int prev;
     bool ok;
@@ -96,6 +102,7 @@ struct apus_replica {
     uint64_t submitted, flushed;  /* tickets handed out / tickets whose slots the device can read */
     uint64_t belled;              /* doorbell value the kernel has been given */
     uint8_t *stage;               /* pinned bounce buffer for log reads */
+    pthread_mutex_t stage_mu;     /* ... used by the consensus thread and by inspection calls from other threads */
     size_t   stage_bytes;
     uint64_t pay_head;            /* payload bytes handed out (monotone; position = % ring_bytes) */
     uint64_t pay_flushed;         /* payload bytes already made visible to the kernel */
@@ -179,6 +186,7 @@ static int replica_init(apus_replica *r, const apus_config_t *cfg, uint64_t log_
     CK(cudaHostAlloc(&r->hw, sizeof(apus_hostwords_t), cudaHostAllocMapped | cudaHostAllocPortable));
     memset((void *)r->hw, 0, sizeof(apus_hostwords_t));
     CK(cudaHostGetDevicePointer(&r->hw_dev, r->hw, 0));
+    pthread_mutex_init(&r->stage_mu, NULL);
     r->stage_bytes = 1u << 20;
     CK(cudaHostAlloc(&r->stage, r->stage_bytes, cudaHostAllocPortable));
     CK(cudaMalloc(&r->d_ctx, sizeof(apus_devctx_t)));
@@ -720,7 +728,7 @@ static void pool_run(const fill_job *j)
     pthread_mutex_lock(&g_pool_run);
     pthread_mutex_lock(&g_pool.mu);
     if (!g_pool.started) {
-        int want = 4;
+        int want = 8;
         const char *e = getenv("apus_submit_threads");
         if (e) want = atoi(e);
         long cores = sysconf(_SC_NPROCESSORS_ONLN);
@@ -965,6 +973,7 @@ extern "C" int apus_log_read(apus_replica_t *r, uint64_t off, uint64_t len, void
     if (!r || !dst) return fail("null argument");
     if (off + len > r->log_len) return fail("range beyond the log");
     DeviceGuard g(r->cfg.device);
+    StageLock sl(&r->stage_mu);
     /* through the pinned bounce buffer: a pageable destination would make every copy a synchronous staged one */
     uint8_t *out = (uint8_t *)dst;
     while (len) {
@@ -1054,6 +1063,7 @@ extern "C" int apus_latency_samples(apus_replica_t *r, uint32_t *dst, uint32_t m
 
 static int own_read(apus_replica *r, size_t off, void *dst, size_t len)
 {
+    StageLock sl(&r->stage_mu);
     CK(cudaMemcpyAsync(r->stage, r->region + off, len, cudaMemcpyDeviceToHost, r->copy_stream));
     CK(cudaStreamSynchronize(r->copy_stream));
     memcpy(dst, r->stage, len);
@@ -1061,6 +1071,7 @@ static int own_read(apus_replica *r, size_t off, void *dst, size_t len)
 }
 static int own_write(apus_replica *r, size_t off, const void *src, size_t len)
 {
+    StageLock sl(&r->stage_mu);
     memcpy(r->stage, src, len);
     CK(cudaMemcpyAsync(r->region + off, r->stage, len, cudaMemcpyHostToDevice, r->copy_stream));
     CK(cudaStreamSynchronize(r->copy_stream));
@@ -1069,6 +1080,7 @@ static int own_write(apus_replica *r, size_t off, const void *src, size_t len)
 /* a peer's region through the mapping the kernels store through (peer access or CUDA IPC): host-initiated copies */
 static int peer_read(apus_replica *r, uint8_t peer, size_t off, void *dst, size_t len)
 {
+    StageLock sl(&r->stage_mu);
     if (!r->peer_ptr[peer]) return fail("peer %u is not connected", (unsigned)peer);
     CK(cudaMemcpyAsync(r->stage, (uint8_t *)r->peer_ptr[peer] + off, len, cudaMemcpyDefault, r->copy_stream));
     CK(cudaStreamSynchronize(r->copy_stream));
@@ -1077,6 +1089,7 @@ static int peer_read(apus_replica *r, uint8_t peer, size_t off, void *dst, size_
 }
 static int peer_write(apus_replica *r, uint8_t peer, size_t off, const void *src, size_t len)
 {
+    StageLock sl(&r->stage_mu);
     if (!r->peer_ptr[peer]) return fail("peer %u is not connected", (unsigned)peer);
     memcpy(r->stage, src, len);
     CK(cudaMemcpyAsync((uint8_t *)r->peer_ptr[peer] + off, r->stage, len, cudaMemcpyDefault, r->copy_stream));
@@ -1222,7 +1235,7 @@ extern "C" int apus_ctl_adjust_follower(apus_replica_t *r, uint8_t peer, uint64_
     if (mine > j && mh.end != L) {
         /* everything behind the shared prefix: entry bytes [keep_end, my end) -- a wrapped range is two copies, a wrap
          * gap (ghost header) travels with it -- and the offset-index words of entries j+1 .. mine */
-        const uint64_t from = (j == 0) ? ((mh.head <= mh.end) ? mh.head : mh.head) : keep_end;
+        const uint64_t from = (j == 0) ? mh.head : keep_end;
         const uint64_t to = mh.end;
         if (to > from) { if (copy_to_peer(r, peer, r->entries_off + from, to - from) != APUS_OK) return APUS_ERROR; bytes += to - from; }
         else if (to < from || (to == from && mine > j)) {
@@ -1241,6 +1254,12 @@ extern "C" int apus_ctl_adjust_follower(apus_replica_t *r, uint8_t peer, uint64_
     }
     /* the follower now holds exactly my log: set its end (LR_SET_END, dare_ibv_rc.c:1396-1412) and its entry counter,
      * count it as holding everything I hold, then tell it whom to follow */
+    if (j == 0) {
+        /* a follower that shares nothing with me (a joiner, dare_ibv_rc.c:478-856 recover_log): it starts from my head,
+         * and knows my commit offset right away */
+        if (peer_write(r, peer, APUS_HDR_OFF + offsetof(apus_loghdr_t, head), &mh.head, 8) != APUS_OK) return APUS_ERROR;
+        if (peer_write(r, peer, APUS_HDR_OFF + offsetof(apus_loghdr_t, commit), &mh.commit, 8) != APUS_OK) return APUS_ERROR;
+    }
     const uint64_t endw[2] = { mh.end, mh.end };
     if (peer_write(r, peer, APUS_HDR_OFF + offsetof(apus_loghdr_t, end), &endw[0], 8) != APUS_OK) return APUS_ERROR;
     if (peer_write(r, peer, APUS_HDR_OFF + offsetof(apus_loghdr_t, old_end), &endw[1], 8) != APUS_OK) return APUS_ERROR;
@@ -1252,6 +1271,16 @@ extern "C" int apus_ctl_adjust_follower(apus_replica_t *r, uint8_t peer, uint64_
     if (peer_write(r, peer, APUS_CTL_OFF + offsetof(apus_ctlwords_t, adj_end), &adj[1], 16) != APUS_OK) return APUS_ERROR;
     if (peer_write(r, peer, APUS_CTL_OFF + offsetof(apus_ctlwords_t, leader_sid), &adj[0], 8) != APUS_OK) return APUS_ERROR;
     if (resent) *resent = bytes;
+    return APUS_OK;
+}
+
+extern "C" int apus_follower_beats(apus_replica_t *r, uint64_t out[APUS_MAX_SERVER_COUNT])
+{
+    if (!r || !out) return fail("null argument");
+    DeviceGuard g(r->cfg.device);
+    uint64_t b[16];
+    if (own_read(r, offsetof(apus_ctrl_t, fbeat), b, sizeof b) != APUS_OK) return APUS_ERROR;
+    for (int i = 0; i < APUS_MAX_SERVER_COUNT; i++) out[i] = b[i];
     return APUS_OK;
 }
 
@@ -1304,7 +1333,7 @@ extern "C" int apus_replica_set_role(apus_replica_t *r, uint8_t leader_idx, uint
     c.next_idx = last + 1; c.published = last; c.committed = last - unc;
     c.consumed = 0; c.committed_tickets = 0;
     c.hwm = L;                       /* treat every range as written before: prefill reads the log (zeros where it was never written) */
-    for (int i = 0; i < 16; i++) { c.ack[i] = 0; c.apply_off[i] = h.head; }        /* dare_server.c:1507-1510 */
+    for (int i = 0; i < 16; i++) { c.ack[i] = 0; c.apply_off[i] = h.head; c.fbeat[i] = 0; }   /* dare_server.c:1507-1510 */
     h.tail = tail; h.old_end = h.end;
     if (own_write(r, 0, &c, offsetof(apus_ctrl_t, fin_entries)) != APUS_OK) return APUS_ERROR;
     if (own_write(r, APUS_HDR_OFF, &h, sizeof h) != APUS_OK) return APUS_ERROR;

@@ -172,7 +172,7 @@ struct LeaderShared {
     uint8_t  ty[MAXB];
     uint8_t  flg[MAXB];        // bit0 EXT, bit1 WRAP
     // claim
-    uint32_t n_fetch, finish, abort, pad_a;
+    uint32_t n_fetch, finish, abort, was_blocked;
     uint32_t avg_es, avg_xb;   // log / staged bytes per entry seen in this worker's last claim (sizes the next one)
     uint64_t slot0, my_seq, t_dequeue, st_head, t_place_acq, pub_h, pub_tail_seen;
     // placement state while this CTA holds the place turn (mirrors apus_seq_t.p_*)
@@ -613,7 +613,10 @@ __device__ __noinline__ void leader_place(const apus_devctx_t *__restrict__ cx, 
     //      head := the smallest apply offset in the group, published through a HEAD entry
     uint32_t autoh = 0;
     uint64_t new_head = 0;
-    if (autoprune && end != L && used >= (L >> 2) && !S->st_prev_head && L - pos0 >= APUS_HDR_BYTES) {
+    // "never two HEAD entries in a row" (prev_log_entry_head, dare_server.c:2042) keeps an idle log from filling with HEAD
+    // entries; a placement that is BLOCKED on space right behind a HEAD entry must still be able to prune again once the
+    // followers' applications have caught up -- else a slow follower host deadlocks the leader (back-pressure, rule E2)
+    if (autoprune && end != L && used >= (L >> 2) && (!S->st_prev_head || S->was_blocked) && L - pos0 >= APUS_HDR_BYTES) {
         uint64_t d = 0;                                   // distance apply -> end, per replica
         if (lane < N) {
             d = ring_dist(S->ap[lane], end, L);
@@ -684,7 +687,9 @@ __device__ __noinline__ void leader_place(const apus_devctx_t *__restrict__ cx, 
         S->auto_head = autoh; S->auto_head_val = new_head;
         S->idx0 = S->st_next_idx;
         S->fresh = (a >= S->st_hwm) ? 1u : 0u;
+        if (S->blocked) S->was_blocked = 1;
         if (!S->blocked) {
+            S->was_blocked = 0;
             // commit the placement to the state this CTA carries
             if (autoh) st_relaxed_sys(&hdr->head, new_head);
             if (autoh) S->st_head = new_head;
@@ -979,7 +984,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
         } else {
             while (ld_acquire_gpu(&seq->ready_epoch) != cx->epoch) { }
         }
-        S->finish = 0; S->abort = 0; S->avg_es = 128; S->avg_xb = 0; S->pub_tail_seen = 0; S->ap_valid = 0;
+        S->finish = 0; S->abort = 0; S->was_blocked = 0; S->avg_es = 128; S->avg_xb = 0; S->pub_tail_seen = 0; S->ap_valid = 0;
         S->idx_base = ctrl->next_idx - 1 - ctrl->published;
         for (int i = 0; i < APUS_MAX_SERVERS; i++) {
             S->peer_entries[i] = (i < N && i != me && cx->peer[i]) ? cx->peer[i] + cx->entries_off : nullptr;
@@ -1527,7 +1532,7 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
     uint64_t last_hb = ld_relaxed_sys(&ctrl->hb), last_hb_t = globaltimer_ns();
     bool suspected = false;
     const bool fstat = (cx->flags & APUS_FLAG_STATS) != 0;       // follower profiling: phase_ns[0] certificates verified,
-    uint64_t cert_first_cum = 0, cert_first_t = 0;               // [1] ns from first sight to verified, [2] verify retries
+    uint64_t cert_first_cum = 0, cert_first_t = 0, fbeat = globaltimer_ns() >> 8;               // [1] ns from first sight to verified, [2] verify retries
 
     for (;;) {
         if (tid < 32) {
@@ -1601,6 +1606,7 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
                         if (host_apply) ha = ld_relaxed_sys(&hw->host_apply);
                     }
                     if (cx->hb_timeout_ns && globaltimer_ns() - last_hb_t > cx->hb_timeout_ns) suspected = true;
+                    if (lane == 0) st_relaxed_sys(&lctrl->fbeat[me], ++fbeat);          // I am alive (leader's failure detector)
                     stopf = __shfl_sync(0xffffffffu, stopf, 0);
                     ha = __shfl_sync(0xffffffffu, ha, 0);
                     if (host_apply && ha != host_applied) {

@@ -78,6 +78,8 @@ typedef struct apus_ctrl {
     /* --- written by remote followers into the LEADER's region --- */
     uint64_t ack[16];            /* [i] = entries follower i has acked (monotone count) */
     uint64_t apply_off[16];      /* [i] = follower i's apply offset */
+    uint64_t fbeat[16];          /* [i] = follower i's liveness counter (its kernel bumps it while it polls): what the
+                                    leader's failure detector watches (the HB replies of dare_ibv_rc.c:912-958) */
     /* --- kernel-owned state that survives between launches --- */
     uint64_t next_idx;           /* leader: idx of the next entry (last.idx + 1) */
     uint64_t consumed;           /* leader: tickets taken from the submission ring */

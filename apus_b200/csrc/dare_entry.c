@@ -9,6 +9,7 @@
  * engine and the only one that invokes proxy callbacks, as in the reference.
  */
 #define _GNU_SOURCE
+#include <dirent.h>
 #include <errno.h>
 #include <execinfo.h>
 #include <signal.h>
@@ -142,11 +143,165 @@ __attribute__((constructor)) static void engine_env_init(void)
 }
 
 static void cid_image(uint8_t out[16], uint32_t bitmask);
+static uint64_t now_us(void);
+static int launch_self(void);
 static int csm_like(uint8_t type) { return !(type == APUS_NOOP || type == APUS_CONFIG || type == APUS_HEAD); }
 
-/* ---- leader pump ---------------------------------------------------------------------------- */
 #define TK_RING (1u << 20)
 static uint8_t *g_tk_type;        /* type of every ticket in flight, indexed by ticket & (TK_RING-1) */
+static uint64_t g_join_ticket;    /* ticket of a CONFIG entry appended by leader_serve_join (the pump counts it as submitted) */
+
+/* ---- join: a replaced server comes back into an EMPTY SLOT of the configuration ----------------
+ * The reference's joiner multicasts a JOIN request, the leader adds it with a CONFIG entry, the joiner fetches a snapshot
+ * of the state machine from a server (recover_sm: proxy get_db_size / create_db_snapshot there, apply_db_snapshot here,
+ * dare_server.c:598-721) and then the log (recover_log), dare_ibv_ud.c:952-1087, dare_server.c:1883-1937.  On one box the
+ * request / reply messages are files next to the peer handles (the rendezvous directory already stands in for the UD
+ * bootstrap); the snapshot is the proxy's own (its stored records, replayed into the joining application), the log
+ * comes over NVLink with the same peer-to-peer copy the log adjustment uses.  Growing the group (CID_EXTENDED ->
+ * TRANSIT -> STABLE, size[1]) is not built: a join is accepted for a slot that a CONFIG entry has emptied. */
+static int read_handle(unsigned i, apus_peer_handle_t *h)
+{
+    char path[512];
+    snprintf(path, sizeof path, "%s/r%u.handle", g_env_rdv, i);
+    FILE *f = fopen(path, "rb");
+    if (!f) return 1;
+    size_t got = fread(h, sizeof *h, 1, f);
+    fclose(f);
+    return got == 1 ? 0 : 1;
+}
+
+static uint64_t g_last_join_scan;
+/* leader: serve one pending join request, if any.  Called between batches with nothing in flight. */
+static void leader_serve_join(uint64_t submitted, uint64_t applied)
+{
+    const uint64_t now = now_us();
+    if (now - g_last_join_scan < 20000) return;
+    g_last_join_scan = now;
+    for (unsigned i = 0; i < g_n; i++) {
+        if (i == g_idx || (g_live_mask & (1u << i))) continue;
+        char req[512], ack[560], snap[512];
+        snprintf(req, sizeof req, "%s/join%u.req", g_env_rdv, i);
+        if (access(req, F_OK)) continue;
+        if (submitted != applied) return;                     /* quiesce first: everything appended is committed and applied */
+        LOGT("JOIN request from p%u\n", i);
+        /* the state machine snapshot (poll_sm_requests, dare_server.c:598-652) */
+        uint32_t len = g_in.get_db_size ? g_in.get_db_size(g_in.up_para) : 0;
+        uint8_t *buf = (uint8_t *)malloc(len ? len : 1);
+        if (len && g_in.create_db_snapshot) g_in.create_db_snapshot(buf, g_in.up_para);
+        snprintf(snap, sizeof snap, "%s/snap%u.bin", g_env_rdv, i);
+        FILE *f = fopen(snap, "wb");
+        if (f) { fwrite(buf, 1, len, f); fclose(f); }
+        free(buf);
+        LOGT("   # snapshot len = %u\n", len);
+        /* the log: stop my kernel, map the joiner, copy my log behind its (empty) one, take it into the configuration */
+        apus_replica_t *rs[1] = { g_rep };
+        apus_replicas_stop(rs, 1);
+        apus_peer_handle_t h;
+        uint64_t resent = 0, last_idx = 0, last_term = 0, commit = 0, end = 0;
+        int ok = read_handle(i, &h) == 0 && apus_replica_connect(g_rep, (uint8_t)i, &h) == APUS_OK &&
+                 apus_ctl_last_entry(g_rep, &last_idx, &last_term, &commit, &end) == APUS_OK &&
+                 apus_ctl_adjust_follower(g_rep, (uint8_t)i, SID_MAKE(g_term, 1, g_idx), &resent) == APUS_OK;
+        if (!ok) LOGT("join of p%u failed: %s\n", i, apus_last_error());
+        if (launch_self() != APUS_OK) { LOGT("launch: %s\n", apus_last_error()); g_terminate = 1; return; }
+        unlink(req);
+        if (!ok) return;
+        g_live_mask |= 1u << i; g_removed_mask &= ~(1u << i);
+        uint8_t cid[16];
+        cid_image(cid, g_live_mask);
+        uint64_t t = 0;
+        if (apus_submit(g_rep, APUS_CONFIG, 0, 0, cid, 0, &t) == APUS_OK) { g_tk_type[t & (TK_RING - 1)] = APUS_CONFIG; g_join_ticket = t; apus_submit_flush(g_rep); }
+        snprintf(ack, sizeof ack, "%s/join%u.ack.tmp", g_env_rdv, i);
+        f = fopen(ack, "w");
+        if (f) {
+            fprintf(f, "%u %llu %llu %llu %u %u\n", (unsigned)g_idx, (unsigned long long)g_term, (unsigned long long)commit,
+                    (unsigned long long)(last_idx + 1), len, g_live_mask);
+            fclose(f);
+            char fin[512];
+            snprintf(fin, sizeof fin, "%s/join%u.ack", g_env_rdv, i);
+            rename(ack, fin);
+        }
+        LOGT("p%u joined: %llu log bytes sent, CONFIG entry appended (bitmask %03x)\n", i, (unsigned long long)resent, g_live_mask);
+        return;
+    }
+}
+
+/* joiner: announce myself, wait for the leader's reply, load the snapshot; returns 0 when ready to run as a follower */
+static int join_group(void)
+{
+    char path[560], tmp[600];
+    snprintf(path, sizeof path, "%s/join%u.ack", g_env_rdv, (unsigned)g_idx);
+    unlink(path);
+    snprintf(path, sizeof path, "%s/join%u.req", g_env_rdv, (unsigned)g_idx);
+    snprintf(tmp, sizeof tmp, "%s.tmp", path);
+    FILE *f = fopen(tmp, "w");
+    if (!f) return 1;
+    fprintf(f, "%d\n", (int)getpid());
+    fclose(f);
+    rename(tmp, path);
+    LOGT("JOIN request sent (slot p%u)\n", (unsigned)g_idx);
+    snprintf(path, sizeof path, "%s/join%u.ack", g_env_rdv, (unsigned)g_idx);
+    unsigned lead = 0, snaplen = 0, mask = 0;
+    unsigned long long term = 0, apply = 0, next_idx = 0;
+    for (int tries = 0;; tries++) {
+        f = fopen(path, "r");
+        if (f) {
+            int got = fscanf(f, "%u %llu %llu %llu %u %u", &lead, &term, &apply, &next_idx, &snaplen, &mask);
+            fclose(f);
+            if (got == 6) break;
+        }
+        if (g_terminate || tries > 60000) { LOGT("no reply to the JOIN request\n"); return 1; }
+        usleep(1000);
+    }
+    /* recover_sm: the snapshot goes through the proxy into the application (apply_db_snapshot, proxy.c:300-339) */
+    if (snaplen) {
+        snprintf(path, sizeof path, "%s/snap%u.bin", g_env_rdv, (unsigned)g_idx);
+        uint8_t *buf = (uint8_t *)malloc(snaplen);
+        f = fopen(path, "rb");
+        size_t got = f ? fread(buf, 1, snaplen, f) : 0;
+        if (f) fclose(f);
+        if (got != snaplen) { LOGT("snapshot short: %zu of %u bytes\n", got, snaplen); free(buf); return 1; }
+        if (g_in.apply_db_snapshot && g_in.apply_db_snapshot(buf, snaplen, g_in.up_para)) { LOGT("apply_db_snapshot failed\n"); free(buf); return 1; }
+        free(buf);
+    }
+    g_leader_idx = (uint8_t)lead; g_term = term; g_live_mask = mask;
+    g_apply = apply; g_apply_next_idx = next_idx;
+    apus_set_applied(g_rep, apply);
+    LOGT("joined: leader p%u, term %llu, snapshot of %u bytes applied, log follows from offset %llu (idx %llu)\n", lead, term, snaplen, apply, next_idx);
+    return 0;
+}
+
+/* leader: failure detector for FOLLOWERS.  A follower's kernel bumps its liveness counter in my HBM while it polls
+ * (the HB replies of dare_ibv_rc.c:912-958); a counter that stands still for hb_timeout is a server that is gone:
+ * it is disconnected and removed from the configuration with a CONFIG entry (check_failure_count,
+ * dare_server.c:1189-1228), so that nothing stores into its memory any more and a replacement can join its slot. */
+static uint64_t g_beat_val[APUS_MAX_SERVER_COUNT], g_beat_seen[APUS_MAX_SERVER_COUNT], g_last_beat_scan;
+static void leader_check_followers(uint64_t *submitted)
+{
+    const uint64_t now = now_us();
+    if (now - g_last_beat_scan < 5000) return;
+    g_last_beat_scan = now;
+    uint64_t b[APUS_MAX_SERVER_COUNT];
+    if (apus_follower_beats(g_rep, b) != APUS_OK) return;
+    uint64_t timeout = g_env_hbto_us > 0 ? (uint64_t)g_env_hbto_us : (uint64_t)(10.0 * cfg_hb_period * 1e6);
+    if (timeout < 20000) timeout = 20000;
+    for (unsigned i = 0; i < g_n; i++) {
+        if (i == g_idx || !(g_live_mask & (1u << i))) continue;
+        if (b[i] != g_beat_val[i]) { g_beat_val[i] = b[i]; g_beat_seen[i] = now; continue; }
+        if (!g_beat_seen[i] || now - g_beat_seen[i] < timeout) continue;       /* never seen yet (still starting), or recent */
+        LOGT("REMOVE SERVER p%u\n", i);                                          /* dare_server.c:1203 */
+        apus_replica_t *rs[1] = { g_rep };
+        apus_replicas_stop(rs, 1);
+        apus_replica_disconnect(g_rep, (uint8_t)i);
+        g_live_mask &= ~(1u << i); g_removed_mask |= 1u << i;
+        if (launch_self() != APUS_OK) { LOGT("launch: %s\n", apus_last_error()); g_terminate = 1; return; }
+        uint8_t cid[16];
+        cid_image(cid, g_live_mask);
+        uint64_t t = 0;
+        if (apus_submit(g_rep, APUS_CONFIG, 0, 0, cid, 0, &t) == APUS_OK) { g_tk_type[t & (TK_RING - 1)] = APUS_CONFIG; *submitted = t; apus_submit_flush(g_rep); }
+    }
+}
+
+/* ---- leader pump ---------------------------------------------------------------------------- */
 
 static void leader_pump(int elected)
 {
@@ -210,6 +365,11 @@ static void leader_pump(int elected)
             memcpy(image + 24, &n3->cmd.len, 2);
             if (g_in.store_cmd) g_in.store_cmd(image, g_in.up_para);
             free(n3);
+        }
+        if (g_n > 1 && !g_env_colocate) leader_check_followers(&submitted);
+        if (g_n > 1 && g_live_mask != ((1u << g_n) - 1u)) {
+            leader_serve_join(submitted, applied);
+            if (g_join_ticket) { submitted = g_join_ticket; g_join_ticket = 0; }
         }
         /* apply_committed_entries, leader branch (dare_server.c:1851-1861, 1951-1952) */
         uint64_t c = apus_committed_tickets(g_rep);
@@ -350,6 +510,11 @@ static int elect(void)
     if (apus_ctl_last_entry(g_rep, &last_idx, &last_term, &commit, &end) != APUS_OK) { LOGT("%s\n", apus_last_error()); return 1; }
     uint8_t cid[16];
     cid_image(cid, g_live_mask);
+    {   /* servers that joined after my start-up published their handles later: map them now (no-op for known peers) */
+        apus_peer_handle_t h;
+        for (unsigned i = 0; i < g_n; i++)
+            if (i != g_idx && i != dead && read_handle(i, &h) == 0) apus_replica_connect(g_rep, (uint8_t)i, &h);
+    }
     int candidate = 0;
     /* the first round starts at once (hb_receive_cb -> start_election); a split vote is retried after a random timeout */
     uint64_t deadline = now_us();
@@ -468,7 +633,8 @@ void *dare_server_init(void *arg)
     read_dare_config(g_in.config_path);
     if (g_env_elec_lo > 0) { cfg_elec_low = (uint64_t)g_env_elec_lo; cfg_elec_high = (uint64_t)g_env_elec_hi; }
     if (g_env_hb_us > 0) cfg_hb_period = g_env_hb_us * 1e-6;
-    if (g_in.srv_type != SRV_TYPE_START) { LOGT("server_type=join is not supported by the GPU engine yet\n"); return NULL; }
+    const int joining = (g_in.srv_type == SRV_TYPE_JOIN);
+    if (g_in.srv_type != SRV_TYPE_START && !joining) { LOGT("unknown server_type\n"); return NULL; }
     if (g_n < 1 || g_n > APUS_MAX_SERVER_COUNT || g_idx >= g_n) { LOGT("bad group_size/server_idx\n"); return NULL; }
 
     apus_config_t cfg;
@@ -477,6 +643,7 @@ void *dare_server_init(void *arg)
     int ndev = apus_device_count();
     if (ndev < 1) { LOGT("no CUDA device: the engine has no CPU fallback\n"); return NULL; }
     cfg.device = g_env_gpu >= 0 ? g_env_gpu : (int)(g_idx % (unsigned)ndev);
+    if (joining && g_leader_idx == g_idx) g_leader_idx = (uint8_t)((g_idx + 1) % g_n);   /* placeholder until the reply names the leader */
     cfg.server_idx = g_idx; cfg.group_size = g_n; cfg.leader_idx = g_leader_idx;
     cfg.ring_mode = APUS_RING_HOST_MAPPED;
     cfg.flags = APUS_F_EXPLICIT | APUS_F_DEVICE_STATS | APUS_F_AUTOPRUNE | APUS_F_HOST_APPLY;
@@ -491,7 +658,23 @@ void *dare_server_init(void *arg)
     cfg.leader_ctas = 2;
     if (apus_replica_create(&cfg, &g_rep) != APUS_OK) { LOGT("apus_replica_create: %s\n", apus_last_error()); return NULL; }
 
-    if (g_env_colocate && g_idx == g_leader_idx && g_n > 1) {
+    if (joining) {
+        /* server_type=join: publish my handle, map whoever is there, ask to be let in (join_group) */
+        apus_peer_handle_t mine, h;
+        char path[512], tmp[560];
+        mkdir(g_env_rdv, 0777);
+        snprintf(path, sizeof path, "%s/r%u.handle", g_env_rdv, (unsigned)g_idx);
+        snprintf(tmp, sizeof tmp, "%s.tmp.%d", path, (int)getpid());
+        FILE *hf = fopen(tmp, "wb");
+        if (apus_replica_export(g_rep, &mine) != APUS_OK || !hf) { LOGT("cannot publish my peer handle\n"); dare_server_shutdown(); }
+        fwrite(&mine, sizeof mine, 1, hf); fclose(hf); rename(tmp, path);
+        for (unsigned i = 0; i < g_n; i++)
+            if (i != g_idx && read_handle(i, &h) == 0 && apus_replica_connect(g_rep, (uint8_t)i, &h) != APUS_OK)
+                LOGT("   (p%u is not reachable: %s)\n", i, apus_last_error());
+        if (join_group() != 0 || apus_replica_set_role(g_rep, g_leader_idx, g_term) != APUS_OK || launch_self() != APUS_OK) {
+            LOGT("join failed: %s\n", apus_last_error()); dare_server_shutdown();
+        }
+    } else if (g_env_colocate && g_idx == g_leader_idx && g_n > 1) {
         /* One GPU cannot run the persistent kernels of several PROCESSES at once (contexts are time-sliced), so a
          * single-GPU box can host the followers' replicas inside the leader's process: their kernels ack and follow the
          * commit exactly as anywhere else, only their host side (do_action replay) does not exist.  Measurement aid for

@@ -543,15 +543,22 @@ def run_ours(args):
         e2e = {"value": round(world * K * batch / e_elapsed, 1), "unit": "ops/s",
                "h2d_bytes_per_step": batch * (96 + img), "d2h_bytes_per_step": 16,
                "ms_per_step": round(1e3 * e_elapsed / K, 4),
-               "submit_threads": int(os.environ.get("apus_submit_threads", "4")),
+               "submit_threads": int(os.environ.get("apus_submit_threads", "8")),
                "path": f"apus_submit_uniform(host numpy buffer, engine host threads) -> {args.e2e_ring} submission ring "
                        f"(pinned host memory read by the kernel over PCIe: 96 of the 128 slot bytes) -> resident kernels "
                        f"-> apus_wait_committed (16 B pinned commit record)"}
         # closed loop, one request in flight: host-view commit latency (proxy.c:160 spin)
         if rank == 0 and args.lat_requests > 0:
             st0 = cell.leader.stats()
+            f0 = [r.stats()["phase_ns"] for r in cell.local if not r.is_leader]
             lats = cell.leader.closed_loop(args.lat_requests, payload, conn, req)
             st1 = cell.leader.stats()
+            f1 = [r.stats()["phase_ns"] for r in cell.local if not r.is_leader]
+            nx = max(1, st1["turn_ns"][5] - st0["turn_ns"][5])
+            log("closed loop, leader express ns per request [place, compose, push, publish turn, publish]: "
+                f"{[round((b - a) / nx) for a, b in zip(st0['phase_ns'][1:6], st1['phase_ns'][1:6])]} over {nx} requests")
+            log("closed loop, followers [certificates verified, ns first sight -> verified (mean), verify retries]: "
+                f"{[(b[0] - a[0], round((b[1] - a[1]) / max(1, b[0] - a[0])), b[2] - a[2]) for a, b in zip(f0, f1)]}")
             req += args.lat_requests
             lats = np.sort(lats[args.lat_requests // 10:].astype(np.float64)) / 1e3
             lat_host = {"p50_us": round(float(lats[len(lats) // 2]), 2), "p99_us": round(float(lats[int(len(lats) * 0.99)]), 2),

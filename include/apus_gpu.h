@@ -172,7 +172,7 @@ int  apus_submit_batch(apus_replica_t *leader, uint32_t n, const uint8_t *types,
                        const uint16_t *lens, const void *payloads, size_t stride,
                        uint64_t *first_ticket);
 /* n requests of ONE shape (type, connection, len; req_id = first_req_id + k; payload k at payloads + k*stride):
- * the bulk form of proxy.c:108-161's enqueue, filled by several host threads (env apus_submit_threads, default 4). */
+ * the bulk form of proxy.c:108-161's enqueue, filled by several host threads (env apus_submit_threads, default 8). */
 int  apus_submit_uniform(apus_replica_t *leader, uint32_t n, uint8_t type, uint16_t connection_id,
                          uint64_t first_req_id, uint16_t len, const void *payloads, size_t stride,
                          uint64_t *first_ticket);
@@ -251,6 +251,9 @@ int  apus_ctl_adjust_follower(apus_replica_t *leader, uint8_t peer_idx, uint64_t
 /* role and term for the next launch.  Becoming leader takes over the log as this replica holds it (entry counters,
  * tail, submission ring); becoming follower adopts what the new leader's adjustment left (apus_ctl_view.adj_*). */
 int  apus_replica_set_role(apus_replica_t *r, uint8_t leader_idx, uint64_t term);
+/* leader: liveness counters of the followers (their kernels bump them while polling); a counter that stands still
+ * is a follower that is gone (HB replies, dare_ibv_rc.c:912-958 -> fail_count -> check_failure_count) */
+int  apus_follower_beats(apus_replica_t *leader, uint64_t out[APUS_MAX_SERVER_COUNT]);
 /* stop storing into a peer that is gone (dare_ib_disconnect_server, dare_server.c:1200) */
 int  apus_replica_disconnect(apus_replica_t *r, uint8_t peer_idx);
 

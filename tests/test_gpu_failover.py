@@ -28,7 +28,8 @@ def test_leader_failover(n):
     nconn, nreq2, plen = 3, 600, 64
     r = FD.run(n=n, nconn=nconn, nreq2=nreq2, plen=plen, kill_after_s=0.5, spread=nd > 1, ndev=nd)
     res, lead = r["results"], r["new_leader"]
-    assert lead in res and r["term"] == 2
+    T = r["term"]
+    assert lead in res and T >= 2              # (a split first round costs a term, as in the reference's own runs: term 4 there)
     assert "] LEADER" in r["logs"][lead]                       # the line reconf_bench.sh greps for
     # every survivor holds the same entries (reply bytes masked), committed up to the same end
     ents = {i: [(e["idx"], e["term"], e["type"], e["sender"], e["sha"]) for e in res[i]["entries"]] for i in res}
@@ -38,9 +39,9 @@ def test_leader_failover(n):
     idx = [e[0] for e in ref]
     assert idx == list(range(1, len(idx) + 1))
     # structure: term-1 entries stamped by p0, then two CONFIG entries of term 2 stamped by the new leader, then its requests
-    first2 = next(k for k, e in enumerate(ref) if e[1] == 2)
+    first2 = next(k for k, e in enumerate(ref) if e[1] == T)
     assert all(e[1] == 1 and e[3] == 0 for e in ref[:first2])
-    assert all(e[1] == 2 and e[3] == lead for e in ref[first2:])
+    assert all(e[1] == T and e[3] == lead for e in ref[first2:])
     c1, c2 = res[lead]["entries"][first2], res[lead]["entries"][first2 + 1]
     assert c1["type"] == 2 and c2["type"] == 2
     full = (1 << n) - 1

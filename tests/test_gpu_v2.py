@@ -175,6 +175,13 @@ def test_device_generated_requests_exact(eng, orc, payload):
 
 
 def _replay_thread(r, L, expect, sink, stop, delay_s):
+    try:
+        _replay(r, L, expect, sink, stop, delay_s)
+    except Exception as ex:                                  # noqa: BLE001 - surfaced by the test
+        sink["error"] = f"{type(ex).__name__}: {ex}"
+
+
+def _replay(r, L, expect, sink, stop, delay_s):
     """What follower_pump of libapus_dare.so does: read the committed range, walk it, 'apply', report the offset."""
     apply, next_idx = 0, 0
     h = hashlib.sha256()
@@ -267,7 +274,11 @@ def test_slow_follower_host_apply_many_laps(eng):
                     continue
                 t = t0 + k - 1
                 req += k; done += k
-        lead.wait_committed(t, 120_000_000)
+        t_end = time.time() + 150
+        while lead.committed() < t:
+            assert time.time() < t_end, f"stuck: committed {lead.committed()} of {t}; sinks {sinks}; leader {lead.offsets()} {lead.stats()}"
+            assert not any("error" in s_ for s_ in sinks), sinks
+            time.sleep(0.01)
         for th in ths:
             th.join(timeout=60)
         stop.set()
