@@ -128,15 +128,23 @@ __device__ __forceinline__ uint64_t ring_dist(uint64_t from, uint64_t to, uint64
 {
     return to >= from ? to - from : L - (from - to);
 }
-// A head offset read from the log header (a host control plane may move it, apus_set_head) replaces the one the
-// placement state carries only when it lies INSIDE the used region [head, end]: a header value read a while ago -- the
-// reader may have waited for its turn while almost a whole ring was appended -- lies in the free region by now, and
-// "closer to end" alone would mistake it for an advance and move the head backwards into freshly written bytes.
-__device__ __forceinline__ uint64_t merge_head(uint64_t head, uint64_t hdr_head, uint64_t end, uint64_t L)
+// A host control plane moves the head the way the reference's log_pruning does (dare_server.c:2041-2046): it appends a
+// HEAD entry that CARRIES the new head offset.  The leader adopts the offset when it places that entry -- never by
+// re-reading the log header: a ring offset read "a while ago" cannot be told from a new one (the reader may have waited
+// for its turn while almost a whole ring was appended), and a stale head taken for an advance unprotects entries the
+// followers' applications have not replayed yet.
+__device__ __forceinline__ uint64_t adopt_head(uint64_t head, uint64_t carried, uint64_t new_end, uint64_t L)
 {
-    if (end == L || hdr_head == head) return head;
-    const uint64_t used = ring_dist(head, end, L), at = ring_dist(head, hdr_head, L);
-    return (at <= used) ? hdr_head : head;
+    if (carried >= L) return head;
+    const uint64_t ne = (new_end == L) ? 0 : new_end;
+    return (ring_dist(head, carried, L) <= ring_dist(head, ne, L)) ? carried : head;     // only forward, only inside the used region
+}
+__device__ __forceinline__ uint64_t slot_head_value(const apus_cslot_t *sl)
+{
+    uint64_t v = 0;
+#pragma unroll
+    for (int q = 7; q >= 0; q--) v = (v << 8) | sl->inl[q];
+    return v;
 }
 
 #define WATCHDOG_NS (20ull * 1000ull * 1000ull * 1000ull)
@@ -168,6 +176,7 @@ struct LeaderShared {
     uint32_t ap_valid;         // ap[] was read for this claim
     uint32_t static_cut;       // first k > 0 whose payload image restarted the payload ring (else n_fetch)
     uint32_t first_ext_all;    // first entry with an external payload image (else 0xffffffff)
+    uint32_t host_head_k;      // last HEAD entry submitted by the host in this batch (else 0xffffffff): it carries the new head
     uint64_t idx_base;         // idx of an entry = idx_base + its 1-based position in the placement order
     uint8_t  ty[MAXB];
     uint8_t  flg[MAXB];        // bit0 EXT, bit1 WRAP
@@ -570,7 +579,7 @@ __device__ __noinline__ void leader_prescan(const apus_devctx_t *__restrict__ cx
     apus_ctrl_t *ctrl = reinterpret_cast<apus_ctrl_t *>(cx->region);
     apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_HDR_OFF);
     const uint32_t nf = S->n_fetch;
-    uint32_t carry = 0, xcarry = 0, scut = nf, fext = 0xffffffffu;
+    uint32_t carry = 0, xcarry = 0, scut = nf, fext = 0xffffffffu, hhk = 0xffffffffu;
     for (uint32_t r = 0; r < nf; r += 32) {
         const uint32_t k = r + lane;
         const bool in = k < nf;
@@ -584,12 +593,14 @@ __device__ __noinline__ void leader_prescan(const apus_devctx_t *__restrict__ cx
         if (in) { S->cum_es[k] = carry + inc; S->cum_xb[k] = xcarry + xinc; }
         carry += __shfl_sync(0xffffffffu, inc, 31);
         xcarry += __shfl_sync(0xffffffffu, xinc, 31);
+        const uint32_t hm = __ballot_sync(0xffffffffu, in && S->ty[k] == T_HEAD);
+        if (hm) hhk = r + (31u - (uint32_t)__clz(hm));                 // the LAST host HEAD entry of the batch
         const uint32_t wm = __ballot_sync(0xffffffffu, in && k > 0 && (S->flg[k] & 2u));
         const uint32_t em = __ballot_sync(0xffffffffu, in && (S->flg[k] & 1u));
         if (wm && scut == nf) scut = r + (uint32_t)(__ffs(wm) - 1);
         if (em && fext == 0xffffffffu) fext = r + (uint32_t)(__ffs(em) - 1);
     }
-    if (lane == 0) { S->static_cut = scut; S->first_ext_all = fext; }
+    if (lane == 0) { S->static_cut = scut; S->first_ext_all = fext; S->host_head_k = hhk; }
     if (lane < cx->group_size)
         S->ap[lane] = (lane == cx->idx) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[lane]);
 }
@@ -693,6 +704,10 @@ __device__ __noinline__ void leader_place(const apus_devctx_t *__restrict__ cx, 
             // commit the placement to the state this CTA carries
             if (autoh) st_relaxed_sys(&hdr->head, new_head);
             if (autoh) S->st_head = new_head;
+            if (S->host_head_k != 0xffffffffu && S->host_head_k >= kbase && S->host_head_k < kbase + m) {
+                const uint64_t nh = adopt_head(S->st_head, slot_head_value(&sl[S->host_head_k]), b, L);
+                if (nh != S->st_head) { S->st_head = nh; st_relaxed_sys(&hdr->head, nh); }
+            }
             if (S->gap) {
                 S->st_end = 0; S->st_hwm = L;
             } else {
@@ -746,16 +761,28 @@ __device__ __forceinline__ void express_release(apus_seq_t *seq, Express &X, int
     __syncwarp();
 }
 
+// first n bytes of a 16 B chunk from `nw`, the rest from `old`
+__device__ __forceinline__ uint4 chunk_select(const uint4 nw, const uint4 old, int n)
+{
+    uint32_t a[4] = {nw.x, nw.y, nw.z, nw.w}, o[4] = {old.x, old.y, old.z, old.w}, r[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const int k = n - 4 * w;                      // bytes of this word that come from `nw`
+        const uint32_t m = k >= 4 ? 0xffffffffu : (k <= 0 ? 0u : ((1u << (8 * k)) - 1u));
+        r[w] = (a[w] & m) | (o[w] & ~m);
+    }
+    return make_uint4(r[0], r[1], r[2], r[3]);
+}
+
 __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx, const LeaderShared *S, Express &X,
                                               const uint64_t claimed, uint4 sv, const bool have_slot, uint8_t *scratch,
-                                              const int lane)
+                                              const int lane, const uint4 pf, const uint64_t pf_pos)
 {
     const int N = cx->group_size, me = cx->idx;
     const uint64_t L = cx->log_len;
     apus_ctrl_t *ctrl = reinterpret_cast<apus_ctrl_t *>(cx->region);
     apus_seq_t *seq = reinterpret_cast<apus_seq_t *>(cx->region + APUS_SEQ_OFF);
     apus_pubrec_t *pubring = reinterpret_cast<apus_pubrec_t *>(cx->region + APUS_PUBRING_OFF);
-    apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_HDR_OFF);
     uint8_t *entries = cx->region + cx->entries_off;
     uint32_t *lindex = reinterpret_cast<uint32_t *>(cx->region + APUS_INDEX_OFF);
     const uint64_t t_deq = globaltimer_ns();
@@ -768,13 +795,10 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
     if (!has_cmd(ty) || (to & APUS_SLOT_EXT)) return 1;
     const uint32_t es = APUS_HDR_BYTES + len, nb = 2u + len;
 
-    // loads that do not depend on the placement, all in flight together: the followers' ack counts (is everybody
-    // caught up?), the apply offsets (is the pruning rule due?), a head moved by the host
+    // the followers' ack counts (is everybody caught up?) are needed only when the entry is published: in flight meanwhile
     const bool isf = lane < N && lane != me && cx->peer[lane];
-    uint64_t ackv = 0, apv = 0;
+    uint64_t ackv = 0;
     if (isf) ackv = ld_relaxed_sys(&ctrl->ack[lane]);
-    if (lane < N) apv = (lane == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[lane]);
-    const uint64_t hh = ld_relaxed_sys(&hdr->head);
 
     // ---- place turn ----
     uint64_t placed = X.placed, end = X.end, tf = X.tf, headv = X.head;
@@ -798,21 +822,14 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
         tf = __shfl_sync(0xffffffffu, tf, 0); headv = __shfl_sync(0xffffffffu, headv, 0);
         X.placed = placed; X.end = end; X.tf = tf; X.head = headv; X.have_place = 1; X.next_seq = claimed;
     }
-    const bool wrapped = (tf & APUS_REC_WRAPPED) != 0, prevh = (tf & APUS_REC_PREV_HEAD) != 0;
-    headv = merge_head(headv, hh, end, L);
+    const bool wrapped = (tf & APUS_REC_WRAPPED) != 0;
     const uint64_t pos0 = (end == L) ? 0 : end;
     const uint64_t used = (end == L) ? 0 : ring_dist(headv, end, L);
     const bool autoprune = (cx->flags & APUS_FLAG_AUTOPRUNE) != 0;
     const uint64_t reserve = autoprune ? APUS_HDR_BYTES : 0;
-    if (autoprune && end != L && used >= (L >> 2) && !prevh && L - pos0 >= APUS_HDR_BYTES) {
-        // the pruning rule of leader_place, evaluated by the whole warp; when it is due the tile machine appends the HEAD entry
-        uint64_t d = 0;
-        if (lane < N) { d = ring_dist(apv, end, L); if (d > used) d = used; }
-#pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) { const uint64_t o = __shfl_xor_sync(0xffffffffu, d, sft); d = o > d ? o : d; }
-        if (d == 0) d = ring_dist(tf & ~(APUS_REC_WRAPPED | APUS_REC_PREV_HEAD), end, L);
-        if (d <= used && used - d >= (L >> 3)) return 1;
-    }
+    // Pruning is the tile machine's business (it appends the HEAD entry): once the ring is half used every request is
+    // handed over until a HEAD entry has made room.  Below that the express path does not even look at the apply offsets.
+    if (autoprune && used >= (L >> 1)) return 1;
     if (pos0 + es > L || used + es + reserve >= L) return 1;          // wrap / no room: general placement
 
     const uint64_t a = pos0, b = pos0 + es;
@@ -831,26 +848,47 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
     const bool xprof = (cx->flags & APUS_FLAG_STATS) != 0;
     const uint64_t t_place = xprof ? globaltimer_ns() : 0;
 
-    // ---- compose: prefill (holes keep what the log held), header, data image ----
+    // ---- compose: lane c builds the 16 B chunk c of the entry.  Everything except two HOLES (bytes 41..47 and the
+    //      slack behind the data image) is new; the holes keep what the log held (dare_log.h:507-529 never writes them) --
+    //      those bytes were PREFETCHED while this warp was idle (pf, taken at the offset the next entry was going to get) ----
     const uint64_t a16 = a & ~15ull;
     const uint32_t nch = (uint32_t)(((b + 15ull) & ~15ull) - a16) >> 4;          // <= 11
-    uint8_t *img = scratch, *xsl = scratch + 256;
-    if (lane < (int)nch)
-        reinterpret_cast<uint4 *>(img)[lane] = wrapped ? ld_relaxed_sys_v4(entries + a16 + 16ull * lane) : make_uint4(0, 0, 0, 0);
-    if (lane == 1 || lane == 2) reinterpret_cast<uint4 *>(xsl)[lane - 1] = sv;   // inline image bytes 0..31
-    if (lane >= 4 && lane <= 6) reinterpret_cast<uint4 *>(xsl)[lane - 2] = sv;   // ... 32..79
-    __syncwarp();
-    uint8_t *e = img + (a - a16);
-    group_write_header(e, lane, 32, idx, cx->term, req_id, clt, ty, me, false);
-    group_copy_smem(e + E_DATA, xsl, nb, lane, 32);
-    __syncwarp();
+    const uint64_t lo = a16 + 16ull * lane;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if ((a & 15ull) == 0) {
+        uint4 oldv = make_uint4(0, 0, 0, 0);
+        if (wrapped) {
+            if (pf_pos == a) oldv = pf;
+            else if (lane < (int)nch) oldv = ld_relaxed_sys_v4(entries + lo);
+        }
+        const int j = lane - 3;                                       // data image chunk of this lane
+        const int srcl = (j < 0) ? 0 : ((j < 2) ? j + 1 : ((j + 2) & 31));   // slot chunk holding image bytes [16j, 16j+16)
+        uint4 dv;
+        dv.x = __shfl_sync(0xffffffffu, sv.x, srcl); dv.y = __shfl_sync(0xffffffffu, sv.y, srcl);
+        dv.z = __shfl_sync(0xffffffffu, sv.z, srcl); dv.w = __shfl_sync(0xffffffffu, sv.w, srcl);
+        if (lane == 0) v = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)cx->term, (uint32_t)(cx->term >> 32));
+        else if (lane == 1) v = make_uint4((uint32_t)req_id, (uint32_t)(req_id >> 32), (clt & 0xffffu) | (ty << 16) | ((uint32_t)me << 24), 0u);
+        else if (lane == 2) v = make_uint4(0u, 0u, oldv.z & 0xffffff00u, oldv.w);           // reply[4..12] = 0, bytes 41..47 stay
+        else v = chunk_select(dv, oldv, (int)nb - 16 * j);
+    } else {
+        // entry at an odd offset (ragged payloads): byte-granular composition in shared memory
+        uint8_t *img = scratch, *xsl = scratch + 256;
+        if (lane < (int)nch)
+            reinterpret_cast<uint4 *>(img)[lane] = wrapped ? ld_relaxed_sys_v4(entries + lo) : make_uint4(0, 0, 0, 0);
+        if (lane == 1 || lane == 2) reinterpret_cast<uint4 *>(xsl)[lane - 1] = sv;   // inline image bytes 0..31
+        if (lane >= 4 && lane <= 6) reinterpret_cast<uint4 *>(xsl)[lane - 2] = sv;   // ... 32..79
+        __syncwarp();
+        uint8_t *e = img + (a - a16);
+        group_write_header(e, lane, 32, idx, cx->term, req_id, clt, ty, me, false);
+        group_copy_smem(e + E_DATA, xsl, nb, lane, 32);
+        __syncwarp();
+        if (lane < (int)nch) v = reinterpret_cast<const uint4 *>(img)[lane];
+    }
     const uint64_t t_compose = xprof ? globaltimer_ns() : 0;
 
     // ---- push: local log first, then every follower; checksum of exactly the bytes [a, b) ----
     uint64_t cs = 0;
     if (lane < (int)nch) {
-        const uint4 v = reinterpret_cast<const uint4 *>(img)[lane];
-        const uint64_t lo = a16 + 16ull * lane;
         cs = cs_chunk(v, lo, a, b);
         if (lo >= a && lo + 16 <= b) {
             st_v4(entries + lo, v);
@@ -859,11 +897,11 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
                 if (S->peer_entries[f]) st_v4(S->peer_entries[f] + lo, v);
         } else {
 #pragma unroll 1
-            for (uint32_t j = 0; j < 16; j++) {
-                const uint64_t o = lo + j;
+            for (uint32_t jb = 0; jb < 16; jb++) {
+                const uint64_t o = lo + jb;
                 if (o < a || o >= b) continue;
-                const uint32_t w = (j < 4) ? v.x : (j < 8) ? v.y : (j < 12) ? v.z : v.w;
-                const uint32_t byte = (w >> (8 * (j & 3))) & 0xff;
+                const uint32_t w = (jb < 4) ? v.x : (jb < 8) ? v.y : (jb < 12) ? v.z : v.w;
+                const uint32_t byte = (w >> (8 * (jb & 3))) & 0xff;
                 st_u8(entries + o, byte);
 #pragma unroll 1
                 for (int f = 0; f < N; f++)
@@ -1020,6 +1058,8 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
     X.next_seq = 0; X.placed = 0; X.end = 0; X.tf = 0; X.head = 0; X.pub_h = 0; X.have_place = 0; X.hold = 0; X.pub_tail_seen = 0;
     for (int q = 0; q < 5; q++) X.dt[q] = 0;
     uint64_t xguess = ctrl->consumed;          // worker 0: the slot it expects to be claimed next
+    uint4 pf = make_uint4(0, 0, 0, 0);         // express: prefetched log bytes at offset pf_pos (lane c: chunk c)
+    uint64_t pf_pos = ~0ull;
 
     for (;;) {
         // ---- T0: claim the next slots of the submission ring: lock-free, one compare-and-swap on the
@@ -1038,6 +1078,13 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                 uint4 sv = make_uint4(0, 0, 0, 0);
                 if (poll_slot && lane < 8)
                     sv = ld_relaxed_sys_v4(reinterpret_cast<const uint8_t *>(cx->sub_slots + (xguess & cx->sub_mask)) + 16u * lane);
+                // idle-time prefetch: the bytes the log holds where the NEXT entry will go (its holes keep them); the offset
+                // is known as long as this warp placed the latest entry
+                if (express_on && X.have_place && X.end != cx->log_len && (X.tf & APUS_REC_WRAPPED) && pf_pos != X.end &&
+                    (X.end & 15ull) == 0 && X.end + 16ull * 12 <= cx->log_len) {
+                    if (lane < 12) pf = ld_relaxed_sys_v4(entries + X.end + 16ull * lane);
+                    pf_pos = X.end;
+                }
                 uint32_t ctl = 0;
                 uint64_t t = 0, w0i = 0;
                 if (lane == 0) {
@@ -1089,7 +1136,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     won = __shfl_sync(0xffffffffu, won, 0);
                     if (!won) continue;                   // somebody else took these slots: look again
                     if (nn == 1 && express_on) {
-                        const int rc = leader_express(cx, S, X, claimed, sv, slot_ok, img, lane);
+                        const int rc = leader_express(cx, S, X, claimed, sv, slot_ok, img, lane, pf, pf_pos);
                         if (rc == 0) {
                             xguess = claimed + 1; last_progress = globaltimer_ns();
                             if (prof) { tn[5]++; ph[7]++; for (int q = 0; q < 5; q++) ph[1 + q] += X.dt[q]; }
@@ -1116,7 +1163,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                 }
             }
             if (X.hold) express_release(seq, X, lane);
-            X.have_place = 0;                                  // other workers may place in between
+            X.have_place = 0; pf_pos = ~0ull;                  // other workers may place in between
             if (lane == 0) {
                 if (wid == 0) st_relaxed_sys(&seq->w0_idle, 0);
                 if (prof) { tn[0] += globaltimer_ns() - tw0; tn[6]++; }
@@ -1162,6 +1209,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         if (lane == 0) {
                             S->cum_es[0] = S->es[0]; S->cum_xb[0] = S->xb[0];
                             S->static_cut = 1; S->first_ext_all = (S->flg[0] & 1u) ? 0u : 0xffffffffu;
+                            S->host_head_k = (S->ty[0] == T_HEAD) ? 0u : 0xffffffffu;
                         }
                         S->ap_valid = 0;          // apply offsets are read only if the pruning rule could be due
                     } else {
@@ -1176,7 +1224,6 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         uint32_t spins = 0;
                         const uint64_t tw0 = prof ? globaltimer_ns() : 0;
                         uint64_t s0, s1, s2, s3, placed, end, tf, headv;
-                        const uint64_t hh = ld_relaxed_sys(&hdr->head);     // in flight together with the record
                         for (;;) {
                             ld_relaxed_sys_2x64(seq->rec_placed, s0, placed);
                             ld_relaxed_sys_2x64(seq->rec_end, s1, end);
@@ -1193,8 +1240,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         const uint64_t tail = tf & ~(APUS_REC_WRAPPED | APUS_REC_PREV_HEAD);
                         // ---- fast path ----
                         // a host control plane may also move the head (apus_set_head): take the newer of the two
-                        headv = merge_head(headv, hh, end, L);
-                        S->st_head = headv;
+                                            S->st_head = headv;
                         const uint64_t pos0 = (end == L) ? 0 : end;
                         const uint64_t used = (end == L) ? 0 : ring_dist(headv, end, L);
                         const uint64_t total = S->cum_es[nf - 1];
@@ -1223,6 +1269,10 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                             const uint64_t ne = (b == L) ? 0 : b;
                             const uint64_t nt = b - S->es[nf - 1];
                             const bool nw = wrapped || b == L;
+                            if (S->host_head_k != 0xffffffffu) {          // a HEAD entry submitted by the host carries the new head
+                                const uint64_t nh = adopt_head(headv, slot_head_value(&sl[S->host_head_k]), ne, L);
+                                if (nh != headv) { headv = nh; st_relaxed_sys(&hdr->head, nh); }
+                            }
                             // hand the turn on at once
                             st_relaxed_sys_2x64(seq->rec_placed, S->my_seq + S->n_fetch, placed + nf);
                             st_relaxed_sys_2x64(seq->rec_end, S->my_seq + S->n_fetch, ne);
@@ -1288,11 +1338,6 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         st_relaxed_sys(&hw->error, APUS_KERR_WATCHDOG_LEADER);
                         st_relaxed_sys(&seq->abort_flag, 1); S->finish = 1;
                     }
-                }
-                if (tid == 0) {
-                    // a host control plane may have moved the head; the apply offsets move all the time
-                    const uint64_t hh = ld_relaxed_sys(&hdr->head);
-                    S->st_head = merge_head(S->st_head, hh, S->st_end, cx->log_len);
                 }
                 if (tid < N) S->ap[tid] = (tid == me) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[tid]);
                 bar_sync(1, NT);
