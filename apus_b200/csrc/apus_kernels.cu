@@ -436,6 +436,7 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
         // every lane looks at one 16 B pair of the next four publish records (lane>>3 = record, lane&7 = pair)
         // while lanes 0..N-1 also poll the acks
         uint64_t st = 0, rv = 0, v = 0;
+        const uint64_t seen_before = seen;
         {
             const uint64_t rn = seen + (uint64_t)(lane >> 3);
             ld_relaxed_sys_2x64(&ring[rn & PUBMASK].w[2 * (lane & 7)], st, rv);
@@ -471,10 +472,12 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
             // prefix and an entry boundary (invariant I3).  Four records per step.
             uint64_t off = 0, tickets = committed_tickets, r_tail = 0, r_hwm = 0, r_next = 0;
             bool any = false;
+            bool reuse = (tail == seen_before);          // the pending records are exactly the ones this iteration loaded
             while (tail != seen) {
                 const uint64_t rn = tail + (uint64_t)(lane >> 3);
                 uint64_t st2 = 0, val = 0;
-                if (rn < seen) ld_relaxed_sys_2x64(&ring[rn & PUBMASK].w[2 * (lane & 7)], st2, val);
+                if (reuse) { val = rv; reuse = false; }
+                else if (rn < seen) ld_relaxed_sys_2x64(&ring[rn & PUBMASK].w[2 * (lane & 7)], st2, val);
                 // how many of these (up to four, in order) are covered by the quorum count
                 const uint32_t cm = __ballot_sync(0xffffffffu, (lane & 7) == PR_CUM && rn < seen && val <= Q);
                 uint32_t nc = 0;
@@ -785,7 +788,7 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
     apus_pubrec_t *pubring = reinterpret_cast<apus_pubrec_t *>(cx->region + APUS_PUBRING_OFF);
     uint8_t *entries = cx->region + cx->entries_off;
     uint32_t *lindex = reinterpret_cast<uint32_t *>(cx->region + APUS_INDEX_OFF);
-    const uint64_t t_deq = globaltimer_ns();
+    const uint64_t t_deq = (cx->flags & (APUS_FLAG_STATS | APUS_FLAG_PROFILE)) ? globaltimer_ns() : 0;
 
     if (!have_slot && lane < 8)
         sv = ld_relaxed_sys_v4(reinterpret_cast<const uint8_t *>(cx->sub_slots + (claimed & cx->sub_mask)) + 16u * lane);
@@ -845,7 +848,7 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
     }
     X.placed = cum; X.end = ne; X.tf = a | (nw ? APUS_REC_WRAPPED : 0ull); X.head = headv; X.have_place = 1;
     const uint64_t idx = S->idx_base + placed + 1;
-    const bool xprof = (cx->flags & APUS_FLAG_STATS) != 0;
+    const bool xprof = (cx->flags & APUS_FLAG_PROFILE) != 0;
     const uint64_t t_place = xprof ? globaltimer_ns() : 0;
 
     // ---- compose: lane c builds the 16 B chunk c of the entry.  Everything except two HOLES (bytes 41..47 and the
@@ -909,12 +912,10 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
             }
         }
     }
-    if (lane == 31) {
+    {   // offset index: lane f writes replica f's word (lane `me` the local one)
         const uint32_t at = (uint32_t)cum & cx->idx_mask;
-        lindex[at] = (uint32_t)a;
-#pragma unroll 1
-        for (int f = 0; f < N; f++)
-            if (S->peer_index[f]) S->peer_index[f][at] = (uint32_t)a;
+        uint32_t *ip = (lane == me) ? lindex : (lane < N ? S->peer_index[lane] : nullptr);
+        if (ip) ip[at] = (uint32_t)a;
     }
 #pragma unroll
     for (int sft = 16; sft > 0; sft >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, sft);
@@ -1060,6 +1061,8 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
     uint64_t xguess = ctrl->consumed;          // worker 0: the slot it expects to be claimed next
     uint4 pf = make_uint4(0, 0, 0, 0);         // express: prefetched log bytes at offset pf_pos (lane c: chunk c)
     uint64_t pf_pos = ~0ull;
+    uint4 sv_fly = make_uint4(0, 0, 0, 0);     // worker 0: the slot poll in flight ...
+    uint64_t sv_fly_for = ~0ull;               // ... and the slot number it was issued for
 
     for (;;) {
         // ---- T0: claim the next slots of the submission ring: lock-free, one compare-and-swap on the
@@ -1075,9 +1078,13 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             for (;;) {
                 // worker 0 polls the NEXT SLOT itself (lanes 0..7, one 128 B read over PCIe) while lane 0 looks at the
                 // claim counter and the doorbell: a lone request is in registers one PCIe round trip after the host wrote it
-                uint4 sv = make_uint4(0, 0, 0, 0);
+                // TWO polls are kept in flight (a PCIe read takes ~1.1 us: the host memory is then sampled every ~0.55 us):
+                // this iteration consumes the poll issued in the previous one and issues the next
+                uint4 sv = sv_fly;
+                const uint64_t sv_for = sv_fly_for;
                 if (poll_slot && lane < 8)
-                    sv = ld_relaxed_sys_v4(reinterpret_cast<const uint8_t *>(cx->sub_slots + (xguess & cx->sub_mask)) + 16u * lane);
+                    sv_fly = ld_relaxed_sys_v4(reinterpret_cast<const uint8_t *>(cx->sub_slots + (xguess & cx->sub_mask)) + 16u * lane);
+                sv_fly_for = xguess;
                 // idle-time prefetch: the bytes the log holds where the NEXT entry will go (its holes keep them); the offset
                 // is known as long as this warp placed the latest entry
                 if (express_on && X.have_place && X.end != cx->log_len && (X.tf & APUS_REC_WRAPPED) && pf_pos != X.end &&
@@ -1088,12 +1095,13 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                 uint32_t ctl = 0;
                 uint64_t t = 0, w0i = 0;
                 if (lane == 0) {
-                    if (ld_relaxed_sys(&seq->abort_flag)) ctl = 1;
+                    if ((spins & 0x3fu) == 0 && ld_relaxed_sys(&seq->abort_flag)) ctl = 1;
+                    // (relaxed: a doorbell that shows requests is re-read with acquire before anything is fetched)
+                    t = cx->doorbell_relay ? ld_relaxed_sys(&seq->doorbell) : ld_relaxed_sys(cx->sub_tail);
                     claimed = ld_relaxed_sys(&seq->claimed_slots);
                     if (claimed >= cx->target) ctl = 1;
-                    // slots + payload were written before the doorbell (read directly, or through the relay's mirror)
-                    t = cx->doorbell_relay ? ld_acquire_gpu(&seq->doorbell) : ld_acquire_sys(cx->sub_tail);
                     if (wid != 0) w0i = ld_relaxed_sys(&seq->w0_idle);
+                    if (t > claimed) t = cx->doorbell_relay ? ld_acquire_gpu(&seq->doorbell) : ld_acquire_sys(cx->sub_tail);
                 }
                 ctl = __shfl_sync(0xffffffffu, ctl, 0);
                 claimed = __shfl_sync(0xffffffffu, claimed, 0);
@@ -1105,7 +1113,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                 bool slot_ok = false;
                 if (poll_slot) {
                     const uint64_t stamp = (uint64_t)sv.x | ((uint64_t)sv.y << 32);
-                    slot_ok = (__ballot_sync(0xffffffffu, (lane == 3 || lane == 7) && stamp == xguess + 1) == 0x88u) && xguess == claimed;
+                    slot_ok = (__ballot_sync(0xffffffffu, (lane == 3 || lane == 7) && stamp == sv_for + 1) == 0x88u) && sv_for == claimed;
                     xguess = claimed;
                 }
                 uint64_t avail = t > claimed ? t - claimed : 0;
@@ -1148,7 +1156,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     n = nn;
                     break;
                 }
-                if ((++spins & 0xffu) == 0) {
+                if ((++spins & 0x1ffu) == 0) {
                     uint32_t stopf = 0;
                     if (lane == 0) {
                         if (ld_relaxed_sys_u32(&hw->stop)) stopf = 1;
@@ -1576,7 +1584,7 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
     uint64_t host_applied = hdr->apply;  // HOST_APPLY: the offset the application has replayed (what the leader may prune behind)
     uint64_t last_hb = ld_relaxed_sys(&ctrl->hb), last_hb_t = globaltimer_ns();
     bool suspected = false;
-    const bool fstat = (cx->flags & APUS_FLAG_STATS) != 0;       // follower profiling: phase_ns[0] certificates verified,
+    const bool fstat = (cx->flags & APUS_FLAG_PROFILE) != 0;     // follower profiling: phase_ns[0] certificates verified,
     uint64_t cert_first_cum = 0, cert_first_t = 0, fbeat = globaltimer_ns() >> 8;               // [1] ns from first sight to verified, [2] verify retries
 
     for (;;) {
@@ -1588,10 +1596,17 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
             uint32_t done = 0, is_cert = 0;
             for (;;) {
                 uint64_t x0 = 0, x1 = 0;
+                // lanes 4..15 read, SPECULATIVELY and in the same breath, the bytes where the next entry must land (a
+                // self-certifying publish names exactly that offset): when its certificate shows up the bytes are already
+                // in registers -- verification costs no second trip to memory
+                const uint64_t spec_a = (old_end == L) ? 0 : old_end;
+                const uint64_t spec_lo = (spec_a & ~15ull) + 16ull * (uint64_t)(lane - 4);
+                uint4 spec = make_uint4(0, 0, 0, 0);
                 if (lane == 0) ld_acquire_sys_2x64(&ctrl->pub_end, x0, x1);
                 else if (lane == 1) ld_relaxed_sys_2x64(&ctrl->pub_csum, x0, x1);
                 else if (lane == 2) x0 = ld_relaxed_sys(&hdr->commit);
                 else if (lane == 3) x0 = ld_relaxed_sys(&ctrl->hb);
+                else if (lane < 16 && spec_lo + 16 <= L) spec = ld_relaxed_sys_v4(entries + spec_lo);
                 e = __shfl_sync(0xffffffffu, x0, 0); cumt = __shfl_sync(0xffffffffu, x1, 0);
                 const uint64_t csum = __shfl_sync(0xffffffffu, x0, 1);
                 cert_start = __shfl_sync(0xffffffffu, x1, 1);
@@ -1613,7 +1628,9 @@ __device__ void follower_main(const apus_devctx_t *__restrict__ cx)
                         const uint64_t a16 = a & ~15ull;
                         const uint32_t nch = (uint32_t)(((b + 15ull) & ~15ull) - a16) >> 4;
                         uint64_t cs = 0;
-                        if (lane < (int)nch) cs = cs_chunk(ld_relaxed_sys_v4(entries + a16 + 16ull * lane), a16 + 16ull * lane, a, b);
+                        if (nch <= 12) {                  // the speculative read covers it (lane 4 + c holds chunk c)
+                            if (lane >= 4 && lane < 4 + (int)nch) cs = cs_chunk(spec, spec_lo, a, b);
+                        } else if (lane < (int)nch) cs = cs_chunk(ld_relaxed_sys_v4(entries + a16 + 16ull * lane), a16 + 16ull * lane, a, b);
 #pragma unroll
                         for (int sft = 16; sft > 0; sft >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, sft);
                         ok = (cs + cs_key(cumt)) == csum;

@@ -242,6 +242,8 @@ typedef struct apus_hostwords {
 #define APUS_FLAG_WALK       0x8u   /* follower parses the byte stream itself (reference behaviour) */
 #define APUS_FLAG_HOST_APPLY 0x10u  /* follower: the apply offset it reports is the one the HOST has replayed */
 #define APUS_FLAG_NO_EXPRESS 0x20u  /* leader: no single-warp express path / self-certifying publishes */
+#define APUS_FLAG_PROFILE    0x40u  /* %globaltimer stamps inside the express path and the follower's verification (each read
+                                       costs ~90 ns: kept out of measured runs) */
 
 #define APUS_PUB_CERT      (1ull << 63)          /* pub_end: this publish is self-certifying (no writer fence) */
 #define APUS_PUB_TERM_SHIFT 48                   /* pub_cum / hb: term in the top 16 bits */

@@ -17,7 +17,7 @@ RING_HOST_MAPPED, RING_DEVICE = 0, 1
 LOG_SIZE = 16384 * 4096
 MAX_SERVERS = 13
 F_FENCED_ACK, F_DEVICE_STATS, F_AUTOPRUNE, F_FOLLOWER_WALK, F_EXPLICIT = 0x1, 0x2, 0x4, 0x8, 0x80000000
-F_HOST_APPLY, F_NO_EXPRESS = 0x10, 0x20
+F_HOST_APPLY, F_NO_EXPRESS, F_PROFILE = 0x10, 0x20, 0x40
 UINT64_MAX = (1 << 64) - 1
 
 u64, u32, u16, u8, i64, i32 = C.c_uint64, C.c_uint32, C.c_uint16, C.c_uint8, C.c_int64, C.c_int32

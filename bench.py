@@ -70,6 +70,8 @@ def parse():
     ap.add_argument("--failover-trials", type=int, default=3)
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-proxy-leg", action="store_true", help="skip the 16-connection closed-loop leg through the reference's proxy.c")
+    ap.add_argument("--profile-latency", action="store_true",
+                    help="device timestamps inside the express path (adds ~0.6 us to every closed-loop request: diagnostic runs only)")
     ap.add_argument("--no-express", action="store_true", help="A/B: every publish fenced, no single-warp express path")
     ap.add_argument("--e2e-ring", default="mapped", choices=["mapped", "device"])
     ap.add_argument("--no-e2e", action="store_true")
@@ -411,7 +413,7 @@ def run_ours(args):
     ring_bytes = ((total_req * img + (1 << 20)) + 4095) // 4096 * 4096
     if ring_bytes // 16 > 0xFFFFFF:
         raise SystemExit("steps*batch*payload too large for the device payload ring (256 MiB): lower --batch or --steps")
-    xflag = E.F_NO_EXPRESS if args.no_express else 0
+    xflag = (E.F_NO_EXPRESS if args.no_express else 0) | (E.F_PROFILE if args.profile_latency else 0)
     flags = E.F_DEVICE_STATS | E.F_AUTOPRUNE | xflag
     vflags = (E.F_AUTOPRUNE | xflag) if args.no_stats else flags
     SEED = 0xA5A50000 + payload
@@ -555,10 +557,11 @@ def run_ours(args):
             st1 = cell.leader.stats()
             f1 = [r.stats()["phase_ns"] for r in cell.local if not r.is_leader]
             nx = max(1, st1["turn_ns"][5] - st0["turn_ns"][5])
-            log("closed loop, leader express ns per request [place, compose, push, publish turn, publish]: "
-                f"{[round((b - a) / nx) for a, b in zip(st0['phase_ns'][1:6], st1['phase_ns'][1:6])]} over {nx} requests")
-            log("closed loop, followers [certificates verified, ns first sight -> verified (mean), verify retries]: "
-                f"{[(b[0] - a[0], round((b[1] - a[1]) / max(1, b[0] - a[0])), b[2] - a[2]) for a, b in zip(f0, f1)]}")
+            if args.profile_latency:
+                log("closed loop, leader express ns per request [place, compose, push, publish turn, publish]: "
+                    f"{[round((b - a) / nx) for a, b in zip(st0['phase_ns'][1:6], st1['phase_ns'][1:6])]} over {nx} requests")
+                log("closed loop, followers [certificates verified, ns first sight -> verified (mean), verify retries]: "
+                    f"{[(b[0] - a[0], round((b[1] - a[1]) / max(1, b[0] - a[0])), b[2] - a[2]) for a, b in zip(f0, f1)]}")
             req += args.lat_requests
             lats = np.sort(lats[args.lat_requests // 10:].astype(np.float64)) / 1e3
             lat_host = {"p50_us": round(float(lats[len(lats) // 2]), 2), "p99_us": round(float(lats[int(len(lats) * 0.99)]), 2),

@@ -78,6 +78,7 @@ extern "C" {
                                      log->apply only after do_action (dare_server.c:1939-1962); off = apply follows
                                      commit on the device (nothing replays the log on the host) */
 #define APUS_F_NO_EXPRESS   0x20u /* leader: no single-warp express path, every publish is fenced (A/B switch) */
+#define APUS_F_PROFILE      0x40u /* fine-grained device timestamps in the latency path (diagnostic runs only: each costs ~90 ns) */
 #define APUS_F_EXPLICIT     0x80000000u /* flags are exactly as given (no defaults OR-ed in) */
 
 typedef struct apus_replica apus_replica_t;

@@ -25,7 +25,9 @@ def wait_file(path, timeout, procs, what):
     while not os.path.exists(path):
         assert time.time() - t0 < timeout, f"timed out waiting for {what}"
         for p in procs:
-            assert p.poll() is None or p.returncode == 0 or p.returncode == -9, f"a replica died while waiting for {what}"
+            if not (p.poll() is None or p.returncode == 0 or p.returncode == -9):
+                raise AssertionError(f"a replica died (rc {p.returncode}) while waiting for {what}:\n"
+                                     + (p.communicate()[0] or b"").decode(errors="replace")[-3000:])
         time.sleep(0.01)
 
 

@@ -209,7 +209,8 @@ def _replay(r, L, expect, sink, stop, delay_s):
                 break
             idx = int.from_bytes(buf[p:p + 8].tobytes(), "little")
             if next_idx and idx != next_idx:
-                sink["error"] = f"expected idx {next_idx}, found {idx} at {o}"
+                sink["error"] = (f"expected idx {next_idx}, found {idx} at {o}; batch [{apply}, {off}) of {len(buf)} bytes, p={p}; "
+                                 f"follower offsets {r.offsets()}")
                 return
             next_idx = idx + 1
             if typ == S.SEND:
@@ -277,7 +278,9 @@ def test_slow_follower_host_apply_many_laps(eng):
         t_end = time.time() + 150
         while lead.committed() < t:
             assert time.time() < t_end, f"stuck: committed {lead.committed()} of {t}; sinks {sinks}; leader {lead.offsets()} {lead.stats()}"
-            assert not any("error" in s_ for s_ in sinks), sinks
+            if any("error" in s_ for s_ in sinks):
+                raise AssertionError(f"{sinks}\nleader offsets {lead.offsets()}\nleader's view of the apply offsets "
+                                     f"{lead.remote_apply_offsets()[:n]}\nleader stats {lead.stats()}")
             time.sleep(0.01)
         for th in ths:
             th.join(timeout=60)
