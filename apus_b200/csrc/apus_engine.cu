@@ -128,6 +128,22 @@ extern "C" int apus_device_count(void)
     return n;
 }
 
+/* NUMA node of the host memory closest to a GPU (-1 = unknown): pinned rings and commit words should live there, and
+ * the threads that write / spin on them should run there -- a far-socket ring costs every PCIe poll a QPI/UPI hop */
+extern "C" int apus_device_numa_node(int device)
+{
+    char bus[64] = {0}, path[160];
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char *c = bus; *c; c++) if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
 static inline int is_leader(const apus_replica *r) { return r->cfg.server_idx == r->cfg.leader_idx; }
 
 static int ensure_host_ring(apus_replica *r)

@@ -173,7 +173,7 @@ struct LeaderShared {
     uint32_t rel[MAXB];        // entry start - sub-tile start (bytes)
     uint32_t xoff[MAXB];       // offset of the entry's image in the ext staging
     uint64_t ap[32];           // apply offsets of the replicas, read ahead of the place turn
-    uint32_t ap_valid;         // ap[] was read for this claim
+    uint32_t ap_valid;         // ap[] was read while holding the place turn of this claim (never earlier)
     uint32_t static_cut;       // first k > 0 whose payload image restarted the payload ring (else n_fetch)
     uint32_t first_ext_all;    // first entry with an external payload image (else 0xffffffff)
     uint32_t host_head_k;      // last HEAD entry submitted by the host in this batch (else 0xffffffff): it carries the new head
@@ -579,8 +579,6 @@ __device__ void leader_commit_warp(const apus_devctx_t *__restrict__ cx)
 // of the log strides and of the staged payload bytes of the fetched batch; apply offsets read ahead
 __device__ __noinline__ void leader_prescan(const apus_devctx_t *__restrict__ cx, LeaderShared *S, int lane)
 {
-    apus_ctrl_t *ctrl = reinterpret_cast<apus_ctrl_t *>(cx->region);
-    apus_loghdr_t *hdr = reinterpret_cast<apus_loghdr_t *>(cx->region + APUS_HDR_OFF);
     const uint32_t nf = S->n_fetch;
     uint32_t carry = 0, xcarry = 0, scut = nf, fext = 0xffffffffu, hhk = 0xffffffffu;
     for (uint32_t r = 0; r < nf; r += 32) {
@@ -604,8 +602,9 @@ __device__ __noinline__ void leader_prescan(const apus_devctx_t *__restrict__ cx
         if (em && fext == 0xffffffffu) fext = r + (uint32_t)(__ffs(em) - 1);
     }
     if (lane == 0) { S->static_cut = scut; S->first_ext_all = fext; S->host_head_k = hhk; }
-    if (lane < cx->group_size)
-        S->ap[lane] = (lane == cx->idx) ? ld_relaxed_sys(&hdr->apply) : ld_relaxed_sys(&ctrl->apply_off[lane]);
+    // (the apply offsets are NOT read here: they are ring offsets, and a snapshot taken before the place turn can be so
+    //  old by the time it is used -- other workers may have pruned in between -- that it falls into the used region of
+    //  the NEXT lap and reads as "almost caught up"; they are read while holding the turn, see leader_main)
 }
 
 // T2b (inside the place turn): place the next sub-tile of the fetched batch (entries kbase..nf) --
@@ -1069,7 +1068,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
         //      claimed-slots counter.  The claimed range [slot0, slot0+n) is also the worker's place in
         //      the order: the place and publish turns are stamped with slot numbers ----
         if (warp == 0) {
-            uint32_t n = 0, fin = 0, spins = 0;
+            uint32_t n = 0, fin = 0, spins = 0, lone_waits = 0;
             const uint64_t tw0 = prof ? globaltimer_ns() : 0;
             uint64_t claimed = 0;
             const bool poll_slot = cx->slot_poll != 0 && wid == 0;
@@ -1118,6 +1117,9 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                 }
                 uint64_t avail = t > claimed ? t - claimed : 0;
                 if (slot_ok && avail == 0) avail = 1;
+                // the doorbell may show a lone request before the slot poll in flight does: wait for the poll (next
+                // iteration) instead of claiming now and fetching the slot with one more PCIe round trip
+                if (poll_slot && express_on && avail == 1 && !slot_ok && ++lone_waits < 8) avail = 0; else lone_waits = 0;
                 // lone requests belong to worker 0 while it is polling (express path)
                 if (avail == 1 && wid != 0 && w0i) avail = 0;
                 if (avail) {
@@ -1222,7 +1224,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         S->ap_valid = 0;          // apply offsets are read only if the pruning rule could be due
                     } else {
                         leader_prescan(cx, S, lane);
-                        if (lane == 0) S->ap_valid = 1;
+                        if (lane == 0) S->ap_valid = 0;
                     }
                     __syncwarp();
                     // the place turn: wait until the three stamped pairs carry my claim number.  It is held for

@@ -61,7 +61,7 @@ EXPORTS = [
     "apus_log_read_range", "apus_leader_suspect", "apus_last_commit_ns",
     "apus_ctl_read", "apus_ctl_set_sid", "apus_ctl_reset_votes", "apus_ctl_clear_vote_request", "apus_ctl_send_vote_request",
     "apus_ctl_send_vote_ack", "apus_ctl_last_entry", "apus_ctl_adjust_follower", "apus_replica_set_role",
-    "apus_replica_disconnect", "apus_follower_beats",
+    "apus_replica_disconnect", "apus_follower_beats", "apus_device_numa_node",
 ]
 
 
@@ -305,6 +305,27 @@ def synth_payload(seed: int, req_id: int, length: int) -> bytes:
     x ^= x >> np.uint64(15); x = (x * np.uint64(0x846CA68B)) & M
     x ^= x >> np.uint64(16)
     return x.astype(np.uint32).view(np.uint8)[:length].tobytes()
+
+
+def pin_to_device_node(device: int):
+    """Run this process on the CPUs of the NUMA node next to `device` (its pinned rings are then allocated there too).
+    Returns the node, or None when the topology is not exposed."""
+    try:
+        lib().apus_device_numa_node.argtypes = [C.c_int]
+        node = int(lib().apus_device_numa_node(device))
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:                                        # noqa: BLE001 - best effort
+        pass
+    return None
 
 
 def cid_image(n: int) -> bytes:

@@ -400,6 +400,7 @@ def run_ours(args):
     if not torch.cuda.is_available() or A.lib().apus_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_node = E.pin_to_device_node(local)        # submitting / spinning threads and the pinned rings next to the leader's GPU
 
     n, payload = args.replicas, args.payload
     K, W = args.steps, args.warmup
@@ -613,6 +614,7 @@ def run_ours(args):
                           ("replica r on GPU r % visible GPUs, one process" if world == 1 else
                            f"group g led by GPU g, replica r on GPU (g + r) % {world}, one process per GPU, CUDA IPC")),
             "log_ring_bytes": L, "log_pruning": "device-side HEAD entries (APUS_F_AUTOPRUNE)",
+            "host_numa_node": numa_node,
             "cache": f"inputs larger than L2: {(K + W) * batch * (128 + img) >> 20} MiB of requests stream through once; "
                      f"every step writes {batch * stride >> 20} MiB into each replica's {L >> 20} MiB log ring",
         },

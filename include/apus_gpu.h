@@ -135,6 +135,8 @@ typedef struct apus_stats {
 int         apus_abi_version(void);
 const char *apus_last_error(void);
 int         apus_device_count(void);
+/* NUMA node of the host memory next to a GPU, -1 if unknown: run the submitting threads (and allocate) there */
+int         apus_device_numa_node(int device);
 
 /* ---- replica life cycle --------------------------------------------------------- */
 /* Allocates the HBM region (log header + entries + ctrl words), zeroed like

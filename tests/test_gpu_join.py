@@ -71,6 +71,12 @@ def test_follower_replaced_by_a_joiner():
                 wait_file(os.path.join(d, f"result{tag}.json"), 120, [procs[0], procs[1], joiner], f"result {tag}")
                 res[tag] = json.load(open(os.path.join(d, f"result{tag}.json")))
             logs = {t: open(os.path.join(d, f"dare{t}.log")).read() for t in ("0", "1", "2j")}
+        except AssertionError as ex:
+            logs_txt = ""
+            for f in sorted(os.listdir(d)):
+                if f.startswith("dare") and f.endswith(".log"):
+                    logs_txt += f"\n--- {f}\n" + open(os.path.join(d, f)).read()[-1800:]
+            raise AssertionError(str(ex) + logs_txt) from None
         finally:
             for p in procs:
                 if p.poll() is None:
