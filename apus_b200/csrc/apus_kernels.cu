@@ -1060,8 +1060,6 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
     uint64_t xguess = ctrl->consumed;          // worker 0: the slot it expects to be claimed next
     uint4 pf = make_uint4(0, 0, 0, 0);         // express: prefetched log bytes at offset pf_pos (lane c: chunk c)
     uint64_t pf_pos = ~0ull;
-    uint4 sv_fly = make_uint4(0, 0, 0, 0);     // worker 0: the slot poll in flight ...
-    uint64_t sv_fly_for = ~0ull;               // ... and the slot number it was issued for
 
     for (;;) {
         // ---- T0: claim the next slots of the submission ring: lock-free, one compare-and-swap on the
@@ -1077,13 +1075,12 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
             for (;;) {
                 // worker 0 polls the NEXT SLOT itself (lanes 0..7, one 128 B read over PCIe) while lane 0 looks at the
                 // claim counter and the doorbell: a lone request is in registers one PCIe round trip after the host wrote it
-                // TWO polls are kept in flight (a PCIe read takes ~1.1 us: the host memory is then sampled every ~0.55 us):
-                // this iteration consumes the poll issued in the previous one and issues the next
-                uint4 sv = sv_fly;
-                const uint64_t sv_for = sv_fly_for;
+                uint4 sv = make_uint4(0, 0, 0, 0);
+                const uint64_t sv_for = xguess;
                 if (poll_slot && lane < 8)
-                    sv_fly = ld_relaxed_sys_v4(reinterpret_cast<const uint8_t *>(cx->sub_slots + (xguess & cx->sub_mask)) + 16u * lane);
-                sv_fly_for = xguess;
+                    sv = ld_relaxed_sys_v4(reinterpret_cast<const uint8_t *>(cx->sub_slots + (xguess & cx->sub_mask)) + 16u * lane);
+                // (a second poll in flight does not help: two loads of one line from one SM are merged, the younger one
+                //  returns the older one's sample -- measured: host-clock latency got worse by ~1.5 us)
                 // idle-time prefetch: the bytes the log holds where the NEXT entry will go (its holes keep them); the offset
                 // is known as long as this warp placed the latest entry
                 if (express_on && X.have_place && X.end != cx->log_len && (X.tf & APUS_REC_WRAPPED) && pf_pos != X.end &&

@@ -170,6 +170,7 @@ static int read_handle(unsigned i, apus_peer_handle_t *h)
     return got == 1 ? 0 : 1;
 }
 
+static uint64_t g_beat_val[APUS_MAX_SERVER_COUNT], g_beat_seen[APUS_MAX_SERVER_COUNT], g_last_beat_scan;
 static uint64_t g_last_join_scan;
 /* leader: serve one pending join request, if any.  Called between batches with nothing in flight. */
 static void leader_serve_join(uint64_t submitted, uint64_t applied)
@@ -206,6 +207,8 @@ static void leader_serve_join(uint64_t submitted, uint64_t applied)
         unlink(req);
         if (!ok) return;
         g_live_mask |= 1u << i; g_removed_mask &= ~(1u << i);
+        g_beat_seen[i] = 0; g_beat_val[i] = 0;                /* a new process: its liveness counter starts over */
+        { uint64_t b[APUS_MAX_SERVER_COUNT]; if (apus_follower_beats(g_rep, b) == APUS_OK) g_beat_val[i] = b[i]; }
         uint8_t cid[16];
         cid_image(cid, g_live_mask);
         uint64_t t = 0;
@@ -274,7 +277,6 @@ static int join_group(void)
  * (the HB replies of dare_ibv_rc.c:912-958); a counter that stands still for hb_timeout is a server that is gone:
  * it is disconnected and removed from the configuration with a CONFIG entry (check_failure_count,
  * dare_server.c:1189-1228), so that nothing stores into its memory any more and a replacement can join its slot. */
-static uint64_t g_beat_val[APUS_MAX_SERVER_COUNT], g_beat_seen[APUS_MAX_SERVER_COUNT], g_last_beat_scan;
 static void leader_check_followers(uint64_t *submitted)
 {
     const uint64_t now = now_us();

@@ -537,11 +537,16 @@ def run_ours(args):
         for s in range(W):
             e2e_step()
         host_barrier()
+        es0 = cell.leader.stats()
         t0 = time.perf_counter()
         for s in range(K):
             e2e_step()
         t1 = time.perf_counter()
+        es1 = cell.leader.stats()
         host_barrier()
+        log("e2e, worker-0 phase ns per tile [wait for requests, T1 fetch, T2 place, T3 prefill, T4 compose, T5 store, T6 publish]: "
+            f"{[round((b - a) / max(1, es1['phase_ns'][7] - es0['phase_ns'][7])) for a, b in zip(es0['phase_ns'][:7], es1['phase_ns'][:7])]} "
+            f"over {es1['phase_ns'][7] - es0['phase_ns'][7]} tiles")
         e_elapsed = max_over_ranks_host(t1 - t0)
         e2e = {"value": round(world * K * batch / e_elapsed, 1), "unit": "ops/s",
                "h2d_bytes_per_step": batch * (96 + img), "d2h_bytes_per_step": 16,
