@@ -1319,7 +1319,12 @@ extern "C" int apus_replica_set_role(apus_replica_t *r, uint8_t leader_idx, uint
     r->cfg.term = term;
     if (!is_leader(r)) {
         if (!r->peer_ptr[leader_idx]) return fail("not connected to the new leader");
-        return APUS_OK;              /* the leader's adjustment already set end / old_end / the entry counter */
+        /* the leader's adjustment already set end / old_end / the entry counter (and, for a joiner, head and commit):
+         * what the host sees as "committed and held" starts there, not at a stale or never-written word */
+        apus_loghdr_t h;
+        if (own_read(r, APUS_HDR_OFF, &h, sizeof h) != APUS_OK) return APUS_ERROR;
+        r->hw->commit_off = h.commit;
+        return APUS_OK;
     }
     if (was_leader) return APUS_OK;
     /* ---- a follower takes the log over as it holds it ---- */

@@ -77,7 +77,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stats", action="store_true", help="value run without device-side profiling counters")
-    ap.add_argument("--leader-ctas", type=int, default=8, help="leader worker CTAs (SMs building tiles in parallel)")
+    ap.add_argument("--leader-ctas", type=int, default=16, help="leader worker CTAs (SMs building tiles in parallel)")
     ap.add_argument("--spread", action="store_true",
                     help="single process: place replica r on GPU r %% visible GPUs (NVLink path)")
     return ap.parse_args()

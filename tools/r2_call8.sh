@@ -11,5 +11,7 @@ timeout 150 python tools/sweep_spread.py --sizes 1024,4096 --replicas 7 --ctas 3
 timeout 240 python bench.py --spread --replicas 5 --steps 8 --no-cpu > $OUT/bench_spread5.json 2> $OUT/bench_spread5.err; grep -v "^$" $OUT/bench_spread5.err | tail -8 | cut -c1-600
 timeout 200 python bench.py --failover --failover-trials 2 > $OUT/failover.json 2> $OUT/failover.err; cut -c1-1500 $OUT/failover.json
 timeout 200 python -m pytest tests/test_gpu_failover.py tests/test_gpu_join.py -m gpu -q -s > $OUT/pytest_failover_join_8gpus.log 2>&1; tail -5 $OUT/pytest_failover_join_8gpus.log
+timeout 150 bash benchmarks/run_gpu.sh --app=redis --scount=5 --ccount=16 --rcount=200000 > $OUT/redis_5gpus.txt 2>&1; tail -6 $OUT/redis_5gpus.txt
+timeout 150 bash benchmarks/run_gpu.sh --app=redis --scount=5 --ccount=16 --rcount=100000 --kill-leader --port=9888 > $OUT/redis_5gpus_kill_leader.txt 2>&1; tail -8 $OUT/redis_5gpus_kill_leader.txt
 timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 8 --warmup 3 --no-cpu > $OUT/bench_8gpu_torchrun.json 2> $OUT/bench_8gpu.err; grep "parity\|value:" $OUT/bench_8gpu.err | cut -c1-400; cut -c1-300 $OUT/bench_8gpu_torchrun.json
 ls -la $OUT
