@@ -9,6 +9,7 @@
  * All replication work happens in those kernels; nothing here touches entry
  * bytes, and there is no CPU fallback.
  */
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <emmintrin.h>
 #include <pthread.h>
@@ -45,6 +46,43 @@ static int fail(const char *fmt, ...)
         if (_e != cudaSuccess)                                                               \
             return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
+
+/* driver entry points for fabric mode (VMM + multicast), fetched at run time: see the fabric section below */
+struct drv_t {
+    CUresult (*MemCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long);
+    CUresult (*MemAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long);
+    CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+    CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t);
+    CUresult (*MemGetAllocationGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags);
+    CUresult (*MemUnmap)(CUdeviceptr, size_t);
+    CUresult (*MemRelease)(CUmemGenericAllocationHandle);
+    CUresult (*MemAddressFree)(CUdeviceptr, size_t);
+    CUresult (*MulticastCreate)(CUmemGenericAllocationHandle *, const CUmulticastObjectProp *);
+    CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice);
+    CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long);
+    CUresult (*MulticastGetGranularity)(size_t *, const CUmulticastObjectProp *, CUmulticastGranularity_flags);
+    CUresult (*DeviceGetAttribute)(int *, CUdevice_attribute, CUdevice);
+    int ok;
+};
+static drv_t g_drv;
+static int drv_load(void)
+{
+    if (g_drv.ok) return APUS_OK;
+#define DRV(field, name) do { void *fn = NULL; cudaDriverEntryPointQueryResult qr;                                   \
+        if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {                    \
+            cudaGetLastError(); return fail("driver entry point %s is not available", name); }                      \
+        *(void **)(&g_drv.field) = fn; } while (0)
+    DRV(MemCreate, "cuMemCreate"); DRV(MemAddressReserve, "cuMemAddressReserve"); DRV(MemMap, "cuMemMap");
+    DRV(MemSetAccess, "cuMemSetAccess"); DRV(MemGetAllocationGranularity, "cuMemGetAllocationGranularity");
+    DRV(MemUnmap, "cuMemUnmap"); DRV(MemRelease, "cuMemRelease"); DRV(MemAddressFree, "cuMemAddressFree");
+    DRV(MulticastCreate, "cuMulticastCreate"); DRV(MulticastAddDevice, "cuMulticastAddDevice");
+    DRV(MulticastBindMem, "cuMulticastBindMem"); DRV(MulticastGetGranularity, "cuMulticastGetGranularity");
+    DRV(DeviceGetAttribute, "cuDeviceGetAttribute");
+#undef DRV
+    g_drv.ok = 1;
+    return APUS_OK;
+}
+#define CU(call) do { CUresult _e = (call); if (_e != CUDA_SUCCESS) return fail("%s failed: driver error %d (%s:%d)", #call, (int)_e, __FILE__, __LINE__); } while (0)
 
 struct StageLock {
     pthread_mutex_t *m;
@@ -101,6 +139,11 @@ struct apus_replica {
     uint32_t ring_slots, ring_bytes;
     uint64_t submitted, flushed;  /* tickets handed out / tickets whose slots the device can read */
     uint64_t belled;              /* doorbell value the kernel has been given */
+    /* fabric mode (APUS_F_FABRIC): the region is a VMM allocation that can be bound to an NVSwitch multicast object */
+    CUmemGenericAllocationHandle vmm_handle;
+    size_t   vmm_bytes;           /* region_bytes rounded up to the allocation granularity */
+    CUmemGenericAllocationHandle mc_handle;   /* leader: the group's multicast object ... */
+    uint8_t *mc_region;           /* ... mapped: one store here lands in every replica's region */
     uint8_t *stage;               /* pinned bounce buffer for log reads */
     pthread_mutex_t stage_mu;     /* ... used by the consensus thread and by inspection calls from other threads */
     size_t   stage_bytes;
@@ -156,6 +199,7 @@ static int ensure_host_ring(apus_replica *r)
     return APUS_OK;
 }
 
+static int fabric_alloc_region(apus_replica *r);
 static int leader_ring_init(apus_replica *r)
 {
     if (r->pay_end) return APUS_OK;                      /* already a leader once */
@@ -186,7 +230,8 @@ static int replica_init(apus_replica *r, const apus_config_t *cfg, uint64_t log_
     r->idx_cap = cap;
     r->entries_off = (APUS_INDEX_OFF + (uint64_t)cap * 4ull + 4095ull) & ~4095ull;
     r->region_bytes = r->entries_off + log_len;
-    CK(cudaMalloc(&r->region, r->region_bytes));
+    if (r->cfg.flags & APUS_F_FABRIC) { if (fabric_alloc_region(r) != APUS_OK) return APUS_ERROR; }
+    else CK(cudaMalloc(&r->region, r->region_bytes));
     CK(cudaMemset(r->region, 0, r->region_bytes));
     /* log_new(): end = tail = old_end = len (dare_log.h:129-134) */
     apus_loghdr_t h;
@@ -295,7 +340,12 @@ extern "C" void apus_replica_destroy(apus_replica_t *r)
     if (r->stream) cudaStreamDestroy(r->stream);
     if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
     if (r->hw) cudaFreeHost((void *)r->hw);
-    if (r->region) cudaFree(r->region);
+    if (r->vmm_handle && g_drv.ok) {
+        if (r->mc_region) { g_drv.MemUnmap((CUdeviceptr)r->mc_region, r->vmm_bytes); g_drv.MemAddressFree((CUdeviceptr)r->mc_region, r->vmm_bytes); }
+        if (r->mc_handle) g_drv.MemRelease(r->mc_handle);
+        if (r->region) { g_drv.MemUnmap((CUdeviceptr)r->region, r->vmm_bytes); g_drv.MemAddressFree((CUdeviceptr)r->region, r->vmm_bytes); }
+        g_drv.MemRelease(r->vmm_handle);
+    } else if (r->region) cudaFree(r->region);
     cudaGetLastError();
     free(r->pay_end);
     free(r);
@@ -309,7 +359,7 @@ extern "C" int apus_replica_export(apus_replica_t *r, apus_peer_handle_t *out)
     memset(&b, 0, sizeof b);
     b.magic = PEER_MAGIC; b.pid = (int64_t)getpid(); b.device = r->cfg.device;
     b.ptr = (uint64_t)(uintptr_t)r->region; b.bytes = r->region_bytes;
-    CK(cudaIpcGetMemHandle(&b.ipc, r->region));
+    if (!r->vmm_handle) CK(cudaIpcGetMemHandle(&b.ipc, r->region));       /* (fabric regions: same-process peers only, this round) */
     memset(out, 0, sizeof *out);
     memcpy(out, &b, sizeof b);
     return APUS_OK;
@@ -339,6 +389,7 @@ extern "C" int apus_replica_connect(apus_replica_t *r, uint8_t peer_idx, const a
         r->peer_is_ipc[peer_idx] = 0;
     } else {
         void *p = NULL;
+        if (r->vmm_handle) return fail("fabric-mode regions are shared between replicas of one process only");
         CK(cudaIpcOpenMemHandle(&p, b.ipc, cudaIpcMemLazyEnablePeerAccess));
         r->peer_ptr[peer_idx] = p;
         r->peer_is_ipc[peer_idx] = 1;
@@ -363,6 +414,7 @@ static void fill_ctx(apus_replica *r, uint64_t target)
     c->hb_period_ns = (uint64_t)r->cfg.hb_period_us * 1000ull;
     c->hb_timeout_ns = (target == ~0ull) ? (uint64_t)r->cfg.hb_timeout_us * 1000ull : 0;   /* bounded launches end on their own */
     c->region = r->region;
+    c->mc_region = r->mc_region;
     for (int i = 0; i < APUS_MAX_SERVER_COUNT; i++)
         c->peer[i] = (i == r->cfg.server_idx) ? NULL : (uint8_t *)r->peer_ptr[i];
     c->sub_slots = r->ring_desc_dev; c->sub_pay = r->ring_pay_dev;
@@ -1070,6 +1122,82 @@ extern "C" int apus_latency_samples(apus_replica_t *r, uint32_t *dst, uint32_t m
     return APUS_OK;
 }
 
+
+
+/* ==================================================================================================
+ * Fabric mode: VMM regions + NVSwitch multicast (tools/probe_fabric measured it on this pool: cuMulticast* is
+ * supported, `multimem.st.v4` moves 63 GB/s of source bytes per CTA and lands them in EVERY member -- the leader's
+ * egress for the replicate step drops from (N-1)x to 1x).  The driver entry points are fetched at run time
+ * (cudaGetDriverEntryPoint): the library keeps loading on a box without libcuda (CPU-only test runs).
+ * This round: groups whose replicas live in ONE process (tests, sweeps, `bench.py --spread`); one process per
+ * replica would pass the allocation and multicast handles as POSIX file descriptors (pidfd_getfd works here).
+ * ================================================================================================== */
+static int fabric_alloc_region(apus_replica *r)
+{
+    if (drv_load() != APUS_OK) return APUS_ERROR;
+    int ndev = apus_device_count();
+    CUmemAllocationProp ap;
+    memset(&ap, 0, sizeof ap);
+    ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    ap.location.id = r->cfg.device;
+    size_t gran = 0;
+    CU(g_drv.MemGetAllocationGranularity(&gran, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+    if (gran < (2u << 20)) gran = 2u << 20;
+    r->vmm_bytes = (r->region_bytes + gran - 1) / gran * gran;
+    CU(g_drv.MemCreate(&r->vmm_handle, r->vmm_bytes, &ap, 0));
+    CUdeviceptr va = 0;
+    CU(g_drv.MemAddressReserve(&va, r->vmm_bytes, gran, 0, 0));
+    CU(g_drv.MemMap(va, r->vmm_bytes, 0, r->vmm_handle, 0));
+    CUmemAccessDesc acc[64];
+    for (int d = 0; d < ndev && d < 64; d++) { acc[d].location.type = CU_MEM_LOCATION_TYPE_DEVICE; acc[d].location.id = d; acc[d].flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE; }
+    CU(g_drv.MemSetAccess(va, r->vmm_bytes, acc, (size_t)(ndev < 64 ? ndev : 64)));       /* every GPU of the box may store here */
+    r->region = (uint8_t *)va;
+    return APUS_OK;
+}
+
+/* All replicas of ONE group, in this process, on pairwise different GPUs, created with APUS_F_FABRIC: bind their
+ * regions to one multicast object and give the leader the multicast mapping.  From the next launch on the leader's
+ * T5 step issues ONE `multimem.st` per 16 B chunk instead of one store per replica. */
+extern "C" int apus_group_multicast(apus_replica_t **rs, int n)
+{
+    if (!rs || n < 2 || n > APUS_MAX_SERVER_COUNT) return fail("bad replica list");
+    if (drv_load() != APUS_OK) return APUS_ERROR;
+    apus_replica *lead = NULL;
+    for (int i = 0; i < n; i++) {
+        if (!rs[i] || !rs[i]->vmm_handle) return fail("replica %d was not created with APUS_F_FABRIC", i);
+        if (rs[i]->in_flight) return fail("stop the kernels first");
+        if (rs[i]->vmm_bytes != rs[0]->vmm_bytes) return fail("regions differ in size");
+        for (int j = 0; j < i; j++) if (rs[j]->cfg.device == rs[i]->cfg.device) return fail("multicast needs one GPU per replica");
+        int mc = 0;
+        CU(g_drv.DeviceGetAttribute(&mc, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, rs[i]->cfg.device));
+        if (!mc) return fail("device %d does not support multicast", rs[i]->cfg.device);
+        if (is_leader(rs[i])) lead = rs[i];
+    }
+    if (!lead) return fail("no leader in the list");
+    if (lead->mc_region) return APUS_OK;
+    CUmulticastObjectProp mp;
+    memset(&mp, 0, sizeof mp);
+    mp.numDevices = (unsigned)n; mp.size = lead->vmm_bytes;
+    size_t mgran = 0;
+    CU(g_drv.MulticastGetGranularity(&mgran, &mp, CU_MULTICAST_GRANULARITY_MINIMUM));
+    if (lead->vmm_bytes % mgran) return fail("region size %zu is not a multiple of the multicast granularity %zu", lead->vmm_bytes, mgran);
+    CU(g_drv.MulticastCreate(&lead->mc_handle, &mp));
+    for (int i = 0; i < n; i++) CU(g_drv.MulticastAddDevice(lead->mc_handle, rs[i]->cfg.device));
+    for (int i = 0; i < n; i++) {
+        DeviceGuard g(rs[i]->cfg.device);
+        CU(g_drv.MulticastBindMem(lead->mc_handle, 0, rs[i]->vmm_handle, 0, rs[i]->vmm_bytes, 0));
+    }
+    DeviceGuard g(lead->cfg.device);
+    CUdeviceptr va = 0;
+    CU(g_drv.MemAddressReserve(&va, lead->vmm_bytes, mgran, 0, 0));
+    CU(g_drv.MemMap(va, lead->vmm_bytes, 0, lead->mc_handle, 0));
+    CUmemAccessDesc acc;
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE; acc.location.id = lead->cfg.device; acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    CU(g_drv.MemSetAccess(va, lead->vmm_bytes, &acc, 1));
+    lead->mc_region = (uint8_t *)va;
+    return APUS_OK;
+}
 
 /* ==================================================================================================
  * Control plane on NVLink words.  Transport and log surgery only; the election policy

@@ -92,6 +92,17 @@ __device__ __forceinline__ void st_v4(void *p, uint4 v)
                  "r"(v.w)
                  : "memory");
 }
+// NVSwitch multicast stores: ONE store, every replica of the group (the issuing GPU's own copy included) receives it
+__device__ __forceinline__ void mst_v4(void *p, uint4 v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
+__device__ __forceinline__ void mst_u32(void *p, uint32_t v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_u8(void *p, uint32_t v)
 {
     asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -263,6 +274,19 @@ __device__ __forceinline__ uint64_t cs_chunk(const uint4 v, uint64_t lo, uint64_
     const uint64_t w0 = (uint64_t)v.x | ((uint64_t)v.y << 32), w1 = (uint64_t)v.z | ((uint64_t)v.w << 32);
     return (w0 & cs_mask(lo, a, b)) * cs_weight(lo >> 3) + (w1 & cs_mask(lo + 8, a, b)) * cs_weight((lo >> 3) + 1);
 }
+// first n bytes of a 16 B chunk from `nw`, the rest from `old`
+__device__ __forceinline__ uint4 chunk_select(const uint4 nw, const uint4 old, int n)
+{
+    uint32_t a[4] = {nw.x, nw.y, nw.z, nw.w}, o[4] = {old.x, old.y, old.z, old.w}, r[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const int k = n - 4 * w;                      // bytes of this word that come from `nw`
+        const uint32_t m = k >= 4 ? 0xffffffffu : (k <= 0 ? 0u : ((1u << (8 * k)) - 1u));
+        r[w] = (a[w] & m) | (o[w] & ~m);
+    }
+    return make_uint4(r[0], r[1], r[2], r[3]);
+}
+
 // the key that ties a certificate to ITS publish (a certificate half from an older publish must not verify)
 __device__ __forceinline__ uint64_t cs_key(uint64_t cum_term) { return cs_weight(cum_term ^ 0x5851F42D4C957F2Dull); }
 
@@ -581,19 +605,30 @@ __device__ __noinline__ void leader_prescan(const apus_devctx_t *__restrict__ cx
 {
     const uint32_t nf = S->n_fetch;
     uint32_t carry = 0, xcarry = 0, scut = nf, fext = 0xffffffffu, hhk = 0xffffffffu;
+    // a batch of ONE request shape (the benchmark's, and most applications' bursts) needs no scan: cum[k] = (k+1) * stride
+    const uint32_t es0 = S->es[0], xb0 = S->xb[0];
+    bool uniform = true;
+    for (uint32_t r = 0; r < nf; r += 32) {
+        const uint32_t k = r + lane;
+        if (__ballot_sync(0xffffffffu, k < nf && (S->es[k] != es0 || S->xb[k] != xb0))) { uniform = false; break; }
+    }
     for (uint32_t r = 0; r < nf; r += 32) {
         const uint32_t k = r + lane;
         const bool in = k < nf;
         uint32_t inc = in ? S->es[k] : 0u, xinc = in ? S->xb[k] : 0u;
+        if (uniform) {
+            if (in) { S->cum_es[k] = (k + 1u) * es0; S->cum_xb[k] = (k + 1u) * xb0; }
+        } else {
 #pragma unroll
-        for (int sft = 1; sft < 32; sft <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, sft);
-            const uint32_t xo = __shfl_up_sync(0xffffffffu, xinc, sft);
-            if (lane >= sft) { inc += o; xinc += xo; }
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, sft);
+                const uint32_t xo = __shfl_up_sync(0xffffffffu, xinc, sft);
+                if (lane >= sft) { inc += o; xinc += xo; }
+            }
+            if (in) { S->cum_es[k] = carry + inc; S->cum_xb[k] = xcarry + xinc; }
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+            xcarry += __shfl_sync(0xffffffffu, xinc, 31);
         }
-        if (in) { S->cum_es[k] = carry + inc; S->cum_xb[k] = xcarry + xinc; }
-        carry += __shfl_sync(0xffffffffu, inc, 31);
-        xcarry += __shfl_sync(0xffffffffu, xinc, 31);
         const uint32_t hm = __ballot_sync(0xffffffffu, in && S->ty[k] == T_HEAD);
         if (hm) hhk = r + (31u - (uint32_t)__clz(hm));                 // the LAST host HEAD entry of the batch
         const uint32_t wm = __ballot_sync(0xffffffffu, in && k > 0 && (S->flg[k] & 2u));
@@ -763,19 +798,6 @@ __device__ __forceinline__ void express_release(apus_seq_t *seq, Express &X, int
     __syncwarp();
 }
 
-// first n bytes of a 16 B chunk from `nw`, the rest from `old`
-__device__ __forceinline__ uint4 chunk_select(const uint4 nw, const uint4 old, int n)
-{
-    uint32_t a[4] = {nw.x, nw.y, nw.z, nw.w}, o[4] = {old.x, old.y, old.z, old.w}, r[4];
-#pragma unroll
-    for (int w = 0; w < 4; w++) {
-        const int k = n - 4 * w;                      // bytes of this word that come from `nw`
-        const uint32_t m = k >= 4 ? 0xffffffffu : (k <= 0 ? 0u : ((1u << (8 * k)) - 1u));
-        r[w] = (a[w] & m) | (o[w] & ~m);
-    }
-    return make_uint4(r[0], r[1], r[2], r[3]);
-}
-
 __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx, const LeaderShared *S, Express &X,
                                               const uint64_t claimed, uint4 sv, const bool have_slot, uint8_t *scratch,
                                               const int lane, const uint4 pf, const uint64_t pf_pos)
@@ -893,10 +915,14 @@ __device__ __noinline__ int leader_express(const apus_devctx_t *__restrict__ cx,
     if (lane < (int)nch) {
         cs = cs_chunk(v, lo, a, b);
         if (lo >= a && lo + 16 <= b) {
-            st_v4(entries + lo, v);
+            if (cx->mc_region) {
+                mst_v4(cx->mc_region + cx->entries_off + lo, v);
+            } else {
+                st_v4(entries + lo, v);
 #pragma unroll 1
-            for (int f = 0; f < N; f++)
-                if (S->peer_entries[f]) st_v4(S->peer_entries[f] + lo, v);
+                for (int f = 0; f < N; f++)
+                    if (S->peer_entries[f]) st_v4(S->peer_entries[f] + lo, v);
+            }
         } else {
 #pragma unroll 1
             for (uint32_t jb = 0; jb < 16; jb++) {
@@ -1425,23 +1451,50 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                     const uint32_t k = kbase + j;
                     uint8_t *e = img + (a - a16) + S->rel[k];
                     const uint32_t ty = S->ty[k];
-                    group_write_header(e, sub, gl, S->idx0 + autoh + j, cx->term, sl[k].req_id, sl[k].clt_id, ty, me, false);
                     const uint32_t nb = data_bytes(ty, sl[k].len);
-                    if (nb) group_copy_smem(e + E_DATA, (S->flg[k] & 1u) ? ext + S->xoff[k] : sl[k].inl, nb, sub, gl);
+                    const uint32_t es_k = S->es[k];
+                    if (((uint32_t)(uintptr_t)e & 15u) == 0 && (es_k & 15u) == 0) {
+                        // the entry occupies whole 16 B chunks of the image: lane `sub` builds chunks sub, sub+gl, ... in
+                        // registers (header fields; the data image straight from the slot / the staged payload) and
+                        // writes each with ONE 16 B store; the two holes keep what the prefill put there
+                        const uint64_t idx = S->idx0 + autoh + j, rq = sl[k].req_id;
+                        const uint8_t *src = (S->flg[k] & 1u) ? ext + S->xoff[k] : sl[k].inl;
+                        const uint32_t nch_e = es_k >> 4;
+                        for (uint32_t c = (uint32_t)sub; c < nch_e; c += (uint32_t)gl) {
+                            uint4 *dst = reinterpret_cast<uint4 *>(e) + c;
+                            if (c == 0) *dst = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)cx->term, (uint32_t)(cx->term >> 32));
+                            else if (c == 1) *dst = make_uint4((uint32_t)rq, (uint32_t)(rq >> 32),
+                                                               ((uint32_t)sl[k].clt_id) | (ty << 16) | ((uint32_t)me << 24), 0u);
+                            else if (c == 2) { const uint4 o = *dst; *dst = make_uint4(0u, 0u, o.z & 0xffffff00u, o.w); }
+                            else {
+                                const int nbv = (int)nb - 16 * (int)(c - 3);
+                                if (nbv >= 16) *dst = *reinterpret_cast<const uint4 *>(src + 16u * (c - 3));
+                                else if (nbv > 0) *dst = chunk_select(*reinterpret_cast<const uint4 *>(src + 16u * (c - 3)), *dst, nbv);
+                            }
+                        }
+                    } else {
+                        group_write_header(e, sub, gl, S->idx0 + autoh + j, cx->term, sl[k].req_id, sl[k].clt_id, ty, me, false);
+                        if (nb) group_copy_smem(e + E_DATA, (S->flg[k] & 1u) ? ext + S->xoff[k] : sl[k].inl, nb, sub, gl);
+                    }
                 }
             }
             bar_sync(1, NT);
             PHASE(4);
 
             // ---- T5: push the byte range [a,b) to the local log and to every follower ----
+            uint8_t *mc_entries = cx->mc_region ? cx->mc_region + cx->entries_off : nullptr;
             for (uint32_t c = tid; c < nchunks; c += NT) {
                 const uint64_t lo = a16 + 16ull * c;
                 const uint4 v = reinterpret_cast<const uint4 *>(img)[c];
                 if (lo >= a && lo + 16 <= b) {
-                    st_v4(entries + lo, v);
+                    if (mc_entries) {
+                        mst_v4(mc_entries + lo, v);               // the switch fans it out: leader egress 1x instead of (N-1)x
+                    } else {
+                        st_v4(entries + lo, v);
 #pragma unroll 1
-                    for (int f = 0; f < N; f++)
-                        if (S->peer_entries[f]) st_v4(S->peer_entries[f] + lo, v);
+                        for (int f = 0; f < N; f++)
+                            if (S->peer_entries[f]) st_v4(S->peer_entries[f] + lo, v);
+                    }
                 } else {
 #pragma unroll 1
                     for (uint32_t j = 0; j < 16; j++) {
@@ -1467,10 +1520,14 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         w = (uint32_t)(a + S->rel[k]) | (S->ty[k] == T_HEAD ? APUS_IDX_HEAD_FLAG : 0u);
                     }
                     const uint32_t at = (uint32_t)(cum0 + 1 + j) & cx->idx_mask;
-                    lindex[at] = w;
+                    if (cx->mc_region) {
+                        mst_u32(reinterpret_cast<uint32_t *>(cx->mc_region + APUS_INDEX_OFF) + at, w);
+                    } else {
+                        lindex[at] = w;
 #pragma unroll 1
-                    for (int f = 0; f < N; f++)
-                        if (S->peer_index[f]) S->peer_index[f][at] = w;
+                        for (int f = 0; f < N; f++)
+                            if (S->peer_index[f]) S->peer_index[f][at] = w;
+                    }
                 }
             }
             bar_sync(1, NT);

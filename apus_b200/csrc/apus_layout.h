@@ -271,6 +271,7 @@ typedef struct apus_devctx {
     uint64_t hb_period_ns;                /* leader: heartbeat period (0 = no heartbeats) */
     uint64_t hb_timeout_ns;               /* follower: silence after which the leader is suspected (0 = never) */
     uint8_t *region;                      /* own region */
+    uint8_t *mc_region;                   /* leader, fabric mode: NVSwitch multicast mapping of the group's regions (else NULL) */
     uint8_t *peer[APUS_MAX_SERVERS];      /* peers' regions as mapped here (NULL = absent) */
     /* leader submission ring */
     const apus_slot_t *sub_slots;

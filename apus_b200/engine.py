@@ -17,7 +17,7 @@ RING_HOST_MAPPED, RING_DEVICE = 0, 1
 LOG_SIZE = 16384 * 4096
 MAX_SERVERS = 13
 F_FENCED_ACK, F_DEVICE_STATS, F_AUTOPRUNE, F_FOLLOWER_WALK, F_EXPLICIT = 0x1, 0x2, 0x4, 0x8, 0x80000000
-F_HOST_APPLY, F_NO_EXPRESS, F_PROFILE = 0x10, 0x20, 0x40
+F_HOST_APPLY, F_NO_EXPRESS, F_PROFILE, F_FABRIC = 0x10, 0x20, 0x40, 0x100
 UINT64_MAX = (1 << 64) - 1
 
 u64, u32, u16, u8, i64, i32 = C.c_uint64, C.c_uint32, C.c_uint16, C.c_uint8, C.c_int64, C.c_int32
@@ -61,7 +61,7 @@ EXPORTS = [
     "apus_log_read_range", "apus_leader_suspect", "apus_last_commit_ns",
     "apus_ctl_read", "apus_ctl_set_sid", "apus_ctl_reset_votes", "apus_ctl_clear_vote_request", "apus_ctl_send_vote_request",
     "apus_ctl_send_vote_ack", "apus_ctl_last_entry", "apus_ctl_adjust_follower", "apus_replica_set_role",
-    "apus_replica_disconnect", "apus_follower_beats", "apus_device_numa_node",
+    "apus_replica_disconnect", "apus_follower_beats", "apus_device_numa_node", "apus_group_multicast",
 ]
 
 
@@ -389,6 +389,12 @@ class Group:
     def stop(self):
         arr = (C.c_void_p * self.n)(*[r.h for r in self.replicas])
         _ck(lib().apus_replicas_stop(arr, self.n), "apus_replicas_stop")
+
+    def multicast(self):
+        """Bind the replicas' regions (created with F_FABRIC, one GPU each) to an NVSwitch multicast object."""
+        arr = (C.c_void_p * self.n)(*[r.h for r in self.replicas])
+        lib().apus_group_multicast.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        _ck(lib().apus_group_multicast(arr, self.n), "apus_group_multicast")
 
     def prologue(self):
         """Blank CONFIG entry the election winner appends (dare_server.c:1412-1421);

@@ -840,17 +840,19 @@ def run_failover(args):
     out = {"metric": "leader failover: kill -> new leader serving", "unit": "ms", "higher_is_better": False, "n_gpus": min(nd, n),
            "data": "synthetic", "dtype": "u8", "config": {"workload": f"{n} replica processes (unmodified proxy.c on the engine), closed-loop "
                                                                       f"{args.payload} B requests, leader killed with SIGKILL after 1 s",
-                                                          "replicas": n, "placement": "one GPU per replica" if nd >= n else f"{nd} GPU(s)"}}
-    for name, kw in (("gpu_native_timeouts", dict(hb_us=200, hb_timeout_us=4000, elec_us="2000,6000")),
-                     ("reference_timeouts", dict(hb_us=10000, hb_timeout_us=100000, elec_us="100000,300000"))):
-        trials = []
-        for _ in range(args.failover_trials):
-            r = FD.run(n=n, plen=args.payload, spread=nd > 1, ndev=nd, kill_after_s=1.0, **kw)
-            trials.append({"new_leader": r["new_leader"], "term": r["term"], "kill_to_leader_line_ms": r["recovery_ms_kill_to_leader_line"],
-                           "kill_to_first_commit_ms": r["recovery_ms_kill_to_first_commit"], "requests_before_kill": r["requests_before_kill"]})
-        out[name] = {"hb_period_us": kw["hb_us"], "hb_timeout_us": kw["hb_timeout_us"], "election_timeout_us": kw["elec_us"], "trials": trials,
-                     "median_kill_to_first_commit_ms": statistics.median(t["kill_to_first_commit_ms"] for t in trials)}
-    out["value"] = out["gpu_native_timeouts"]["median_kill_to_first_commit_ms"]
+                                                          "replicas": n, "placement": "all replica processes on GPU 0 (time-sliced contexts: the latencies are "
+                                                                                      "dominated by the driver's time slices, see tools/failover_drill.py)"}}
+    trials = []
+    for _ in range(args.failover_trials):
+        r = FD.run(n=n, plen=args.payload, spread=False, ndev=nd, kill_after_s=1.0)
+        trials.append({"new_leader": r["new_leader"], "term": r["term"], "kill_to_leader_line_ms": r["recovery_ms_kill_to_leader_line"],
+                       "kill_to_first_commit_ms": r["recovery_ms_kill_to_first_commit"], "requests_before_kill": r["requests_before_kill"],
+                       "hb_period_us": r["hb_period_us"], "hb_timeout_us": r["hb_timeout_us"], "election_timeout_us": r["elec_timeout_us"]})
+    out["trials"] = trials
+    out["value"] = statistics.median(t["kill_to_first_commit_ms"] for t in trials)
+    out["note"] = ("replica processes share one GPU (their contexts are time-sliced), so the failure detector runs with a 400 ms heartbeat "
+                   "timeout and the reference's 100-300 ms election timeouts; the reference's own stack needs ~350 ms with its shipped "
+                   "timeouts (profiles/r1_refstack_failover_buildbox.txt)")
     print(json.dumps(out), flush=True)
 
 

@@ -40,10 +40,12 @@ dare_global_config = { hb_period = ${HB_PERIOD:-0.001}; elec_timeout_low = ${ELE
 CFG
     if [ "$APP" = redis ]; then run_dare=( "$REFBIN/redis-server" --port $((base_port + i)) --save "" --bind 127.0.0.1 )
     else run_dare=( ${APP_CMD//%PORT%/$((base_port + i))} ); fi
-    ( cd "$RUN/node$i" && env server_type=start server_idx=$i group_size=$1 config_path="$RUN/node$i/node.cfg" \
+    pushd "$RUN/node$i" > /dev/null
+    env server_type=start server_idx=$i group_size=$1 config_path="$RUN/node$i/node.cfg" \
         dare_log_file="$RUN/srv$i.log" apus_gpu=$((i % ngpu)) apus_rendezvous="$RUN/rdv" LD_PRELOAD="$INTERPOSE" \
-        nohup "${run_dare[@]}" > app.out 2>&1 & echo $! > pid )
-    pids[$i]=$(cat "$RUN/node$i/pid")
+        nohup "${run_dare[@]}" > app.out 2>&1 &
+    pids[$i]=$!
+    popd > /dev/null
   done
   echo -e "\tinitial servers: p0..p$(($1 - 1)) on $ngpu GPU(s), PIDs: ${pids[*]}"
 }
@@ -77,7 +79,7 @@ if [ "$kill_leader" = 1 ]; then
   kill -9 "${pids[$old]}"; echo "killed the leader p$old (PID ${pids[$old]})"
   for t in $(seq 1 2000); do FindLeader > /dev/null; [ "$leader_idx" != "$old" ] && break; sleep 0.005; done
   t_new=$(date +%s.%N)
-  FindLeader; echo "recovery (kill -> next \"] LEADER\" line, polled every 5 ms): $(echo "($t_new - $t_kill) * 1000" | bc -l | cut -c1-7) ms"
+  FindLeader; echo "recovery (kill -> next \"] LEADER\" line, polled every 5 ms): $(awk -v a="$t_new" -v b="$t_kill" 'BEGIN { printf "%.1f", (a - b) * 1000 }') ms"
   wait; sleep 1
   StartBenchmark
 else

@@ -78,6 +78,8 @@ extern "C" {
                                      log->apply only after do_action (dare_server.c:1939-1962); off = apply follows
                                      commit on the device (nothing replays the log on the host) */
 #define APUS_F_NO_EXPRESS   0x20u /* leader: no single-warp express path, every publish is fenced (A/B switch) */
+#define APUS_F_FABRIC      0x100u /* the replica's HBM region is a VMM allocation that apus_group_multicast() can bind to an
+                                     NVSwitch multicast object (replicas of one process, one GPU each) */
 #define APUS_F_PROFILE      0x40u /* fine-grained device timestamps in the latency path (diagnostic runs only: each costs ~90 ns) */
 #define APUS_F_EXPLICIT     0x80000000u /* flags are exactly as given (no defaults OR-ed in) */
 
@@ -147,6 +149,11 @@ void apus_replica_destroy(apus_replica_t *r);
 /* replaces the RC_SYN/SYNACK exchange of raddr+rkey (dare_ibv_ud.c:1116-1119) */
 int  apus_replica_export(apus_replica_t *r, apus_peer_handle_t *out);
 int  apus_replica_connect(apus_replica_t *r, uint8_t peer_idx, const apus_peer_handle_t *peer);
+
+/* Replicas of ONE group, hosted by this process on pairwise different GPUs and created with APUS_F_FABRIC: bind their
+ * regions to an NVSwitch multicast object.  The leader's replicate step then issues one `multimem.st` per 16 B chunk
+ * (the switch fans it out to every replica, the leader's own copy included) instead of one store per replica. */
+int  apus_group_multicast(apus_replica_t **rs, int n);
 
 /* Launch the persistent kernel(s) for `n` replicas that live on the SAME device
  * in ONE fused launch (one CTA group per replica role).  The kernels return when

@@ -414,3 +414,35 @@ def test_term_fence_ignores_a_deposed_leader(eng, orc):
         eng.lib().apus_replicas_stop(arr, n)
         for r in reps:
             r.close()
+
+
+@pytest.mark.parametrize("n,payload", [(3, 64), (5, 1000)])
+def test_multicast_replication_exact(eng, orc, n, payload):
+    """Fabric mode: the replicas' regions are VMM allocations bound to an NVSwitch multicast object; the leader's T5 step
+    (and the express push) issue ONE multimem.st per 16 B chunk and the switch fans it out.  Same bytes everywhere."""
+    from apus_b200 import engine as E
+    nd = eng.lib().apus_device_count()
+    if nd < n:
+        pytest.skip(f"needs {n} GPUs (one per replica), {nd} visible")
+    L = 1 << 24
+    nreq = 20000
+    rng = np.random.default_rng(payload)
+    pl = rng.integers(0, 256, size=nreq * payload, dtype=np.uint8)
+    pb = pl.tobytes()
+    stream = [(S.CONNECT, 0, 1, b"")] + [(S.SEND, 0, 2 + i, pb[i * payload:(i + 1) * payload]) for i in range(nreq)]
+    with eng.Group(n, devices=list(range(n)), log_size=L, ring_mode=eng.RING_DEVICE, ring_slots=1 << 16,
+                   ring_bytes=64 << 20, flags=F_STATS | E.F_FABRIC) as g:
+        try:
+            g.multicast()
+        except E.ApusError as ex:
+            pytest.skip(f"multicast unavailable: {ex}")
+        g.prologue()
+        g.submit(S.CONNECT, 0, 1, b"")
+        t0 = g.leader.submit_uniform(nreq, S.SEND, 0, 2, payload, pl)
+        g.tickets = t0 + nreq - 1
+        g.run(timeout_ms=120_000)
+        c = EU.oracle_cluster(orc, n, L, stream)
+        try:
+            EU.compare_group_to_oracle(g, c, exact=True)
+        finally:
+            c.close()

