@@ -518,6 +518,7 @@ static int elect(void)
             if (i != g_idx && i != dead && read_handle(i, &h) == 0) apus_replica_connect(g_rep, (uint8_t)i, &h);
     }
     int candidate = 0;
+    unsigned rounds = 0;
     /* the first round starts at once (hb_receive_cb -> start_election); a split vote is retried after a random timeout */
     uint64_t deadline = now_us();
     uint64_t voted_deadline = 0;
@@ -546,7 +547,7 @@ static int elect(void)
             if (votes >= (unsigned)g_n / 2 + 1) {
                 /* won.  Give the remaining live servers a moment to answer as well: whoever has not voted by then is
                  * treated as failed (check_failure_count, dare_server.c:1189-1228) */
-                const uint64_t grace = now_us() + 5000;
+                const uint64_t grace = now_us() + (cfg_elec_low > 5000 ? cfg_elec_low : 5000);
                 while (now_us() < grace && votes < g_n - 1u) {
                     if (apus_ctl_read(g_rep, &v) != APUS_OK) break;
                     votes = 1; voters = 0;
@@ -604,6 +605,7 @@ static int elect(void)
         }
         /* (d) nobody leads, nobody I voted for made it: stand myself (start_election) */
         if (now_us() >= deadline) {
+            if (++rounds > 200) { LOGT("no leader after %u election rounds: giving up\n", rounds); return 1; }
             sid = SID_MAKE(SID_TERM(sid) + 1, 0, g_idx);
             apus_ctl_set_sid(g_rep, sid);
             apus_ctl_reset_votes(g_rep);
