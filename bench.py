@@ -133,13 +133,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def ncu_traffic(n, payload, batch):
+def ncu_traffic(n, payload, batch, ctas):
     """dram__bytes_read.sum + dram__bytes_write.sum of the replica kernel per launch, from the committed
-    `ncu --set full` capture (profiles/r1_ncu_v5.json); only valid for the configuration it was taken on."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_v5.json")
+    `ncu --set full` capture (profiles/r2_ncu.json); only valid for the configuration it was taken on."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu.json")
     try:
         d = json.load(open(p))
-        if n == 5 and payload == 64 and batch == 65536:
+        c = d["config"]
+        if (n, payload, batch, ctas) == (c["replicas"], c["payload_bytes"], c["batch"], c["leader_ctas"]):
             return float(d["traffic_bytes_per_launch"])
     except Exception:
         pass
@@ -629,9 +630,10 @@ def run_ours(args):
         "parity": parity if parity is None else dict(parity, live_log=live),
         "roofline": {"bound": bound, "achieved": round(ach, 3), "peak": peak, "unit": "GB/s",
                      "frac": round(ach / peak, 6),
-                     "traffic": (ncu_traffic(n, payload, batch) if world == 1 and not args.spread else None),
-                     "traffic_note": "bytes per launch (dram read+write) from the committed ncu capture of this configuration, when one "
-                                     f"exists; algorithmic bytes per launch = {alg_bytes_per_op * batch}",
+                     "traffic": (ncu_traffic(n, payload, batch, args.leader_ctas) if world == 1 and not args.spread else None),
+                     "traffic_note": "bytes per launch (dram read+write), profiles/r2_ncu.json (ncu --set full of this configuration: above "
+                                     "the algorithmic bytes because the leader's own copy, the slot reads and the hole-preserving "
+                                     f"prefill read reach DRAM once the rings outgrow the L2); algorithmic bytes per launch = {alg_bytes_per_op * batch}",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_op": alg_bytes_per_op,
                      "kernel": "apus_replica_kernel (one fused launch per step: leader CTAs + follower CTAs)",
