@@ -1141,6 +1141,7 @@ static int fabric_alloc_region(apus_replica *r)
     ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
     ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
     ap.location.id = r->cfg.device;
+    ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;     /* (as probed; also what one process per replica will export) */
     size_t gran = 0;
     CU(g_drv.MemGetAllocationGranularity(&gran, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
     if (gran < (2u << 20)) gran = 2u << 20;
@@ -1178,7 +1179,7 @@ extern "C" int apus_group_multicast(apus_replica_t **rs, int n)
     if (lead->mc_region) return APUS_OK;
     CUmulticastObjectProp mp;
     memset(&mp, 0, sizeof mp);
-    mp.numDevices = (unsigned)n; mp.size = lead->vmm_bytes;
+    mp.numDevices = (unsigned)n; mp.size = lead->vmm_bytes; mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
     size_t mgran = 0;
     CU(g_drv.MulticastGetGranularity(&mgran, &mp, CU_MULTICAST_GRANULARITY_MINIMUM));
     if (lead->vmm_bytes % mgran) return fail("region size %zu is not a multiple of the multicast granularity %zu", lead->vmm_bytes, mgran);

@@ -416,7 +416,7 @@ def test_term_fence_ignores_a_deposed_leader(eng, orc):
             r.close()
 
 
-@pytest.mark.parametrize("n,payload", [(3, 64), (5, 1000)])
+@pytest.mark.parametrize("n,payload", [(2, 64), (2, 1000), (3, 64), (5, 1000)])
 def test_multicast_replication_exact(eng, orc, n, payload):
     """Fabric mode: the replicas' regions are VMM allocations bound to an NVSwitch multicast object; the leader's T5 step
     (and the express push) issue ONE multimem.st per 16 B chunk and the switch fans it out.  Same bytes everywhere."""
