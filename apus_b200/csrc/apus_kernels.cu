@@ -1272,8 +1272,7 @@ __device__ void leader_main(const apus_devctx_t *__restrict__ cx, const uint32_t
                         const bool wrapped = (tf & APUS_REC_WRAPPED) != 0, prevh = (tf & APUS_REC_PREV_HEAD) != 0;
                         const uint64_t tail = tf & ~(APUS_REC_WRAPPED | APUS_REC_PREV_HEAD);
                         // ---- fast path ----
-                        // a host control plane may also move the head (apus_set_head): take the newer of the two
-                                            S->st_head = headv;
+                        S->st_head = headv;
                         const uint64_t pos0 = (end == L) ? 0 : end;
                         const uint64_t used = (end == L) ? 0 : ring_dist(headv, end, L);
                         const uint64_t total = S->cum_es[nf - 1];

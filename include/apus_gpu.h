@@ -267,7 +267,9 @@ int  apus_follower_beats(apus_replica_t *leader, uint64_t out[APUS_MAX_SERVER_CO
 /* stop storing into a peer that is gone (dare_ib_disconnect_server, dare_server.c:1200) */
 int  apus_replica_disconnect(apus_replica_t *r, uint8_t peer_idx);
 
-/* control plane hooks used by pruning (log_pruning, dare_server.c:1996-2067) */
+/* control plane hooks used by pruning (log_pruning, dare_server.c:1996-2067).  apus_set_head writes the header word a
+ * LAUNCH starts from; while kernels are resident the head moves the way the reference moves it: with the HEAD entry that
+ * carries the new offset (submit APUS_HEAD with the 8-byte offset; the leader adopts it when it places the entry). */
 int  apus_set_head(apus_replica_t *r, uint64_t head);
 int  apus_remote_apply_offsets(apus_replica_t *leader, uint64_t out[APUS_MAX_SERVER_COUNT]);
 

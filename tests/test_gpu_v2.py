@@ -424,7 +424,7 @@ def test_multicast_replication_exact(eng, orc, n, payload):
     nd = eng.lib().apus_device_count()
     if nd < n:
         pytest.skip(f"needs {n} GPUs (one per replica), {nd} visible")
-    L = 1 << 24
+    L = 1 << 26                           # no pruning flag here: the whole stream (21 MB at 1000 B) has to fit
     nreq = 20000
     rng = np.random.default_rng(payload)
     pl = rng.integers(0, 256, size=nreq * payload, dtype=np.uint8)
