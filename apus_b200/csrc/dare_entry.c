@@ -525,9 +525,13 @@ static int elect(void)
     const uint64_t t_start = now_us();
     while (!g_terminate) {
         if (apus_ctl_read(g_rep, &v) != APUS_OK) { LOGT("%s\n", apus_last_error()); return 1; }
-        /* (a) somebody won and has adjusted my log: follow */
-        if (SID_L(v.leader_sid) && SID_TERM(v.leader_sid) >= SID_TERM(sid) && SID_IDX(v.leader_sid) != g_idx &&
-            SID_TERM(v.leader_sid) > g_term) {
+        /* (a) somebody won and has adjusted my log: follow.  An announcement below the term I stand in myself is normally
+         * ignored -- but a candidacy that timed out without winning gives way to a leader that is newer than the one I lost
+         * (`> g_term`): the servers that already follow it no longer answer vote requests (their pumps do not poll them, unlike
+         * dare_server.c:1119), so insisting could neither win nor end.  A self-vote helps nobody else win, giving it up is safe;
+         * a stale announcement costs one heartbeat timeout and is not accepted twice (g_term moves up to it). */
+        const int announced = SID_L(v.leader_sid) && SID_IDX(v.leader_sid) != g_idx && SID_TERM(v.leader_sid) > g_term;
+        if (announced && (SID_TERM(v.leader_sid) >= SID_TERM(sid) || (candidate && now_us() >= deadline))) {
             g_term = SID_TERM(v.leader_sid); g_leader_idx = SID_IDX(v.leader_sid);
             apus_ctl_set_sid(g_rep, v.leader_sid);
             if (apus_replica_set_role(g_rep, g_leader_idx, g_term) != APUS_OK || launch_self() != APUS_OK) {
@@ -600,7 +604,10 @@ static int elect(void)
             LOGT("[T%llu] Vote for p%u\n", (unsigned long long)SID_TERM(sid), (unsigned)SID_IDX(sid));
             apus_ctl_send_vote_ack(g_rep, SID_IDX(sid), commit);
             apus_ctl_clear_vote_request(g_rep, (uint8_t)best_i);
-            voted_deadline = now_us() + (uint64_t)(10.0 * cfg_hb_period * 1e6);   /* hb_timeout() */
+            /* hb_timeout(): the same patience the failure detector has (an environment override included) -- the winner's
+             * take-over (grace for late voters, role change, log adjustment) has to fit into it, or this voter stands
+             * against a leader that is about to announce itself */
+            voted_deadline = now_us() + (g_env_hbto_us > 0 ? (uint64_t)g_env_hbto_us : (uint64_t)(10.0 * cfg_hb_period * 1e6));
             deadline = voted_deadline + random_election_timeout_us();
         }
         /* (d) nobody leads, nobody I voted for made it: stand myself (start_election) */

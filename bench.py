@@ -204,26 +204,57 @@ def host_cores():
 
 
 REFSTACK_CONNS = 16         # BASELINE.json configs[2]: 16 concurrent clients
+TRANSPORT_TEXT = {"shm": "shm transport: the log is a shared mapping, an RDMA WRITE is a memcpy -- no wire latency, no system call",
+                  "process_vm": "process_vm_writev transport: one or two system calls per RDMA operation, no wire latency"}
 
 
-def refstack_leg(n, payload, nreq, steps, timeout=600):
+def refstack_leg(n, payload, nreq, steps, timeout=600, transport=None):
     """The reference's OWN software stack -- its unmodified election / replication / commit code (src/dare/*.c) and
     proxy.c, built by oracle/build_refapp.sh into oracle/_ref/libref_stack.so -- as n replica processes on this
-    box's host cores, with oracle/verbs_shim standing in for the NIC (process_vm_writev, no wire latency), driven by
-    application threads through proxy_on_accept/read/close.  Returns (per-step dicts, cores, threads) or None when
-    the stack cannot run here (library absent, or the box forbids process_vm_writev)."""
+    box's host cores, with oracle/verbs_shim standing in for the NIC (no wire latency; transport None: one or two
+    process_vm_* system calls per RDMA operation, "shm": log writes are memcpys into a mapping the replicas share -- the
+    zero-latency bound BASELINE.md s2 planned), driven by application threads through proxy_on_accept/read/close.
+    Returns (per-step dicts, cores, threads, how the leader's RDMA operations travelled) or None when the stack cannot
+    run here (library absent, or the box forbids process_vm_writev)."""
     import refstack as R
     if not R.available() or n < 2:        # a group of one never holds an election in the reference (it waits for joins)
         return None
+    # The replicas are n worker processes that each load the reference stack; this process maps the same library too, so
+    # that whoever records the native libraries of the bench process sees which build of the reference was timed.
+    import ctypes
+    ctypes.CDLL(R.STACK)
     cores = host_cores()
     threads = max(1, min(REFSTACK_CONNS, cores - n))
     try:
-        rr = R.run(n, REFSTACK_CONNS, nreq, payload, threads=threads, steps=steps, images=False, timeout=timeout)
+        rr = R.run(n, REFSTACK_CONNS, nreq, payload, threads=threads, steps=steps, images=False, timeout=timeout,
+                   transport=transport)
     except Exception as e:                                   # noqa: BLE001 - reported, and the caller falls back
-        sys.stderr.write(f"[bench] reference stack could not run ({type(e).__name__}: {str(e)[:300]}); "
-                         f"falling back to the log-code-only baseline\n")
+        sys.stderr.write(f"[bench] reference stack ({transport or 'process_vm'} transport) could not run "
+                         f"({type(e).__name__}: {str(e)[:300]})\n")
         return None
-    return rr["results"][rr["leader"]]["steps"], n + threads, threads
+    lead = rr["results"][rr["leader"]]
+    return lead["steps"], n + threads, threads, lead.get("rdma_ops")
+
+
+def refstack_both(n, payload, nreq, steps, first):
+    """The reference stack on both shim transports.  Returns (primary leg, {transport: summary}) -- primary = the shm
+    transport when the leader's log writes really travelled as memcpys, else process_vm; None when neither ran."""
+    legs, summary = {}, {}
+    for tr in ("shm", None):
+        leg = refstack_leg(n, payload, nreq, steps, transport=tr)
+        name = tr or "process_vm"
+        if leg is None:
+            summary[name] = None
+            continue
+        st, cores, threads, ops = leg
+        timed = st[first:]
+        summary[name] = {"ops_per_s": round(sum(x["requests"] for x in timed) / sum(x["seconds"] for x in timed), 1),
+                         "p50_us": round(statistics.median(x["p50_us"] for x in timed), 1),
+                         "p99_us": round(max(x["p99_us"] for x in timed), 1), "leader_rdma_ops": ops}
+        legs[name] = leg
+    shm_real = "shm" in legs and (legs["shm"][3] or {}).get("memcpy", 0) > 0
+    primary = "shm" if shm_real else ("process_vm" if "process_vm" in legs else ("shm" if "shm" in legs else None))
+    return (legs[primary] if primary else None), primary, summary
 
 
 def refstack_nreq(payload, steps_total):
@@ -238,19 +269,20 @@ def cpu_baseline(n, payload, batch, budget_s=10.0):
     what its log code alone could do, the dare_log.h append/replicate/commit loop on threads with a memcpy transport."""
     loop = log_code_baseline(n, payload, batch, budget_s=min(budget_s, 5.0))
     nreq = refstack_nreq(payload, 4)
-    leg = refstack_leg(n, payload, nreq, steps=4)
+    leg, primary, transports = refstack_both(n, payload, nreq, 4, first=1)
     if leg is None:
         return loop
-    steps, cores, threads = leg
+    steps, cores, threads, _ = leg
     timed = steps[1:]
     ops = sum(s["requests"] for s in timed) / sum(s["seconds"] for s in timed)
     return {"value": round(ops, 1), "unit": "ops/s", "cores": cores, "kind": "reference",
             "sample": f"the reference's unmodified stack (src/dare/*.c, proxy.c; -O0 as it builds) as {n} replica "
                       f"processes + {threads} application threads on {host_cores()} host cores, {REFSTACK_CONNS} "
-                      f"connections, closed loop, verbs shim NIC (process_vm_writev: no wire latency), "
+                      f"connections, closed loop, verbs shim NIC ({TRANSPORT_TEXT[primary]}), "
                       f"{len(timed)} x {nreq} requests of {payload} B after one warm-up pass",
             "p50_us": round(statistics.median(s["p50_us"] for s in timed), 1),
             "p99_us": round(max(s["p99_us"] for s in timed), 1),
+            "shim_transport": primary, "shim_transports": transports,
             "log_code_only": loop}
 
 
@@ -261,9 +293,9 @@ def run_reference(args):
     n, payload = args.replicas, args.payload
     total = args.steps + args.warmup
     nreq = refstack_nreq(payload, total)
-    leg = refstack_leg(n, payload, nreq, steps=total)
+    leg, primary, transports = refstack_both(n, payload, nreq, total, first=args.warmup)
     if leg is not None:
-        steps, cores, threads = leg
+        steps, cores, threads, _ = leg
         timed = steps[args.warmup:]
         t = sum(s["seconds"] for s in timed)
         value = sum(s["requests"] for s in timed) / t
@@ -271,12 +303,13 @@ def run_reference(args):
         workload = (f"{n} replicas, {payload} B SEND requests, {nreq} requests per step over {REFSTACK_CONNS} connections; "
                     f"the reference's unmodified software stack (src/dare/*.c election/replication/commit, proxy.c, "
                     f"libev, BerkeleyDB) as {n} processes + {threads} application threads on the host cores, "
-                    f"verbs shim NIC (process_vm_writev, no wire latency)")
+                    f"verbs shim NIC ({TRANSPORT_TEXT[primary]})")
         sample = (f"{len(timed)} timed steps x {nreq} requests after {args.warmup} warm-up steps, closed loop, "
                   f"{REFSTACK_CONNS} connections on {threads} application threads")
         extra = {"latency_us": {"p50": round(statistics.median(s["p50_us"] for s in timed), 1),
                                 "p99": round(max(s["p99_us"] for s in timed), 1),
-                                "clock": "host, around proxy_on_read (returns at commit)"}}
+                                "clock": "host, around proxy_on_read (returns at commit)"},
+                 "shim_transport": primary, "shim_transports": transports}
     else:
         oracle, kind = cpu_library()
         nreq = cpu_nreq(payload, default_batch(args))

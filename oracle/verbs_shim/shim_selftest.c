@@ -81,7 +81,7 @@ int main(void)
     struct ibv_context *ctx = ibv_open_device(dl[0]);
     struct ibv_port_attr pa; CHECK(ibv_query_port(ctx, 1, &pa) == 0 && pa.lid == me && pa.state == IBV_PORT_ACTIVE);
     struct ibv_pd *pd = ibv_alloc_pd(ctx);
-    static uint8_t region[4096] __attribute__((aligned(64)));
+    static uint8_t region[8192] __attribute__((aligned(4096)));   /* whole pages of its own: the shm transport re-backs them */
     static uint8_t local[4096];
     struct ibv_mr *mr = ibv_reg_mr(pd, region, sizeof region, IBV_ACCESS_REMOTE_WRITE | IBV_ACCESS_REMOTE_READ | IBV_ACCESS_LOCAL_WRITE);
     struct ibv_mr *lmr = ibv_reg_mr(pd, local, sizeof local, IBV_ACCESS_LOCAL_WRITE);
@@ -138,7 +138,7 @@ int main(void)
         CHECK(memcmp(local, local + 1024, 64) == 0);
         barrier();                                                                   /* A */
         /* 2: out of the registered range, wrong rkey */
-        CHECK(rdma(qp[0], lmr, local, 64, IBV_WR_RDMA_WRITE, peer.addr + 4090, peer.rkey, 0) == 0);
+        CHECK(rdma(qp[0], lmr, local, 64, IBV_WR_RDMA_WRITE, peer.addr + 8186, peer.rkey, 0) == 0);
         CHECK(poll1(cq, &wc) == 1 && wc.status == IBV_WC_REM_ACCESS_ERR);         /* errors complete even when unsignalled */
         struct ibv_qp_attr qa; struct ibv_qp_init_attr qi;
         CHECK(ibv_query_qp(qp[0], &qa, IBV_QP_STATE, &qi) == 0 && qa.qp_state == IBV_QPS_ERR);

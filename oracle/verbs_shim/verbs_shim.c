@@ -23,10 +23,20 @@
  *
  * Latency of the emulated wire: one or two system calls (about a microsecond); there is no NIC, no retransmission
  * and no loss.  That makes the timing an UPPER bound on what the reference's software path can do.
+ *
+ *   APUS_SHIM_TRANSPORT=shm   the zero-latency variant BASELINE.md s2 planned: the published QP / MR record lives in a
+ *                    memfd every peer maps, and a memory region of 1 MiB or more (the log) is re-backed IN PLACE by a
+ *                    memfd (same virtual address, contents kept) that the peers map too -- an RDMA WRITE / READ into it
+ *                    is a memcpy + store fence, the responder-QP check is a load; no system call on the replicate path.
+ *                    Smaller regions (control data: heartbeats, votes) keep the process_vm path, which is also what
+ *                    notices a dead peer (ESRCH); for mapped regions the peer's pid is probed every 64 operations.
  */
 #define _GNU_SOURCE
 #include <dirent.h>
+#include <errno.h>
 #include <fcntl.h>
+#include <signal.h>
+#include <sys/mman.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -47,9 +57,13 @@
 
 /* what a peer may read about this process (process_vm_readv) */
 typedef struct { uint32_t qpn, type, state, dest_qpn, rq_psn, sq_psn; } pub_qp_t;
-typedef struct { uint32_t rkey, access; uint64_t addr, len; } pub_mr_t;
+typedef struct { uint32_t rkey, access; uint64_t addr, len; int32_t shm_fd; uint32_t shm_gen; uint64_t shm_base, shm_len; } pub_mr_t;
 typedef struct { pub_qp_t qp[SHIM_MAX_QP]; pub_mr_t mr[SHIM_MAX_MR]; } pub_t;
-static pub_t g_pub __attribute__((aligned(4096)));
+static pub_t g_pub_static __attribute__((aligned(4096)));
+static pub_t *g_pubp = &g_pub_static;        /* shm transport: a memfd mapping the peers share */
+#define g_pub (*g_pubp)
+static size_t g_shm_min = 1u << 20;          /* regions this large are re-backed by a memfd the peers map (APUS_SHIM_SHM_MIN) */
+#define SHIM_MAX_SEG 8
 
 typedef struct { struct ibv_wc *ring; int cap, head, tail; struct ibv_qp *ud_recv_qp; } shim_cq_t;
 typedef struct { uint64_t wr_id; uint64_t addr; uint32_t len; } shim_rwr_t;
@@ -61,7 +75,13 @@ typedef struct {
     shim_rwr_t *rq; int rq_cap, rq_head, rq_tail;
 } shim_qp_t;
 
-typedef struct { int known; pid_t pid; uint64_t pub_addr; pub_mr_t mr_cache[64]; } peer_t;
+typedef struct { uint32_t rkey, gen; int32_t fd; uint8_t *map; uint64_t base, len; } peer_seg_t;
+typedef struct {
+    int known; pid_t pid; uint64_t pub_addr; pub_mr_t mr_cache[64];
+    int pub_fd; pub_t *pub_map;              /* shm transport: the peer's public record, mapped */
+    peer_seg_t seg[SHIM_MAX_SEG];            /* ... and its large regions */
+    uint32_t ops;
+} peer_t;
 
 static struct ibv_device g_dev = { "apus_shim0" };
 static struct ibv_device *g_dev_list[2] = { &g_dev, NULL };
@@ -73,6 +93,10 @@ static peer_t g_peer[SHIM_MAX_PEER];
 static struct ibv_qp *g_qps[SHIM_MAX_QP];
 static uint32_t g_next_handle = 1;
 static int g_trace;
+static int g_shm;                            /* APUS_SHIM_TRANSPORT=shm */
+static uint64_t g_ops_memcpy, g_ops_vm;      /* RC operations carried by a memcpy / by process_vm_* (shim_transport_stats) */
+static int g_pub_fd = -1;
+static int g_mr_fd[SHIM_MAX_MR];
 
 #define TRACE(...) do { if (g_trace) { fprintf(stderr, "[shim %u] ", (unsigned)g_lid); fprintf(stderr, __VA_ARGS__); } } while (0)
 
@@ -94,6 +118,14 @@ static void shim_init(void)
     if (g_lid == 0 || g_lid >= SHIM_MAX_PEER) { fprintf(stderr, "verbs shim: bad APUS_SHIM_ID\n"); exit(1); }
     snprintf(g_dir, sizeof g_dir, "%s", (s = getenv("APUS_SHIM_DIR")) ? s : "/tmp/apus-verbs-shim");
     mkdir(g_dir, 0777);
+    if ((s = getenv("APUS_SHIM_TRANSPORT")) && !strcmp(s, "shm")) {
+        int fd = memfd_create("apus-shim-pub", MFD_CLOEXEC);
+        void *m = MAP_FAILED;
+        if (fd >= 0 && ftruncate(fd, sizeof(pub_t)) == 0) m = mmap(NULL, sizeof(pub_t), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (m == MAP_FAILED) { perror("verbs shim: shm transport unavailable, using process_vm"); if (fd >= 0) close(fd); }
+        else { g_pubp = m; g_pub_fd = fd; g_shm = 1; }
+        if ((s = getenv("APUS_SHIM_SHM_MIN"))) g_shm_min = (size_t)strtoull(s, NULL, 0);
+    }
     prctl(PR_SET_PTRACER, PR_SET_PTRACER_ANY, 0, 0, 0);           /* let the peers write into this process */
     /* UD port */
     struct sockaddr_un sa;
@@ -112,9 +144,46 @@ static void shim_init(void)
     snprintf(tmp, sizeof tmp, "%s.tmp", path);
     FILE *f = fopen(tmp, "w");
     if (!f) { perror("verbs shim: proc file"); exit(1); }
-    fprintf(f, "%d %llu\n", (int)getpid(), (unsigned long long)(uintptr_t)&g_pub);
+    fprintf(f, "%d %llu %d\n", (int)getpid(), (unsigned long long)(uintptr_t)&g_pub, g_pub_fd);
     fclose(f);
     rename(tmp, path);
+}
+
+static void *map_peer_fd(pid_t pid, int fd, size_t len)
+{
+    char path[64];
+    snprintf(path, sizeof path, "/proc/%d/fd/%d", (int)pid, fd);
+    int h = open(path, O_RDWR | O_CLOEXEC);
+    if (h < 0) return NULL;
+    void *m = mmap(NULL, len, PROT_READ | PROT_WRITE, MAP_SHARED, h, 0);
+    close(h);
+    return m == MAP_FAILED ? NULL : m;
+}
+static void peer_unmap(peer_t *p)
+{
+    if (p->pub_map) munmap(p->pub_map, sizeof(pub_t));
+    for (int i = 0; i < SHIM_MAX_SEG; i++) if (p->seg[i].map) munmap(p->seg[i].map, p->seg[i].len);
+    p->pub_map = NULL;
+    memset(p->seg, 0, sizeof p->seg);
+}
+/* the peer's mapping of a large region of `p`, or NULL (then the caller uses process_vm) */
+static uint8_t *peer_seg(peer_t *p, const pub_mr_t *m)
+{
+    if (!p->pub_map || m->shm_fd < 0 || !m->shm_len) return NULL;
+    peer_seg_t *freep = NULL;
+    for (int i = 0; i < SHIM_MAX_SEG; i++) {
+        peer_seg_t *g = &p->seg[i];
+        if (g->map && g->rkey == m->rkey) {
+            if (g->gen == m->shm_gen && g->fd == m->shm_fd && g->base == m->shm_base && g->len == m->shm_len) return g->map;
+            munmap(g->map, g->len); memset(g, 0, sizeof *g);  /* the region was registered anew */
+        }
+        if (!g->map && !freep) freep = g;
+    }
+    if (!freep) return NULL;
+    void *mm = map_peer_fd(p->pid, m->shm_fd, m->shm_len);
+    if (!mm) return NULL;
+    freep->rkey = m->rkey; freep->gen = m->shm_gen; freep->fd = m->shm_fd; freep->map = mm; freep->base = m->shm_base; freep->len = m->shm_len;
+    return mm;
 }
 
 static peer_t *peer_of(uint16_t lid, int refresh)
@@ -126,12 +195,17 @@ static peer_t *peer_of(uint16_t lid, int refresh)
     snprintf(path, sizeof path, "%s/proc.%u", g_dir, (unsigned)lid);
     FILE *f = fopen(path, "r");
     if (!f) return NULL;
-    int pid; unsigned long long a;
-    int got = fscanf(f, "%d %llu", &pid, &a);
+    int pid, pfd = -1; unsigned long long a;
+    int got = fscanf(f, "%d %llu %d", &pid, &a, &pfd);
     fclose(f);
-    if (got != 2) return NULL;
+    if (got < 2) return NULL;
+    peer_unmap(p);
     memset(p, 0, sizeof *p);
-    p->known = 1; p->pid = pid; p->pub_addr = a;
+    p->known = 1; p->pid = pid; p->pub_addr = a; p->pub_fd = got == 3 ? pfd : -1;
+    if (g_shm && p->pub_fd >= 0) {
+        void *m = map_peer_fd(pid, p->pub_fd, sizeof(pub_t));
+        if (m) p->pub_map = m;                                 /* else: this peer is reached through process_vm */
+    }
     return p;
 }
 
@@ -185,6 +259,28 @@ struct ibv_pd *ibv_alloc_pd(struct ibv_context *c) { struct ibv_pd *pd = calloc(
 int ibv_dealloc_pd(struct ibv_pd *pd) { free(pd); return 0; }
 
 /* ---- memory regions ------------------------------------------------------------------------------------------ */
+/* shm transport: put the pages of [addr, addr+length) on a memfd, at the same virtual address and with the same
+ * contents, so that peers can map them.  The page-rounded range is what moves; for the one region this applies to (the
+ * log: a malloc of 64 MiB, i.e. its own anonymous mapping) the rounding adds the chunk header and the tail slack only.
+ * On any failure the region simply stays process_vm-only. */
+static void shm_back_region(int i, void *addr, size_t length)
+{
+    static uint32_t gen;
+    uintptr_t base = (uintptr_t)addr & ~(uintptr_t)4095, end = ((uintptr_t)addr + length + 4095) & ~(uintptr_t)4095;
+    size_t sz = end - base;
+    int fd = memfd_create("apus-shim-mr", MFD_CLOEXEC);
+    if (fd < 0) return;
+    void *tmp = MAP_FAILED;
+    if (ftruncate(fd, (off_t)sz) == 0) tmp = mmap(NULL, sz, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (tmp == MAP_FAILED) { close(fd); return; }
+    memcpy(tmp, (void *)base, sz);
+    munmap(tmp, sz);
+    if (mmap((void *)base, sz, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED, fd, 0) == MAP_FAILED) { close(fd); return; }
+    g_mr_fd[i] = fd;
+    g_pub.mr[i].shm_base = base; g_pub.mr[i].shm_len = sz; g_pub.mr[i].shm_gen = ++gen; g_pub.mr[i].shm_fd = fd;
+    TRACE("region %d: %zu bytes at %p re-backed by memfd %d\n", i, sz, (void *)base, fd);
+}
+
 struct ibv_mr *ibv_reg_mr(struct ibv_pd *pd, void *addr, size_t length, int access)
 {
     for (int i = 0; i < SHIM_MAX_MR; i++) {
@@ -193,6 +289,8 @@ struct ibv_mr *ibv_reg_mr(struct ibv_pd *pd, void *addr, size_t length, int acce
         mr->context = pd->context; mr->pd = pd; mr->addr = addr; mr->length = length; mr->handle = (uint32_t)i;
         mr->lkey = mr->rkey = ((uint32_t)g_lid << 16) | (uint32_t)(i + 1);
         g_pub.mr[i].addr = (uint64_t)(uintptr_t)addr; g_pub.mr[i].len = length; g_pub.mr[i].access = (uint32_t)access;
+        g_pub.mr[i].shm_fd = -1; g_pub.mr[i].shm_base = g_pub.mr[i].shm_len = 0; g_mr_fd[i] = -1;
+        if (g_shm && length >= g_shm_min) shm_back_region(i, addr, length);
         __atomic_store_n(&g_pub.mr[i].rkey, mr->rkey, __ATOMIC_RELEASE);
         return mr;
     }
@@ -203,6 +301,8 @@ int ibv_dereg_mr(struct ibv_mr *mr)
 {
     if (!mr) return EINVAL;
     __atomic_store_n(&g_pub.mr[mr->handle].rkey, 0, __ATOMIC_RELEASE);
+    /* the pages stay memfd-backed until the owner frees them (free() of a large chunk unmaps); peers keep their own mapping */
+    if (g_mr_fd[mr->handle] >= 0) { g_pub.mr[mr->handle].shm_fd = -1; close(g_mr_fd[mr->handle]); g_mr_fd[mr->handle] = -1; }
     free(mr);
     return 0;
 }
@@ -455,6 +555,10 @@ static const pub_mr_t *remote_mr(peer_t *p, uint32_t rkey, int refresh)
     uint32_t i = (rkey & 0xFFFF) - 1;
     if (i >= SHIM_MAX_MR) return NULL;
     pub_mr_t *c = &p->mr_cache[i % 64];
+    if (p->pub_map) {                                               /* the live record: a load, never stale */
+        *c = p->pub_map->mr[i];
+        return __atomic_load_n(&p->pub_map->mr[i].rkey, __ATOMIC_ACQUIRE) == rkey && c->rkey == rkey ? c : NULL;
+    }
     if (c->rkey == rkey && !refresh) return c;
     pub_mr_t m;
     if (peer_read(p, p->pub_addr + offsetof(pub_t, mr) + (uint64_t)i * sizeof m, &m, sizeof m)) return NULL;
@@ -479,7 +583,14 @@ static int post_rc(struct ibv_qp *qp, struct ibv_send_wr *wr)
         /* the responder's queue pair must be connected back to this one and willing to receive */
         pub_qp_t rq;
         uint32_t ridx = q->attr.dest_qp_num & 0xFFF;
-        if (ridx >= SHIM_MAX_QP || peer_read(p, p->pub_addr + offsetof(pub_t, qp) + (uint64_t)ridx * sizeof rq, &rq, sizeof rq)) {
+        int unreachable = ridx >= SHIM_MAX_QP;
+        if (!unreachable && p->pub_map) {
+            rq = *(volatile pub_qp_t *)&p->pub_map->qp[ridx];
+            if ((++p->ops & 63u) == 0 && kill(p->pid, 0) && errno == ESRCH) unreachable = 1;   /* a mapping outlives its owner */
+        } else if (!unreachable) {
+            unreachable = peer_read(p, p->pub_addr + offsetof(pub_t, qp) + (uint64_t)ridx * sizeof rq, &rq, sizeof rq) != 0;
+        }
+        if (unreachable) {
             st = IBV_WC_RETRY_EXC_ERR;
         } else if (rq.qpn != q->attr.dest_qp_num || rq.type != IBV_QPT_RC || (rq.state != IBV_QPS_RTR && rq.state != IBV_QPS_RTS) ||
                    rq.dest_qpn != qp->qp_num || rq.rq_psn != q->attr.sq_psn) {
@@ -495,8 +606,18 @@ static int post_rc(struct ibv_qp *qp, struct ibv_send_wr *wr)
                 const pub_mr_t *m = remote_mr(p, wr->wr.rdma.rkey, attempt);
                 uint32_t need = wr->opcode == IBV_WR_RDMA_WRITE ? IBV_ACCESS_REMOTE_WRITE : IBV_ACCESS_REMOTE_READ;
                 if (!m || raddr < m->addr || raddr + len > m->addr + m->len || !(m->access & need)) { st = IBV_WC_REM_ACCESS_ERR; break; }
-                int rc = wr->opcode == IBV_WR_RDMA_WRITE ? peer_write(p, raddr, (void *)(uintptr_t)wr->sg_list[i].addr, len)
+                uint8_t *seg = peer_seg(p, m);
+                int rc = 0;
+                if (seg) {
+                    uint8_t *remote = seg + (raddr - m->shm_base), *local = (uint8_t *)(uintptr_t)wr->sg_list[i].addr;
+                    if (wr->opcode == IBV_WR_RDMA_WRITE) memcpy(remote, local, len); else memcpy(local, remote, len);
+                    __atomic_thread_fence(__ATOMIC_SEQ_CST);         /* placement order of consecutive work requests */
+                    g_ops_memcpy++;
+                } else {
+                    g_ops_vm++;
+                    rc = wr->opcode == IBV_WR_RDMA_WRITE ? peer_write(p, raddr, (void *)(uintptr_t)wr->sg_list[i].addr, len)
                                                          : peer_read(p, raddr, (void *)(uintptr_t)wr->sg_list[i].addr, len);
+                }
                 if (rc) st = (errno == ESRCH || errno == EPERM) ? IBV_WC_RETRY_EXC_ERR : IBV_WC_REM_ACCESS_ERR;
                 raddr += len; total += len;
             }
@@ -513,6 +634,9 @@ static int post_rc(struct ibv_qp *qp, struct ibv_send_wr *wr)
     if ((wr->send_flags & IBV_SEND_SIGNALED) || q->init.sq_sig_all) complete(qp, wr, IBV_WC_SUCCESS, total);
     return 0;
 }
+
+/* test hook (not a verbs call): how the RC operations of this process travelled so far */
+void shim_transport_stats(uint64_t out[2]) { out[0] = g_ops_memcpy; out[1] = g_ops_vm; }
 
 int ibv_post_send(struct ibv_qp *qp, struct ibv_send_wr *wr, struct ibv_send_wr **bad)
 {

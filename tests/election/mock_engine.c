@@ -102,7 +102,14 @@ int apus_ctl_adjust_follower(apus_replica_t *r, uint8_t peer, uint64_t sid, uint
     __sync_synchronize();
     return APUS_OK;
 }
-int apus_replica_set_role(apus_replica_t *r, uint8_t leader, uint64_t term) { r->blk[r->idx]->role_leader = leader; r->blk[r->idx]->role_term = term; return APUS_OK; }
+int apus_replica_set_role(apus_replica_t *r, uint8_t leader, uint64_t term)
+{
+    /* MOCK_TAKEOVER_DELAY_US: a winner that is slow to take over (descheduled, a long role change): its voters' patience
+     * runs out and they stand in a higher term before it announces itself */
+    const char *d = getenv("MOCK_TAKEOVER_DELAY_US");
+    if (d && leader == r->idx) usleep((useconds_t)atol(d));
+    r->blk[r->idx]->role_leader = leader; r->blk[r->idx]->role_term = term; return APUS_OK;
+}
 int apus_replica_disconnect(apus_replica_t *r, uint8_t peer) { r->blk[r->idx]->disconnected_mask |= 1ull << peer; return APUS_OK; }
 
 /* ---- the rest of the ABI dare_entry.c references: never reached by the election harness ---- */

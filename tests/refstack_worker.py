@@ -165,6 +165,10 @@ def main():
     time.sleep(0.2)
     o = offsets() or {}
     result["offsets"] = o
+    if hasattr(st, "shim_transport_stats"):                  # how this replica's RDMA operations travelled (verbs_shim.c)
+        ts = (C.c_uint64 * 2)()
+        st.shim_transport_stats(ts)
+        result["rdma_ops"] = {"memcpy": int(ts[0]), "process_vm": int(ts[1])}
     if o and not os.environ.get("REFSTACK_NO_IMAGE"):
         end = o["end"] if o["end"] != o["len"] else 0
         img = C.create_string_buffer(max(end, 1))

@@ -39,16 +39,18 @@ def read_blk(d, i):
                 end=tail[3], role_leader=tail[4], role_term=tail[5], launches=tail[6], adjusted_by=tail[7] - 1, disconnected=tail[8])
 
 
-def run_election(harness, n, dead, logs, absent=(), elec=(2000, 6000), timeout=60):
+def run_election(harness, n, dead, logs, absent=(), elec=(2000, 6000), timeout=60, env=None):
     """logs: {idx: (last_idx, last_term)}; returns ({idx: result dict}, dir-free block dicts)"""
     with tempfile.TemporaryDirectory() as d:
         procs = {}
+        env = dict(os.environ, **(env or {}))
         for i in range(n):
             if i == dead or i in absent:
                 continue
             li, lt = logs[i]
             procs[i] = subprocess.Popen([harness, d, str(i), str(n), str(dead), "1", str(li), str(lt), str(64 * li), str(64 * li),
-                                         str(elec[0]), str(elec[1])], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                                         str(elec[0]), str(elec[1])], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                                        env=env)
         # `up<i>` of servers that never start: the harness only waits for the ones that exist
         for i in absent:
             open(os.path.join(d, f"up{i}"), "w").close()
@@ -123,3 +125,23 @@ def test_silent_server_is_disconnected_by_the_winner(harness):
         w, term = check(res, blks, logs, 5)
         assert blks[w]["disconnected"] & (1 << 4)
         assert "REMOVE SERVER p4" in res[w]["log"]
+
+
+@pytest.mark.timeout(300)
+def test_slow_winner_is_followed_not_fought(harness):
+    """The winner needs 60 ms to take over -- longer than its voter's patience (hb_timeout 20 ms + a random election
+    timeout): the voter stands in a higher term meanwhile.  The winner no longer answers vote requests (it leads), so that
+    candidacy can never win; when it times out the voter must give way to the announced leader instead of raising its term
+    for ever (the give-way rule in elect(), case (a))."""
+    for trial in range(4):
+        logs = {1: (40, 1), 2: (40, 1)}
+        res, blks = run_election(harness, 3, 0, logs, env={"MOCK_TAKEOVER_DELAY_US": "60000"})
+        leaders = [i for i, r in res.items() if r["role"] == "leader"]
+        assert len(leaders) == 1, {i: (r["role"], r["term"]) for i, r in res.items()}
+        w = leaders[0]
+        for i, r in res.items():
+            assert r["rc"] == 0, r["log"][-600:]
+            if i != w:
+                assert r["role"] == "follower" and r["leader"] == w and r["term"] == res[w]["term"]
+                assert blks[i]["role_leader"] == w and blks[i]["adjusted_by"] == w
+                assert "Start election" in r["log"], "the scenario needs the voter to have stood meanwhile"

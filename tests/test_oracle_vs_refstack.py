@@ -46,7 +46,18 @@ def check_replay(rr, nconn, nreq, plen):
 @pytest.mark.parametrize("n,nconn,nreq,plen", [(3, 2, 300, 64), (5, 3, 200, 128), (3, 1, 120, -3000), (7, 4, 400, 64)])
 def test_reference_log_equals_oracle_log(orc, n, nconn, nreq, plen):
     """log_pruning_period is set out of reach, so the log holds exactly CONFIG + the stream."""
-    rr = R.run(n, nconn, nreq, plen, prune=1000.0)
+    _log_equals_oracle(orc, n, nconn, nreq, plen)
+
+
+@pytest.mark.parametrize("n,nconn,nreq,plen", [(5, 3, 200, 128), (3, 1, 120, -3000)])
+def test_reference_log_equals_oracle_log_shm_transport(orc, n, nconn, nreq, plen):
+    """The shim's shm transport (the log re-backed by a shared mapping, RDMA WRITE = memcpy: what bench.py's reference arm
+    also times) leaves the same logs as the process_vm transport."""
+    _log_equals_oracle(orc, n, nconn, nreq, plen, transport="shm")
+
+
+def _log_equals_oracle(orc, n, nconn, nreq, plen, transport=None):
+    rr = R.run(n, nconn, nreq, plen, prune=1000.0, transport=transport)
     c = oracle_for(orc, rr, n, nconn, nreq, plen)
     lead = rr["leader"]
     oo = c.offsets(lead)
