@@ -208,7 +208,7 @@ TRANSPORT_TEXT = {"shm": "shm transport: the log is a shared mapping, an RDMA WR
                   "process_vm": "process_vm_writev transport: one or two system calls per RDMA operation, no wire latency"}
 
 
-def refstack_leg(n, payload, nreq, steps, timeout=600, transport=None):
+def refstack_leg(n, payload, nreq, steps, timeout=150, transport=None):
     """The reference's OWN software stack -- its unmodified election / replication / commit code (src/dare/*.c) and
     proxy.c, built by oracle/build_refapp.sh into oracle/_ref/libref_stack.so -- as n replica processes on this
     box's host cores, with oracle/verbs_shim standing in for the NIC (no wire latency; transport None: one or two
@@ -226,8 +226,10 @@ def refstack_leg(n, payload, nreq, steps, timeout=600, transport=None):
     cores = host_cores()
     threads = max(1, min(REFSTACK_CONNS, cores - n))
     try:
-        rr = R.run(n, REFSTACK_CONNS, nreq, payload, threads=threads, steps=steps, images=False, timeout=timeout,
-                   transport=transport)
+        # one attempt on the shm transport (the process_vm leg follows anyway), two on process_vm: a hung or disturbed
+        # group must not stretch the arm beyond a few minutes
+        rr = R.run(n, REFSTACK_CONNS, nreq, payload, attempts=1 if transport else 2, threads=threads, steps=steps,
+                   images=False, timeout=timeout, transport=transport)
     except Exception as e:                                   # noqa: BLE001 - reported, and the caller falls back
         sys.stderr.write(f"[bench] reference stack ({transport or 'process_vm'} transport) could not run "
                          f"({type(e).__name__}: {str(e)[:300]})\n")
