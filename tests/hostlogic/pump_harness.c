@@ -12,8 +12,16 @@
  *             "committed"; `apus_submit` writes down what it was given and hands out tickets, `apus_committed_tickets`
  *             trails the submissions; store_cmd / update_state callbacks are written down.
  *
+ *   membership  a leader of three whose follower p2 stops beating: the failure detector must remove it (disconnect, CONFIG
+ *             entry without it); then a replacement process (mode `joiner`, a second process sharing the rendezvous
+ *             directory) asks to join: the leader snapshots the state machine through the proxy callbacks, maps the
+ *             joiner, sends its log, appends the CONFIG entry that puts the slot back and answers; the joiner loads the
+ *             snapshot and knows where to follow from (leader_check_followers / leader_serve_join / join_group).
+ *
  *   pump_harness follower <dir> <log_len> <n_stages> <read_cap>      reads <dir>/stage<k>.bin, <dir>/stage<k>.commit
  *   pump_harness leader   <dir> <n_threads> <n_requests_per_thread> <payload_len>
+ *   pump_harness membership <dir> <p2_dies_after_ms> 0 0
+ *   pump_harness joiner     <dir> 0 0 0
  * Output: <dir>/calls.txt.  Nothing of this is linked into the product.
  */
 #include "../../apus_b200/csrc/dare_entry.c"
@@ -107,6 +115,10 @@ int apus_submit(apus_replica_t *l, uint8_t t, uint16_t c, uint64_t q, const void
     (void)l;
     pthread_mutex_lock(&g_mu);
     *k = ++g_tickets;
+    if (t == APUS_CONFIG && m) {                              /* dare_cid_t image: size at byte 8, bitmask at bytes 12..15 */
+        uint32_t mask; memcpy(&mask, (const uint8_t *)m + 12, 4);
+        fprintf(g_calls, "CONFIG %llu size=%u mask=%u\n", (unsigned long long)*k, (unsigned)((const uint8_t *)m)[8], mask);
+    } else
     fprintf(g_calls, "T %llu %u %u %llu %u %016llx\n", (unsigned long long)*k, (unsigned)t, (unsigned)c, (unsigned long long)q,
             (unsigned)n, (unsigned long long)fnv(m ? m : (const void *)"", m ? n : 0));
     pthread_mutex_unlock(&g_mu);
@@ -163,33 +175,73 @@ static void *app_thread(void *a)
     return NULL;
 }
 
-/* ---- the rest of the ABI dare_entry.c references: not reached by the pumps ---- */
+/* ---- membership: what the failure detector and the join service ask of the engine ---- */
+static uint64_t g_t0_us, g_p2_dies_us, g_beat[APUS_MAX_SERVER_COUNT];
+static unsigned g_stops, g_launches;
+static volatile unsigned g_disconnected_mask;
+int apus_replicas_stop(apus_replica_t **rs, int n) { (void)rs; (void)n; g_stops++; return APUS_OK; }
+int apus_replicas_launch(apus_replica_t **rs, int n, uint64_t t) { (void)rs; (void)n; (void)t; g_launches++; return APUS_OK; }
+int apus_follower_beats(apus_replica_t *l, uint64_t o[APUS_MAX_SERVER_COUNT])
+{
+    (void)l;
+    g_beat[1]++;                                               /* p1 is alive */
+    if (now_us() - g_t0_us < g_p2_dies_us) g_beat[2]++;        /* p2's kernel stops polling when its process dies */
+    memcpy(o, g_beat, sizeof g_beat);
+    return APUS_OK;
+}
+int apus_replica_disconnect(apus_replica_t *r, uint8_t p)
+{
+    (void)r;
+    pthread_mutex_lock(&g_mu); fprintf(g_calls, "D %u\n", (unsigned)p); pthread_mutex_unlock(&g_mu);
+    g_disconnected_mask |= 1u << p;
+    return APUS_OK;
+}
+int apus_replica_connect(apus_replica_t *r, uint8_t p, const apus_peer_handle_t *h)
+{
+    (void)r;
+    pthread_mutex_lock(&g_mu); fprintf(g_calls, "C %u %016llx\n", (unsigned)p, (unsigned long long)fnv((const uint8_t *)h, sizeof *h)); pthread_mutex_unlock(&g_mu);
+    return APUS_OK;
+}
+int apus_ctl_last_entry(apus_replica_t *r, uint64_t *idx, uint64_t *term, uint64_t *commit, uint64_t *end)
+{
+    (void)r; *idx = 41; *term = 5; *commit = 2624; *end = 2624;
+    return APUS_OK;
+}
+int apus_ctl_adjust_follower(apus_replica_t *l, uint8_t f, uint64_t sid, uint64_t *resent)
+{
+    (void)l; *resent = 2624;
+    pthread_mutex_lock(&g_mu); fprintf(g_calls, "J %u %llu\n", (unsigned)f, (unsigned long long)sid); pthread_mutex_unlock(&g_mu);
+    return APUS_OK;
+}
+static uint32_t snap_size(void *arg) { (void)arg; return 1000; }
+static void snap_fill(void *buf, void *arg) { (void)arg; for (int i = 0; i < 1000; i++) ((uint8_t *)buf)[i] = (uint8_t)(i * 7 + 3); }
+static int snap_apply(void *buf, uint32_t n, void *arg)
+{
+    (void)arg;
+    fprintf(g_calls, "SNAP %u %016llx\n", n, (unsigned long long)fnv(buf, n));
+    return 0;
+}
+
+/* ---- the rest of the ABI dare_entry.c references: not reached here ---- */
 #define STUB(sig) sig { snprintf(g_merr, sizeof g_merr, "mock: not part of the pump harness"); return APUS_ERROR; }
 int apus_device_count(void) { return 0; }
 STUB(int apus_replica_create(const apus_config_t *c, apus_replica_t **o))
 void apus_replica_destroy(apus_replica_t *r) { (void)r; }
 STUB(int apus_replica_export(apus_replica_t *r, apus_peer_handle_t *o))
-STUB(int apus_replica_connect(apus_replica_t *r, uint8_t p, const apus_peer_handle_t *h))
-int apus_replicas_stop(apus_replica_t **rs, int n) { (void)rs; (void)n; return APUS_OK; }
-int apus_replicas_launch(apus_replica_t **rs, int n, uint64_t t) { (void)rs; (void)n; (void)t; return APUS_OK; }
-STUB(int apus_follower_beats(apus_replica_t *l, uint64_t o[APUS_MAX_SERVER_COUNT]))
 STUB(int apus_ctl_read(apus_replica_t *r, apus_ctl_view_t *o))
 STUB(int apus_ctl_set_sid(apus_replica_t *r, uint64_t s))
 STUB(int apus_ctl_reset_votes(apus_replica_t *r))
 STUB(int apus_ctl_clear_vote_request(apus_replica_t *r, uint8_t f))
 STUB(int apus_ctl_send_vote_request(apus_replica_t *r, uint8_t p, uint64_t s, uint64_t i, uint64_t t, const void *c))
 STUB(int apus_ctl_send_vote_ack(apus_replica_t *r, uint8_t c, uint64_t k))
-STUB(int apus_ctl_last_entry(apus_replica_t *r, uint64_t *a, uint64_t *b, uint64_t *c, uint64_t *d))
-STUB(int apus_ctl_adjust_follower(apus_replica_t *l, uint8_t f, uint64_t s, uint64_t *b))
 STUB(int apus_replica_set_role(apus_replica_t *r, uint8_t l, uint64_t t))
-STUB(int apus_replica_disconnect(apus_replica_t *r, uint8_t p))
 
 int main(int argc, char **argv)
 {
     if (argc < 6) return 2;
     g_dir = argv[2];
     char path[600];
-    snprintf(path, sizeof path, "%s/calls.txt", g_dir);
+    snprintf(path, sizeof path, "%s/%s", g_dir, !strcmp(argv[1], "joiner") ? "joiner_calls.txt" : "calls.txt");
     g_calls = fopen(path, "w");
     if (!g_calls) return 2;
     g_log = stdout;
@@ -203,6 +255,42 @@ int main(int argc, char **argv)
         int rc = follower_pump(g_L);
         fprintf(g_calls, "END rc=%d apply=%llu next_idx=%llu reads=%u two_piece=%u capped=%u\n", rc, (unsigned long long)g_apply,
                 (unsigned long long)g_apply_next_idx, g_reads, g_two_piece_reads, g_capped_reads);
+    } else if (!strcmp(argv[1], "membership")) {
+        g_n = 3; g_idx = 0; g_leader_idx = 0; g_live_mask = 7; g_term = 5;
+        cfg_hb_period = 0.002;                                      /* hb_timeout() = 10 periods, floored at 20 ms */
+        snprintf(g_env_rdv, sizeof g_env_rdv, "%s/rdv", g_dir);
+        mkdir(g_env_rdv, 0777);
+        g_in.get_db_size = snap_size; g_in.create_db_snapshot = snap_fill; g_in.update_state = rec_update; g_in.store_cmd = rec_store_leader;
+        g_t0_us = now_us(); g_p2_dies_us = strtoull(argv[3], NULL, 0) * 1000ull;
+        pthread_spin_init(&tailq_lock, PTHREAD_PROCESS_PRIVATE);
+        TAILQ_INIT(&tailhead);
+        pthread_t pump;
+        pthread_create(&pump, NULL, pump_thread, NULL);
+        char mark[700];
+        for (int k = 0; k < 10000 && !(g_disconnected_mask & 4u); k++) usleep(1000);
+        snprintf(mark, sizeof mark, "%s/removed", g_dir);
+        FILE *f = fopen(mark, "w"); if (f) { fprintf(f, "%llu\n", (unsigned long long)(now_us() - g_t0_us)); fclose(f); }
+        snprintf(mark, sizeof mark, "%s/join2.ack", g_env_rdv);
+        for (int k = 0; k < 20000 && access(mark, F_OK); k++) usleep(1000);
+        usleep(100000);
+        g_terminate = 1;
+        pthread_join(pump, NULL);
+        pthread_mutex_lock(&g_mu);
+        fprintf(g_calls, "END stops=%u launches=%u live_mask=%u removed_mask=%u\n", g_stops, g_launches, g_live_mask, g_removed_mask);
+        pthread_mutex_unlock(&g_mu);
+    } else if (!strcmp(argv[1], "joiner")) {
+        g_n = 3; g_idx = 2; g_leader_idx = 2; g_L = 1ull << 30;
+        snprintf(g_env_rdv, sizeof g_env_rdv, "%s/rdv", g_dir);
+        g_in.apply_db_snapshot = snap_apply;
+        char path[700];
+        apus_peer_handle_t h;
+        memset(&h, 0xA7, sizeof h);                                 /* (dare_server_init publishes the handle before join_group) */
+        snprintf(path, sizeof path, "%s/r2.handle", g_env_rdv);
+        FILE *f = fopen(path, "wb"); if (f) { fwrite(&h, sizeof h, 1, f); fclose(f); }
+        int rc = join_group();
+        fprintf(g_calls, "END rc=%d leader=%u term=%llu apply=%llu next_idx=%llu live_mask=%u handle=%016llx\n", rc, (unsigned)g_leader_idx,
+                (unsigned long long)g_term, (unsigned long long)g_apply, (unsigned long long)g_apply_next_idx, g_live_mask,
+                (unsigned long long)fnv((const uint8_t *)&h, sizeof h));
     } else {
         int nthr = atoi(argv[3]), nreq = atoi(argv[4]), plen = atoi(argv[5]);
         g_n = 1; g_idx = 0; g_leader_idx = 0; g_live_mask = 1;      /* (a group of one appends no CONFIG prologue) */

@@ -117,3 +117,40 @@ def test_leader_pump_order_callbacks(harness, tmp_path, threads, nreq, plen):
     assert len(stores) == total
     assert sorted((int(s[1]), int(s[2]), int(s[3])) for s in stores) == sorted(
         (c, t, ln) for c, seq in per.items() for t, _, ln, _ in seq)
+
+
+def test_failure_detector_removal_then_join(harness, tmp_path):
+    """leader_check_followers + leader_serve_join + join_group, two processes sharing a rendezvous directory: p2 of a
+    group of three stops beating after 60 ms; a replacement asks to join the emptied slot."""
+    import time
+    lead = subprocess.Popen([harness, "membership", str(tmp_path), "60", "0", "0"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    t0 = time.time()
+    while not (tmp_path / "removed").exists():
+        assert time.time() - t0 < 20 and lead.poll() is None, "the failure detector never removed p2"
+        time.sleep(0.005)
+    removed_after_ms = int((tmp_path / "removed").read_text()) / 1e3
+    assert 60 <= removed_after_ms < 60 + 20 + 60, removed_after_ms          # death + hb_timeout (20 ms floor) + scan period / slack
+    join = subprocess.run([harness, "joiner", str(tmp_path), "0", "0", "0"], capture_output=True, text=True, timeout=60)
+    lout = lead.communicate(timeout=60)[0]
+    assert join.returncode == 0 and lead.returncode == 0, join.stdout + join.stderr + lout
+    calls = (tmp_path / "calls.txt").read_text().split("\n")
+    # the election winner's prologue (all three), the removal of p2, the re-admission of p2 -- in this order
+    configs = [l for l in calls if l.startswith("CONFIG")]
+    assert [c.split()[2:] for c in configs] == [["size=3", "mask=7"], ["size=3", "mask=3"], ["size=3", "mask=7"]], configs
+    order = ["CONFIG" if l.startswith("CONFIG") else " ".join(l.split()[:2]) for l in calls if l.split()[:1] and l.split()[0] in ("D", "C", "J", "CONFIG")]
+    assert order == ["CONFIG", "D 2", "CONFIG", "C 2", "J 2", "CONFIG"], order
+    sid = int([l for l in calls if l.startswith("J ")][0].split()[2])
+    assert sid == (5 << 9) | (1 << 8) | 0                                    # the joiner is adjusted under [term 5 | L | p0]
+    end = [l for l in calls if l.startswith("END")][0]
+    assert "live_mask=7" in end and "removed_mask=0" in end
+    # the kernel was stopped and relaunched around each change of the peer set (removal, join)
+    assert "stops=2" in end and "launches=2" in end, end
+    assert "REMOVE SERVER p2" in lout and "JOIN request from p2" in lout and "p2 joined" in lout
+    # the joiner: the leader's answer, the snapshot through apply_db_snapshot, where to follow from
+    j = (tmp_path / "joiner_calls.txt").read_text().split("\n")
+    snap = bytes((i * 7 + 3) & 0xFF for i in range(1000))
+    assert [l for l in j if l.startswith("SNAP")] == [f"SNAP 1000 {fnv(snap):016x}"]
+    jend = [l for l in j if l.startswith("END")][0]
+    assert "rc=0 leader=0 term=5 apply=2624 next_idx=42 live_mask=7" in jend, jend
+    # the handle the leader mapped is the one the joiner published
+    assert [l for l in calls if l.startswith("C 2")][0].split()[2] == jend.split("handle=")[1]
