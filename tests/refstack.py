@@ -106,9 +106,13 @@ def _run_once(n, nconn, nreq, plen, threads=1, prune=None, timeout=120, keep=Non
     leaders = [r["idx"] for r in res if r["leader"]]
     if len(leaders) != 1:
         raise Disturbed(f"expected one leader, got {leaders}:\n" + "\n".join(l[-800:] for l in logs))
-    removed = [i for i in range(n) if "REMOVE SERVER" in logs[i]]
+    # (counted by each replica when it wrote its result: the tear-down that follows logs removals of its own)
+    removed = [i for i in range(n) if res[i].get("log_marks", {}).get("removals", 0)]
     if removed:
-        raise Disturbed(f"the reference removed a server from the group (logs of {removed}); not a quiet run")
+        raise Disturbed(f"the reference removed a server from the group while it ran (logs of {removed}); not a quiet run")
+    led = sum(r.get("log_marks", {}).get("leaderships", 1 if r["leader"] else 0) for r in res)
+    if led != 1:
+        raise Disturbed(f"{led} leaderships in one run (a leader was deposed during start-up: one CONFIG entry per term); not a quiet run")
     if keep is None:
         subprocess.run(["rm", "-rf", d])
     return dict(leader=leaders[0], term=res[leaders[0]]["offsets"]["term"], results=res, images=imgs, logs=logs)

@@ -186,6 +186,13 @@ def main():
     with lock:
         result["replay"] = {"conns": len(received), "bytes": sum(v[0] for v in received.values()),
                             "sha": sorted(v[1].hexdigest() for v in received.values())}
+    # what the reference logged UP TO HERE (tear-down follows: replicas exit at slightly different times and the last ones
+    # log the others as failed)
+    try:
+        text = open(os.path.join(wd, "dare.log"), errors="replace").read()
+    except OSError:
+        text = ""
+    result["log_marks"] = {"removals": text.count("REMOVE SERVER"), "leaderships": text.count("] LEADER")}
     with open(os.path.join(outdir, f"result{idx}.json.tmp"), "w") as f:
         json.dump(result, f)
     os.rename(os.path.join(outdir, f"result{idx}.json.tmp"), os.path.join(outdir, f"result{idx}.json"))

@@ -63,7 +63,7 @@ def _log_equals_oracle(orc, n, nconn, nreq, plen, transport=None):
     oo = c.offsets(lead)
     for i in range(n):
         ro = rr["results"][i]["offsets"]
-        assert ro["end"] == oo["end"] and ro["head"] == 0 and ro["len"] == O.LOG_SIZE
+        assert ro["end"] == oo["end"] and ro["head"] == 0 and ro["len"] == O.LOG_SIZE, (i, ro, oo, rr["term"], lead)
         assert ro["commit"] == ro["end"] == ro["apply"], ro
         if i == lead:
             assert ro["tail"] == oo["tail"]
@@ -101,11 +101,16 @@ def test_reference_pruning_matches_oracle_rules(orc):
     Rebuilding the log with the oracle's append -- the stream plus HEAD entries where the reference put them --
     must reproduce the reference's bytes."""
     n, nconn, nreq, plen = 3, 2, 6000, 64
-    rr = R.run(n, nconn, nreq, plen, prune=0.005)
-    lead = rr["leader"]
-    img = rr["images"][lead]
-    end = rr["results"][lead]["offsets"]["end"]
-    ents = O.walk_entries(img, 0, end, O.LOG_SIZE)
+    for attempt in range(3):
+        rr = R.run(n, nconn, nreq, plen, prune=0.005)
+        lead = rr["leader"]
+        img = rr["images"][lead]
+        end = rr["results"][lead]["offsets"]["end"]
+        ents = O.walk_entries(img, 0, end, O.LOG_SIZE)
+        # whether the timer finds something to prune is timing (it needs every follower's apply offset to have moved since
+        # the last HEAD entry): a run without two HEAD entries says nothing about the rules, take another one
+        if sum(1 for off, _ in ents if int(img[off + 26]) == O.HEAD) >= 2:
+            break
     bounds = {off for off, _ in ents}
     stream = iter(R.expected_stream(lead, nconn, nreq, plen))
     orc.set_rules(O.RULES_REFERENCE)
