@@ -9,6 +9,7 @@
 # plus, per replica, apus_gpu=<i> (one GPU per replica) and a shared apus_rendezvous directory (CUDA IPC handles).
 #
 #   benchmarks/run_gpu.sh --app=redis --scount=5 --ccount=16 --rcount=200000 [--dsize=128] [--kill-leader]
+#   benchmarks/run_gpu.sh --app=memcached --scount=7 --ccount=16 --rcount=100000 --dsize=1024        (BASELINE config 4)
 #   APP_CMD="memcached -p %PORT%" benchmarks/run_gpu.sh --app=custom --scount=7     (any server the interposer can wrap)
 set -u
 HERE="$(cd "$(dirname "$0")/.." && pwd)"
@@ -20,7 +21,7 @@ for arg in "$@"; do
     --app=*) APP="${arg#*=}";; --scount=*) server_count="${arg#*=}";; --ccount=*) client_count="${arg#*=}";;
     --rcount=*) request_count="${arg#*=}";; --dsize=*) dsize="${arg#*=}";; --port=*) base_port="${arg#*=}";;
     --kill-leader) kill_leader=1;;
-    *) echo "usage: $0 --app=redis|custom --scount=N --ccount=C --rcount=R [--dsize=B] [--port=P] [--kill-leader]"; exit 1;;
+    *) echo "usage: $0 --app=redis|memcached|custom --scount=N --ccount=C --rcount=R [--dsize=B] [--port=P] [--kill-leader]"; exit 1;;
   esac
 done
 ngpu=$(nvidia-smi -L 2>/dev/null | wc -l); [ "$ngpu" -lt 1 ] && { echo "no GPU visible: the engine has no CPU fallback"; exit 1; }
@@ -39,6 +40,7 @@ dare_global_config = { hb_period = ${HB_PERIOD:-0.001}; elec_timeout_low = ${ELE
                        retransmit_period = 0.02; rc_info_period = 0.01; log_pruning_period = 0.03; };
 CFG
     if [ "$APP" = redis ]; then run_dare=( "$REFBIN/redis-server" --port $((base_port + i)) --save "" --bind 127.0.0.1 )
+    elif [ "$APP" = memcached ]; then run_dare=( "$REFBIN/memcached" -u root -p $((base_port + i)) -U 0 -t 4 -l 127.0.0.1 -m 1024 )
     else run_dare=( ${APP_CMD//%PORT%/$((base_port + i))} ); fi
     pushd "$RUN/node$i" > /dev/null
     env server_type=start server_idx=$i group_size=$1 config_path="$RUN/node$i/node.cfg" \
@@ -64,7 +66,11 @@ FindLeader() {          # the latest "[T<term>] LEADER" line over all logs (run.
 }
 
 StartBenchmark() {
-  "$REFBIN/redis-benchmark" -t set -d "$dsize" -p $((base_port + leader_idx)) -n "$request_count" -c "$client_count" -r 100000 -q
+  if [ "$APP" = memcached ]; then   # config 4: set/get half and half (apps/memcached/run uses memslap; here a Python client)
+    python "$HERE/tests/memcached_group.py" $((base_port + leader_idx)) "$client_count" $((request_count / client_count / 2)) "$dsize"
+  else
+    "$REFBIN/redis-benchmark" -t set -d "$dsize" -p $((base_port + leader_idx)) -n "$request_count" -c "$client_count" -r 100000 -q
+  fi
 }
 
 trap 'StopDare; echo "logs kept in $RUN"' EXIT
