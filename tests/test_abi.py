@@ -119,3 +119,48 @@ def test_reference_interposer_links_on_engine_and_refuses_without_gpu(built, tmp
     finally:
         p.kill()
         p.wait(timeout=10)
+
+
+def test_memcached_under_engine_interposer_refuses_without_gpu(built, tmp_path):
+    """The second application of the reference (BASELINE config 4): an unmodified four-thread memcached 1.4.21 started
+    under the same interposer (linked on libapus_dare.so / libapus_gpu.so).  Without a GPU the engine refuses loudly and
+    memcached keeps serving, unreplicated -- the hooks (accept / read / close from several worker threads) stay out of
+    the way.  With a GPU the full run is tests/test_zz_gpu_memcached_dropin.py."""
+    import socket
+    import time
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    inter, server = os.path.join(ref, "interpose.so"), os.path.join(ref, "memcached")
+    if not (os.path.exists(inter) and os.path.exists(server)):
+        pytest.skip("oracle/_ref/memcached or interpose.so absent (oracle/build_memcached.sh, build_refapp.sh need /root/reference)")
+    if built.lib().apus_device_count() > 0:
+        pytest.skip("a GPU is visible: this is the no-GPU half")
+    cfg = tmp_path / "node.cfg"
+    cfg.write_text('db_name = "node_test";\nreq_log = 0;\nip_address = "127.0.0.1";\nport = 21470;\n')
+    env = dict(os.environ, server_type="start", server_idx="0", group_size="3", config_path=str(cfg),
+               dare_log_file=str(tmp_path / "dare.log"), apus_rendezvous=str(tmp_path / "rdv"), LD_PRELOAD=inter)
+    p = subprocess.Popen([server, "-u", "root", "-p", "21470", "-U", "0", "-t", "4", "-l", "127.0.0.1"], cwd=tmp_path, env=env,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    try:
+        log = ""
+        for _ in range(100):
+            time.sleep(0.1)
+            if (tmp_path / "dare.log").exists():
+                log = (tmp_path / "dare.log").read_text()
+                if "no CPU fallback" in log:
+                    break
+        assert "no CUDA device: the engine has no CPU fallback" in log, log
+        assert p.poll() is None
+        replies = []
+        for c in range(4):                            # several connections: the worker threads' read() hooks
+            s = socket.create_connection(("127.0.0.1", 21470))
+            s.settimeout(5)
+            s.sendall(b"set k%d 0 0 5\r\nhello\r\nget k%d\r\n" % (c, c))
+            buf = b""
+            while buf.count(b"\r\n") < 4:
+                buf += s.recv(4096)
+            replies.append(buf)
+            s.close()
+        assert all(r == b"STORED\r\nVALUE k%d 0 5\r\nhello\r\nEND\r\n" % c for c, r in enumerate(replies)), replies
+    finally:
+        p.kill()
+        p.wait(timeout=10)
