@@ -346,10 +346,18 @@ static void ud_pump(struct ibv_cq *cq)
     shim_qp_t *q = qp->shim;
     if (q->attr.qp_state < IBV_QPS_RTR || q->attr.qp_state == IBV_QPS_ERR) return;
     static uint8_t buf[sizeof(dgram_hdr_t) + 8192];
+    /* Polling an empty completion queue is a memory read on a real HCA; here it would be a recv() system call, and the
+     * reference polls its UD queue in every turn of its event loop (dare_server.c:1020 poll_ud) -- about half of a
+     * replica's CPU time went into EAGAIN.  After an empty poll the socket is left alone for ~15 us (UD carries the
+     * start-up handshake and join requests only; nothing on the replication path waits for it). */
+    static uint64_t quiet_since;
+    const uint64_t now = __builtin_ia32_rdtsc();
+    if (quiet_since && now - quiet_since < 40000u) return;
+    quiet_since = 0;
     for (int budget = 0; budget < 16; budget++) {
         if (q->rq_head == q->rq_tail) return;                     /* no receive posted: leave it in the socket */
         ssize_t n = recv(g_sock, buf, sizeof buf, MSG_DONTWAIT);
-        if (n < (ssize_t)sizeof(dgram_hdr_t)) return;
+        if (n < (ssize_t)sizeof(dgram_hdr_t)) { quiet_since = now | 1; return; }
         dgram_hdr_t *h = (dgram_hdr_t *)buf;
         if (h->dst_qpn != 0xFFFFFF && h->dst_qpn != qp->qp_num) continue;
         if (h->dst_qpn == 0xFFFFFF && !q->mcast) continue;
