@@ -1326,6 +1326,13 @@ static int entry_at(apus_replica *r, int peer, uint64_t cum, uint64_t *off, uint
     return APUS_OK;
 }
 
+extern "C" int apus_ctl_heartbeat(apus_replica_t *r, uint64_t *word)
+{
+    if (!r || !word) return fail("null argument");
+    DeviceGuard g(r->cfg.device);
+    return own_read(r, offsetof(apus_ctrl_t, hb), word, sizeof *word);
+}
+
 extern "C" int apus_ctl_last_entry(apus_replica_t *r, uint64_t *idx, uint64_t *term, uint64_t *commit, uint64_t *end)
 {
     if (!r || !idx || !term) return fail("null argument");

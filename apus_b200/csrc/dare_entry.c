@@ -39,6 +39,7 @@ static uint32_t g_live_mask;                /* servers of the configuration (dar
 static uint32_t g_removed_mask;             /* servers a new leader found dead: removed with a CONFIG entry */
 static uint64_t g_log_len = APUS_LOG_SIZE;
 static uint64_t g_apply, g_apply_next_idx;  /* follower apply walk: survives a change of leader */
+static unsigned g_false_positives;          /* suspicions of a leader that turned out to be alive (elect) */
 static dare_server_input_t g_in;
 
 /* dare_global_config of the libconfig file (config-dare.c:12-52; target/nodes.local.cfg) */
@@ -504,6 +505,26 @@ static int elect(void)
     apus_replicas_stop(rs, 1);                              /* exclusive access to my log (dare_ib_revoke_log_access) */
     const uint8_t dead = g_leader_idx;
     LOGT("[T%llu] leader p%u fell silent: failure detector fired\n", (unsigned long long)g_term, (unsigned)dead);
+    {   /* a false positive?  (hb_receive_cb, dare_server.c:781-796: a beat that arrives after the leader was declared failed
+         * only lengthens the timeout.)  The leader's kernel writes its beat into my region whether or not my kernel runs;
+         * its own kernel pauses for milliseconds around a change of the peer set (removal, join).  If the word moves
+         * within a few periods, and is of the term I follow, the leader is alive: keep following. */
+        uint64_t hb0 = 0, hb1 = 0;
+        const uint64_t period_us = (uint64_t)(cfg_hb_period * 1e6);
+        if (apus_ctl_heartbeat(g_rep, &hb0) == APUS_OK) {
+            for (int k = 0; k < 4 && !g_terminate; k++) {
+                usleep((useconds_t)(period_us < 500 ? 500 : period_us));
+                if (apus_ctl_heartbeat(g_rep, &hb1) != APUS_OK) break;
+                if (hb1 != hb0 && (hb1 >> 48) == (g_term & 0xffffull)) {
+                    g_false_positives++;
+                    LOGT("false positive => p%u is alive (beat %llu -> %llu): keep following, %u so far\n", (unsigned)dead,
+                         (unsigned long long)(hb0 & 0xffffffffffffull), (unsigned long long)(hb1 & 0xffffffffffffull), g_false_positives);
+                    if (launch_self() != APUS_OK) { LOGT("launch: %s\n", apus_last_error()); return 1; }
+                    return 0;
+                }
+            }
+        }
+    }
     apus_ctl_view_t v;
     if (apus_ctl_read(g_rep, &v) != APUS_OK) { LOGT("%s\n", apus_last_error()); return 1; }
     uint64_t sid = v.sid;

@@ -61,7 +61,7 @@ EXPORTS = [
     "apus_log_read_range", "apus_leader_suspect", "apus_last_commit_ns",
     "apus_ctl_read", "apus_ctl_set_sid", "apus_ctl_reset_votes", "apus_ctl_clear_vote_request", "apus_ctl_send_vote_request",
     "apus_ctl_send_vote_ack", "apus_ctl_last_entry", "apus_ctl_adjust_follower", "apus_replica_set_role",
-    "apus_replica_disconnect", "apus_follower_beats", "apus_device_numa_node", "apus_group_multicast",
+    "apus_replica_disconnect", "apus_follower_beats", "apus_device_numa_node", "apus_group_multicast", "apus_ctl_heartbeat",
 ]
 
 

@@ -251,6 +251,11 @@ int  apus_ctl_clear_vote_request(apus_replica_t *r, uint8_t from_idx);
 int  apus_ctl_send_vote_request(apus_replica_t *r, uint8_t peer_idx, uint64_t sid, uint64_t index, uint64_t term,
                                 const void *cid16);
 int  apus_ctl_send_vote_ack(apus_replica_t *r, uint8_t candidate_idx, uint64_t commit);
+/* follower: the heartbeat word the leader's kernel last wrote into this replica's region (term << 48 | beat counter;
+ * dare_ibv_rc.c:868-958 writes the leader's SID into ctrl_data.hb[]).  The leader writes it whether or not this replica's
+ * kernel runs, so a host that has stopped its kernel on a suspicion can tell a dead leader (the word stands still) from a
+ * false positive (it moves) -- the reference's "false possitive => increase recomputed timeout", dare_server.c:781-796. */
+int  apus_ctl_heartbeat(apus_replica_t *r, uint64_t *word);
 /* idx and term of the last entry this replica holds (0,0 when the log is empty), its commit and end offsets; the
  * replica's kernel must be stopped (exclusive access, as dare_ib_revoke_log_access gives the reference) */
 int  apus_ctl_last_entry(apus_replica_t *r, uint64_t *idx, uint64_t *term, uint64_t *commit, uint64_t *end);

@@ -111,6 +111,15 @@ int apus_replica_set_role(apus_replica_t *r, uint8_t leader, uint64_t term)
     r->blk[r->idx]->role_leader = leader; r->blk[r->idx]->role_term = term; return APUS_OK;
 }
 int apus_replica_disconnect(apus_replica_t *r, uint8_t peer) { r->blk[r->idx]->disconnected_mask |= 1ull << peer; return APUS_OK; }
+/* MOCK_LEADER_ALIVE=<term>: the "dead" leader still beats (a false positive of the failure detector) */
+int apus_ctl_heartbeat(apus_replica_t *r, uint64_t *word)
+{
+    static uint64_t beat;
+    const char *t = getenv("MOCK_LEADER_ALIVE");
+    (void)r;
+    *word = t ? ((uint64_t)atol(t) << 48) | ++beat : 77;
+    return APUS_OK;
+}
 
 /* ---- the rest of the ABI dare_entry.c references: never reached by the election harness ---- */
 #define STUB(sig) sig { snprintf(g_err, sizeof g_err, "mock: not part of the election harness"); return APUS_ERROR; }

@@ -235,6 +235,7 @@ STUB(int apus_ctl_clear_vote_request(apus_replica_t *r, uint8_t f))
 STUB(int apus_ctl_send_vote_request(apus_replica_t *r, uint8_t p, uint64_t s, uint64_t i, uint64_t t, const void *c))
 STUB(int apus_ctl_send_vote_ack(apus_replica_t *r, uint8_t c, uint64_t k))
 STUB(int apus_replica_set_role(apus_replica_t *r, uint8_t l, uint64_t t))
+STUB(int apus_ctl_heartbeat(apus_replica_t *r, uint64_t *w))
 
 int main(int argc, char **argv)
 {

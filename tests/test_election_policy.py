@@ -145,3 +145,19 @@ def test_slow_winner_is_followed_not_fought(harness):
                 assert r["role"] == "follower" and r["leader"] == w and r["term"] == res[w]["term"]
                 assert blks[i]["role_leader"] == w and blks[i]["adjusted_by"] == w
                 assert "Start election" in r["log"], "the scenario needs the voter to have stood meanwhile"
+
+
+def test_false_positive_keeps_following(harness):
+    """The failure detector fired but the leader's beat still moves (its kernel paused around a change of the peer set, or
+    this replica's context was not scheduled): no election, no term bump -- the replica relaunches its kernel and keeps
+    following (the reference's "false possitive" branch, dare_server.c:781-796)."""
+    logs = {1: (40, 1), 2: (40, 1)}
+    res, blks = run_election(harness, 3, 0, logs, env={"MOCK_LEADER_ALIVE": "1"})
+    for i, r in res.items():
+        assert (r["rc"], r["role"], r["leader"], r["term"]) == (0, "follower", 0, 1), r["log"][-400:]
+        assert "false positive => p0 is alive" in r["log"] and "Start election" not in r["log"]
+        assert blks[i]["launches"] == 1 and blks[i]["sid"] == (1 << 9) | (1 << 8) | 0     # kernel relaunched, SID untouched
+    # a beat of ANOTHER term is not the leader I follow: the election goes ahead
+    res, blks = run_election(harness, 3, 0, logs, env={"MOCK_LEADER_ALIVE": "7"})
+    w, term = check(res, blks, logs, 3)
+    assert term >= 2
