@@ -572,7 +572,10 @@ static int elect(void)
             if (votes >= (unsigned)g_n / 2 + 1) {
                 /* won.  Give the remaining live servers a moment to answer as well: whoever has not voted by then is
                  * treated as failed (check_failure_count, dare_server.c:1189-1228) */
-                const uint64_t grace = now_us() + (cfg_elec_low > 5000 ? cfg_elec_low : 5000);
+                uint64_t wait_us = (g_env_hbto_us > 0 ? (uint64_t)g_env_hbto_us : (uint64_t)(10.0 * cfg_hb_period * 1e6)) / 2;
+                if (wait_us < cfg_elec_low) wait_us = cfg_elec_low;      /* survivors notice the silence within one hb_timeout of */
+                if (wait_us < 5000) wait_us = 5000;                      /* each other; half of it is what their patience leaves me */
+                const uint64_t grace = now_us() + wait_us;
                 while (now_us() < grace && votes < g_n - 1u) {
                     if (apus_ctl_read(g_rep, &v) != APUS_OK) break;
                     votes = 1; voters = 0;
