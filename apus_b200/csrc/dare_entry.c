@@ -447,19 +447,42 @@ static int follower_pump(uint64_t L)
  *      interposer links libconfig for proxy.c; the engine only needs `key = number;` inside that one group ---- */
 static void read_dare_config(const char *path)
 {
+    /* libconfig syntax as far as this group needs it: `name = value;` or `name : value;` settings in any layout (several on
+     * one line -- benchmarks/run_gpu.sh writes them so --, one per line like target/nodes.local.cfg), comments `#`, `//`
+     * and C style, integers with an optional L suffix; only settings inside `dare_global_config = { ... }` count */
     FILE *f = path && path[0] ? fopen(path, "r") : NULL;
     if (!f) return;
-    char line[512];
-    while (fgets(line, sizeof line, f)) {
-        char *hash = strchr(line, '#');
-        if (hash) *hash = 0;
-        char key[64]; double v;
-        if (sscanf(line, " %63[a-z_] = %lf", key, &v) != 2) continue;
-        if (!strcmp(key, "hb_period")) cfg_hb_period = v;
-        else if (!strcmp(key, "elec_timeout_low")) cfg_elec_low = (uint64_t)v;
-        else if (!strcmp(key, "elec_timeout_high")) cfg_elec_high = (uint64_t)v;
-    }
+    char *txt = (char *)malloc(65536);
+    size_t n = txt ? fread(txt, 1, 65535, f) : 0;
     fclose(f);
+    if (!txt) return;
+    txt[n] = 0;
+    for (char *p = txt; *p; p++) {                               /* blank the comments out */
+        if (*p == '"') { for (p++; *p && *p != '"'; p++) if (*p == '\\' && p[1]) p++; if (!*p) break; continue; }
+        if (*p == '#' || (*p == '/' && p[1] == '/')) { while (*p && *p != '\n') *p++ = ' '; if (!*p) break; continue; }
+        if (*p == '/' && p[1] == '*') { while (*p && !(*p == '*' && p[1] == '/')) *p++ = ' '; if (!*p) break; *p++ = ' '; *p = ' '; }
+    }
+    char *g = strstr(txt, "dare_global_config");
+    char *open = g ? strchr(g, '{') : NULL, *close = open ? strchr(open, '}') : NULL;
+    if (open && close) {
+        *close = 0;
+        for (char *p = open + 1; *p; ) {
+            while (*p && !((*p >= 'a' && *p <= 'z') || *p == '_')) p++;
+            char key[64]; size_t k = 0;
+            while ((*p >= 'a' && *p <= 'z') || (*p >= '0' && *p <= '9') || *p == '_') { if (k < sizeof key - 1) key[k++] = *p; p++; }
+            key[k] = 0;
+            while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r') p++;
+            if (*p != '=' && *p != ':') continue;
+            char *end = NULL;
+            const double v = strtod(p + 1, &end);
+            if (end == p + 1) { p++; continue; }
+            p = end;
+            if (!strcmp(key, "hb_period")) cfg_hb_period = v;
+            else if (!strcmp(key, "elec_timeout_low")) cfg_elec_low = (uint64_t)v;
+            else if (!strcmp(key, "elec_timeout_high")) cfg_elec_high = (uint64_t)v;
+        }
+    }
+    free(txt);
 }
 
 static uint64_t now_us(void)

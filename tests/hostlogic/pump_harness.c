@@ -22,6 +22,7 @@
  *   pump_harness leader   <dir> <n_threads> <n_requests_per_thread> <payload_len>
  *   pump_harness membership <dir> <p2_dies_after_ms> 0 0
  *   pump_harness joiner     <dir> 0 0 0
+ *   pump_harness config     <dir> <libconfig file> 0 0        prints what read_dare_config took from the file
  * Output: <dir>/calls.txt.  Nothing of this is linked into the product.
  */
 #include "../../apus_b200/csrc/dare_entry.c"
@@ -248,7 +249,11 @@ int main(int argc, char **argv)
     g_log = stdout;
     g_rep = &g_mock;
     g_tk_type = calloc(TK_RING, 1);
-    if (!strcmp(argv[1], "follower")) {
+    if (!strcmp(argv[1], "config")) {
+        read_dare_config(argv[3]);
+        printf("hb_period=%g elec_timeout_low=%llu elec_timeout_high=%llu\n", cfg_hb_period, (unsigned long long)cfg_elec_low,
+               (unsigned long long)cfg_elec_high);
+    } else if (!strcmp(argv[1], "follower")) {
         g_L = strtoull(argv[3], NULL, 0); g_nstages = atoi(argv[4]); g_read_cap = strtoull(argv[5], NULL, 0);
         g_ring = malloc(g_L);
         g_log_len = g_L; g_n = 3; g_idx = 1; g_leader_idx = 0;

@@ -155,3 +155,28 @@ def test_failure_detector_removal_then_join(harness, tmp_path):
     assert "rc=0 leader=0 term=5 apply=2624 next_idx=42 live_mask=7" in jend, jend
     # the handle the leader mapped is the one the joiner published
     assert [l for l in calls if l.startswith("C 2")][0].split()[2] == jend.split("handle=")[1]
+
+
+@pytest.mark.parametrize("text,want", [
+    # target/nodes.local.cfg: one setting per line, commented-out alternatives above them
+    ('db_name = "node_test";\nport = 8888;\ndare_global_config = {\n    #hb_period = 0.001;\n    #elec_timeout_low = 10000;\n'
+     '    hb_period = 0.01;\n    elec_timeout_low = 100000;\n    elec_timeout_high = 300000;\n    rc_info_period = 0.05;\n};\n',
+     (0.01, 100000, 300000)),
+    # benchmarks/run_gpu.sh: several settings on one line, the group spread over two
+    ('port = 8890;\ndare_global_config = { hb_period = 0.001; elec_timeout_low = 10000; elec_timeout_high = 30000;\n'
+     '                       retransmit_period = 0.02; rc_info_period = 0.01; log_pruning_period = 0.03; };\n', (0.001, 10000, 30000)),
+    # libconfig accepts ':' and an L suffix; comments of all three kinds; a setting of the same name OUTSIDE the group does not count
+    ('hb_period = 7.0; // not ours\ndare_global_config : { /* hb_period = 9; */ hb_period : 0.002; elec_timeout_low = 2000L;\n'
+     '  elec_timeout_high=6000L; # done\n};\n', (0.002, 2000, 6000)),
+    # no group: the defaults of config-dare.c stay
+    ('db_name = "x";\nport = 1;\n', (0.01, 100000, 300000)),
+])
+def test_dare_global_config_is_read_like_libconfig(harness, tmp_path, text, want):
+    """read_dare_config (the three values of config-dare.c:12-52 this engine uses) must accept what libconfig accepts, not
+    only the layout of target/nodes.local.cfg -- benchmarks/run_gpu.sh writes several settings per line."""
+    cfg = tmp_path / "node.cfg"
+    cfg.write_text(text)
+    out = subprocess.run([harness, "config", str(tmp_path), str(cfg), "0", "0"], capture_output=True, text=True, timeout=30)
+    assert out.returncode == 0, out.stdout + out.stderr
+    hb, lo, hi = want
+    assert f"hb_period={hb:g} elec_timeout_low={lo} elec_timeout_high={hi}" in out.stdout, out.stdout
