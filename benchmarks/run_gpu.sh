@@ -27,6 +27,12 @@ done
 ngpu=$(nvidia-smi -L 2>/dev/null | wc -l); [ "$ngpu" -lt 1 ] && { echo "no GPU visible: the engine has no CPU fallback"; exit 1; }
 RUN="$(mktemp -d /tmp/apus-run-XXXXXX)"
 declare -a pids
+if [ "$server_count" -gt "$ngpu" ]; then
+  # fewer GPUs than replicas: the processes' contexts are time-sliced (milliseconds per turn), a heartbeat timeout sized for
+  # resident kernels would fire spuriously -- functional run only, the latencies mean nothing (tools/failover_drill.py does the same)
+  export apus_hb_period_us=${apus_hb_period_us:-2000} apus_hb_timeout_us=${apus_hb_timeout_us:-400000} apus_elec_timeout_us=${apus_elec_timeout_us:-100000,300000}
+  echo "note: $server_count replicas on $ngpu GPU(s): time-sliced contexts, relaxed failure-detector timeouts"
+fi
 
 StartDare() {
   for ((i=0; i<$1; ++i)); do
