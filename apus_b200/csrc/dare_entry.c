@@ -535,7 +535,7 @@ static int elect(void)
         uint64_t hb0 = 0, hb1 = 0;
         const uint64_t period_us = (uint64_t)(cfg_hb_period * 1e6);
         if (apus_ctl_heartbeat(g_rep, &hb0) == APUS_OK) {
-            for (int k = 0; k < 4 && !g_terminate; k++) {
+            for (int k = 0; k < 2 && !g_terminate; k++) {               /* a live leader beats every period: two are enough */
                 usleep((useconds_t)(period_us < 500 ? 500 : period_us));
                 if (apus_ctl_heartbeat(g_rep, &hb1) != APUS_OK) break;
                 if (hb1 != hb0 && (hb1 >> 48) == (g_term & 0xffffull)) {
