@@ -16,4 +16,12 @@ def test_memcached_replicated_through_reference_stack():
     for f in (MG.MEMCACHED, RG.INTERPOSE_REF):
         if not os.path.exists(f):
             pytest.skip(f"{f} absent (built only where /root/reference exists: oracle/build_memcached.sh, build_refapp.sh)")
-    print(MG.run_memcached_group(3, 0, nconn=16, nkeys=60, vlen=1024, stack="refstack", base_port=21360, startup_timeout=60))
+    for attempt in range(2):                       # (the reference's start-up election may remove a slow replica: one more try)
+        try:
+            print(MG.run_memcached_group(3, 0, nconn=16, nkeys=60, vlen=1024, stack="refstack", base_port=21360 + 10 * attempt,
+                                         startup_timeout=60))
+            break
+        except AssertionError as e:
+            if attempt:
+                raise
+            print(f"first attempt failed on the reference stack ({str(e)[:200]}); trying once more")

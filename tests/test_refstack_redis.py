@@ -17,4 +17,13 @@ def test_redis_replicated_through_reference_stack(n):
     for f in (RG.SERVER, RG.BENCH, RG.CLI, RG.INTERPOSE_REF):
         if not os.path.exists(f):
             pytest.skip(f"{f} absent (built only where /root/reference exists: oracle/build_refapp.sh)")
-    print(RG.run_redis_group(n, 0, 3000, 300, stack="refstack", base_port=18860, startup_timeout=60))
+    # the reference's own start-up election now and then removes a replica that was slow to answer (check_failure_count);
+    # that says nothing about the scenario: one more try then
+    for attempt in range(2):
+        try:
+            print(RG.run_redis_group(n, 0, 3000, 300, stack="refstack", base_port=18860 + 10 * attempt, startup_timeout=60))
+            break
+        except AssertionError as e:
+            if attempt:
+                raise
+            print(f"first attempt failed on the reference stack ({str(e)[:200]}); trying once more")
