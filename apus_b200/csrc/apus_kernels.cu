@@ -34,6 +34,7 @@
 #include <stdint.h>
 
 #include "apus_layout.h"
+#include "apus_cert.h"
 
 // ---------------------------------------------------------------------------------
 // memory-model helpers (system scope: peers and the host observe these)
@@ -245,34 +246,13 @@ __device__ __forceinline__ void st_release_gpu(volatile void *p, uint64_t v)
 }
 
 // ---------------------------------------------------------------------------------
-// Self-certifying publishes.  A lone request is pushed to the followers WITHOUT a writer-side
-// fence (a system fence costs 1.5-1.7 us here, more than the NVLink hop it orders): the publish
-// record carries a checksum of the entry bytes, the follower re-reads the bytes from its own HBM
-// until they add up (FaRM-style object validation).  The checksum is LINEAR over 8-byte words with
-// position-dependent odd weights, so "the bytes that were there before" only pass if they are the
-// bytes that were sent -- in which case accepting them is harmless.
+// Self-certifying publishes: the checksum (cs_weight / cs_mask / cs_chunk_words / cs_key) lives in apus_cert.h, which
+// the CPU property test compiles too.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t cs_weight(uint64_t word_index)
-{
-    uint64_t z = word_index * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z ^= z >> 27;
-    return z | 1ull;
-}
-// bytes of the 8-byte word at log offset o that lie inside [a, b)
-__device__ __forceinline__ uint64_t cs_mask(uint64_t o, uint64_t a, uint64_t b)
-{
-    const uint64_t lo = a > o ? a - o : 0, hi = b < o + 8 ? (b > o ? b - o : 0) : 8;
-    if (hi <= lo) return 0;
-    const uint64_t mh = hi >= 8 ? ~0ull : ((1ull << (8 * hi)) - 1ull);
-    const uint64_t ml = (1ull << (8 * lo)) - 1ull;          // lo < 8 here
-    return mh & ~ml;
-}
 // contribution of the 16 B chunk at log offset lo (16 B aligned), restricted to the bytes inside [a, b)
 __device__ __forceinline__ uint64_t cs_chunk(const uint4 v, uint64_t lo, uint64_t a, uint64_t b)
 {
-    const uint64_t w0 = (uint64_t)v.x | ((uint64_t)v.y << 32), w1 = (uint64_t)v.z | ((uint64_t)v.w << 32);
-    return (w0 & cs_mask(lo, a, b)) * cs_weight(lo >> 3) + (w1 & cs_mask(lo + 8, a, b)) * cs_weight((lo >> 3) + 1);
+    return cs_chunk_words((uint64_t)v.x | ((uint64_t)v.y << 32), (uint64_t)v.z | ((uint64_t)v.w << 32), lo, a, b);
 }
 // first n bytes of a 16 B chunk from `nw`, the rest from `old`
 __device__ __forceinline__ uint4 chunk_select(const uint4 nw, const uint4 old, int n)
@@ -287,8 +267,6 @@ __device__ __forceinline__ uint4 chunk_select(const uint4 nw, const uint4 old, i
     return make_uint4(r[0], r[1], r[2], r[3]);
 }
 
-// the key that ties a certificate to ITS publish (a certificate half from an older publish must not verify)
-__device__ __forceinline__ uint64_t cs_key(uint64_t cum_term) { return cs_weight(cum_term ^ 0x5851F42D4C957F2Dull); }
 
 // ---------------------------------------------------------------------------------
 // LEADER
